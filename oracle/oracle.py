@@ -1,0 +1,115 @@
+"""TEST INFRASTRUCTURE -- ctypes binding of oracle/librbd_oracle.so (CPU restatement of the reference path).
+
+Arrays are numpy, structure-of-arrays ``[rows, B]`` C-contiguous (batch index fastest), float32 or float64.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "librbd_oracle.so")
+
+
+def build_oracle(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("rbd_oracle.cpp", "rbd_oracle.hpp")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "librbd_oracle.so"])
+    return _LIB
+
+
+def _load():
+    lib = ctypes.CDLL(build_oracle())
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    lib.rbdo_model_create.restype = vp
+    lib.rbdo_model_create.argtypes = [i32, vp, vp, vp, vp, vp, vp]
+    lib.rbdo_model_destroy.argtypes = [vp]
+    lib.rbdo_nq.argtypes = [vp]
+    lib.rbdo_nv.argtypes = [vp]
+    lib.rbdo_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32, i32]
+    lib.rbdo_inverse_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32]
+    lib.rbdo_mass_matrix.argtypes = [vp, i32, i64, vp, vp, i32]
+    return lib
+
+
+_lib = None
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Oracle:
+    """CPU oracle bound to one flattened model (a ``ModelDesc`` from ``Mechanism.flatten()``)."""
+
+    def __init__(self, desc):
+        global _lib
+        if _lib is None:
+            _lib = _load()
+        self.desc = desc
+        parent = np.ascontiguousarray(desc.parent, np.int32)
+        jtype = np.ascontiguousarray(desc.jtype, np.int32)
+        X = np.ascontiguousarray(desc.X_tree, np.float64)
+        jp = np.ascontiguousarray(desc.jparam, np.float64)
+        inr = np.ascontiguousarray(desc.inertia, np.float64)
+        g = np.ascontiguousarray(desc.gravity, np.float64)
+        self._h = _lib.rbdo_model_create(desc.nb, _ptr(parent), _ptr(jtype), _ptr(X), _ptr(jp), _ptr(inr), _ptr(g))
+        self.nq, self.nv, self.nb = desc.nq, desc.nv, desc.nb
+        assert _lib.rbdo_nq(self._h) == self.nq and _lib.rbdo_nv(self._h) == self.nv
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.rbdo_model_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def _prep(a, rows, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dt)
+        if a.ndim == 1:
+            a = a.reshape(rows, 1)
+        assert a.shape[0] == rows, (a.shape, rows)
+        return a
+
+    @staticmethod
+    def _code(dt):
+        return 0 if np.dtype(dt) == np.float32 else 1
+
+    def dynamics(self, q, v, tau=None, wext=None, *, algo="reference", want_qd=False, nthreads=1, dtype=None):
+        """algo='reference': RNEA bias + CRBA + Cholesky (the reference's dynamics!); algo='aba': world-frame ABA."""
+        dt = np.dtype(dtype or np.asarray(q).dtype)
+        q = self._prep(q, self.nq, dt); v = self._prep(v, self.nv, dt)
+        tau = self._prep(tau, self.nv, dt); wext = self._prep(wext, self.nb * 6, dt)
+        B = q.shape[1]
+        vd = np.empty((self.nv, B), dt)
+        qd = np.empty((self.nq, B), dt) if want_qd else None
+        rc = _lib.rbdo_dynamics(self._h, self._code(dt), B, _ptr(q), _ptr(v), _ptr(tau), _ptr(wext), _ptr(vd), _ptr(qd),
+                                0 if algo == "reference" else 1, nthreads)
+        if rc != 0:
+            raise np.linalg.LinAlgError("mass matrix not positive definite")
+        return (vd, qd) if want_qd else vd
+
+    def inverse_dynamics(self, q, v, vd, wext=None, *, nthreads=1, dtype=None):
+        dt = np.dtype(dtype or np.asarray(q).dtype)
+        q = self._prep(q, self.nq, dt); v = self._prep(v, self.nv, dt)
+        vd = self._prep(vd, self.nv, dt); wext = self._prep(wext, self.nb * 6, dt)
+        B = q.shape[1]
+        tau = np.empty((self.nv, B), dt)
+        _lib.rbdo_inverse_dynamics(self._h, self._code(dt), B, _ptr(q), _ptr(v), _ptr(vd), _ptr(wext), _ptr(tau), nthreads)
+        return tau
+
+    def dynamics_bias(self, q, v, wext=None, *, nthreads=1, dtype=None):
+        return self.inverse_dynamics(q, v, None, wext, nthreads=nthreads, dtype=dtype)
+
+    def mass_matrix(self, q, *, nthreads=1, dtype=None):
+        """Returns [nv*nv, B]; entry (i, j) of sample b at row i + j*nv (column-major like M.data), both triangles filled."""
+        dt = np.dtype(dtype or np.asarray(q).dtype)
+        q = self._prep(q, self.nq, dt)
+        B = q.shape[1]
+        M = np.empty((self.nv * self.nv, B), dt)
+        _lib.rbdo_mass_matrix(self._h, self._code(dt), B, _ptr(q), _ptr(M), nthreads)
+        return M

@@ -1,0 +1,148 @@
+// TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  See rbd_oracle.hpp for scope, citations and parity pinning.
+//
+// C entry points over the templated restatement so that tests (ctypes) and bench.py's CPU-baseline leg
+// can run it on the same structure-of-arrays batches the GPU library takes: every array is [rows][B] with
+// the batch index fastest (element (k, b) at x[k*B + b]).
+#include "rbd_oracle.hpp"
+
+#include <algorithm>
+#include <thread>
+
+using namespace rbdo;
+
+namespace {
+
+template <class F> void parallel_for(int64_t B, int nthreads, F f) {
+  if (nthreads <= 1 || B < 2) { f(0, B, 0); return; }
+  nthreads = (int)std::min<int64_t>(nthreads, B);
+  std::vector<std::thread> th;
+  int64_t chunk = (B + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    int64_t lo = t * chunk, hi = std::min<int64_t>(B, lo + chunk);
+    if (lo >= hi) break;
+    th.emplace_back([=] { f(lo, hi, t); });
+  }
+  for (auto& x : th) x.join();
+}
+
+template <class T> inline void gather(const T* src, int64_t B, int64_t b, int n, T* dst) {
+  for (int k = 0; k < n; ++k) dst[k] = src[(int64_t)k * B + b];
+}
+template <class T> inline void scatter(T* dst, int64_t B, int64_t b, int n, const T* src) {
+  for (int k = 0; k < n; ++k) dst[(int64_t)k * B + b] = src[k];
+}
+
+template <class T>
+int dynamics_t(const Model& m, int64_t B, const T* q, const T* v, const T* tau, const T* wext, T* vd, T* qd,
+               int algo, int nthreads) {
+  std::vector<int> status(std::max(1, nthreads), 0);
+  parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int tid) {
+    Workspace<T> w(m);
+    std::vector<T> ql(m.nq), vl(m.nv), tl(m.nv), wl((size_t)m.nb * 6), vdl(m.nv), qdl(m.nq);
+    for (int64_t b = lo; b < hi; ++b) {
+      gather(q, B, b, m.nq, ql.data());
+      gather(v, B, b, m.nv, vl.data());
+      if (tau) gather(tau, B, b, m.nv, tl.data());
+      if (wext) gather(wext, B, b, m.nb * 6, wl.data());
+      bool ok;
+      if (algo == 0) {
+        ok = dynamics(w, ql.data(), vl.data(), tau ? tl.data() : nullptr, wext ? wl.data() : nullptr, vdl.data(),
+                      qd ? qdl.data() : nullptr);
+      } else {
+        ok = aba(w, ql.data(), vl.data(), tau ? tl.data() : nullptr, wext ? wl.data() : nullptr, vdl.data());
+        if (qd) configuration_derivative(m, ql.data(), vl.data(), qdl.data());
+      }
+      if (!ok) status[tid] = 1;
+      scatter(vd, B, b, m.nv, vdl.data());
+      if (qd) scatter(qd, B, b, m.nq, qdl.data());
+    }
+  });
+  for (int s : status) if (s) return 1;
+  return 0;
+}
+
+template <class T>
+int inverse_dynamics_t(const Model& m, int64_t B, const T* q, const T* v, const T* vd, const T* wext, T* tau, int nthreads) {
+  parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
+    Workspace<T> w(m);
+    std::vector<T> ql(m.nq), vl(m.nv), vdl(m.nv), wl((size_t)m.nb * 6), tl(m.nv);
+    for (int64_t b = lo; b < hi; ++b) {
+      gather(q, B, b, m.nq, ql.data());
+      gather(v, B, b, m.nv, vl.data());
+      if (vd) gather(vd, B, b, m.nv, vdl.data());
+      if (wext) gather(wext, B, b, m.nb * 6, wl.data());
+      if (vd) inverse_dynamics(w, ql.data(), vl.data(), vdl.data(), wext ? wl.data() : nullptr, tl.data());
+      else dynamics_bias(w, ql.data(), vl.data(), wext ? wl.data() : nullptr, tl.data());
+      scatter(tau, B, b, m.nv, tl.data());
+    }
+  });
+  return 0;
+}
+
+template <class T> int mass_matrix_t(const Model& m, int64_t B, const T* q, T* M, int nthreads) {
+  parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
+    Workspace<T> w(m);
+    std::vector<T> ql(m.nq), Ml((size_t)m.nv * m.nv);
+    for (int64_t b = lo; b < hi; ++b) {
+      gather(q, B, b, m.nq, ql.data());
+      update_transforms(w, ql.data());
+      update_motion_subspaces(w);
+      update_spatial_inertias(w);
+      update_crb_inertias(w);
+      mass_matrix(w, Ml.data());
+      scatter(M, B, b, m.nv * m.nv, Ml.data());
+    }
+  });
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* rbdo_model_create(int nb, const int* parent, const int* jtype, const double* X_tree, const double* jparam,
+                        const double* inertia, const double* gravity) {
+  Model* m = new Model();
+  m->nb = nb;
+  m->parent.assign(parent, parent + nb);
+  m->jtype.assign(jtype, jtype + nb);
+  m->qstart.resize(nb);
+  m->vstart.resize(nb);
+  int nq = 0, nv = 0;
+  for (int i = 0; i < nb; ++i) {
+    m->qstart[i] = nq; m->vstart[i] = nv;
+    nq += joint_nq(jtype[i]); nv += joint_nv(jtype[i]);
+  }
+  m->nq = nq; m->nv = nv;
+  m->X_tree.assign(X_tree, X_tree + 12 * (size_t)nb);
+  m->jparam.assign(jparam, jparam + 9 * (size_t)nb);
+  m->inertia.assign(inertia, inertia + 13 * (size_t)nb);
+  for (int k = 0; k < 3; ++k) m->gravity[k] = gravity[k];
+  m->finalize();
+  return m;
+}
+void rbdo_model_destroy(void* m) { delete static_cast<Model*>(m); }
+int rbdo_nq(void* m) { return static_cast<Model*>(m)->nq; }
+int rbdo_nv(void* m) { return static_cast<Model*>(m)->nv; }
+
+// dtype: 0 = float32, 1 = float64.  algo: 0 = reference path (RNEA bias + CRBA + Cholesky), 1 = world-frame ABA.
+int rbdo_dynamics(void* mp, int dtype, int64_t B, const void* q, const void* v, const void* tau, const void* wext,
+                  void* vd, void* qd, int algo, int nthreads) {
+  const Model& m = *static_cast<Model*>(mp);
+  if (dtype == 0) return dynamics_t<float>(m, B, (const float*)q, (const float*)v, (const float*)tau, (const float*)wext, (float*)vd, (float*)qd, algo, nthreads);
+  return dynamics_t<double>(m, B, (const double*)q, (const double*)v, (const double*)tau, (const double*)wext, (double*)vd, (double*)qd, algo, nthreads);
+}
+// vd == NULL  =>  dynamics_bias
+int rbdo_inverse_dynamics(void* mp, int dtype, int64_t B, const void* q, const void* v, const void* vd, const void* wext,
+                          void* tau, int nthreads) {
+  const Model& m = *static_cast<Model*>(mp);
+  if (dtype == 0) return inverse_dynamics_t<float>(m, B, (const float*)q, (const float*)v, (const float*)vd, (const float*)wext, (float*)tau, nthreads);
+  return inverse_dynamics_t<double>(m, B, (const double*)q, (const double*)v, (const double*)vd, (const double*)wext, (double*)tau, nthreads);
+}
+int rbdo_mass_matrix(void* mp, int dtype, int64_t B, const void* q, void* M, int nthreads) {
+  const Model& m = *static_cast<Model*>(mp);
+  if (dtype == 0) return mass_matrix_t<float>(m, B, (const float*)q, (float*)M, nthreads);
+  return mass_matrix_t<double>(m, B, (const double*)q, (double*)M, nthreads);
+}
+
+}  // extern "C"
