@@ -1,0 +1,172 @@
+/*
+ * rbd_b200.h -- C ABI of librbd_b200.so: batched rigid-body dynamics on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of RigidBodyDynamics.jl v2.5.0 (reference at /root/reference):
+ * dynamics!, inverse_dynamics!, mass_matrix!, dynamics_bias! evaluated over a batch of (q, v, tau) states.
+ * The reference has no FFI of its own (it is 100 % Julia; SURVEY.md finding 2), so each entry point below
+ * names the Julia generic function it replaces; a Julia shim (julia/RBDB200.jl) `ccall`s
+ * these symbols, and the Python host package binds the same symbols with ctypes.
+ *
+ * Conventions (identical to the reference):
+ *   - 6-vectors are [angular; linear]                               src/spatial/common.jl:13
+ *   - joint order == q/v/tau index order == tree_joints(mechanism)  src/mechanism_state.jl:101-104
+ *   - QuaternionFloating: q = [w x y z px py pz], v = body-frame twist  src/joint_types/quaternion_floating.jl:9-17
+ *   - external wrenches are given in the ROOT frame, one per non-root body, and are subtracted from the
+ *     Newton-Euler wrench                                            src/mechanism_algorithms.jl:428-439
+ *
+ * Batched array layout: every array is "rows x batch" with the BATCH INDEX FASTEST (structure of arrays):
+ * element (row k, sample b) lives at ptr[k * ld + b], ld >= B.  A Julia Matrix{T}(B, n) / CuArray{T,2}(B, n)
+ * has exactly this layout with ld = B.  dtype selects float / double for ALL arrays of a call.
+ *
+ * Pointers of the plain entry points are DEVICE pointers; work is enqueued asynchronously on `stream`
+ * (a cudaStream_t cast to void*; NULL = legacy default stream).  The *_host variants take HOST pointers
+ * (pinned memory recommended), stage chunks through device buffers owned by the model handle, overlap
+ * H2D / kernel / D2H on internal streams and return when the results are in host memory.
+ *
+ * All functions return an rbd_status (0 = RBD_OK) and never throw; rbd_last_error() returns a message for
+ * the calling thread's last failure.  A model handle is immutable after creation and may be shared between
+ * threads; concurrent calls on the same handle must use different streams only for the plain (device-pointer)
+ * entry points -- the *_host variants serialise on the handle's staging buffers.
+ */
+#ifndef RBD_B200_H
+#define RBD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBD_B200_VERSION 100 /* 0.1.0 */
+#define RBD_MAX_BODIES 64    /* non-root bodies (== tree joints) per model */
+
+typedef enum rbd_status {
+  RBD_OK = 0,
+  RBD_EINVAL = 1,       /* NULL pointer, bad enum, malformed description (ArgumentError in the reference)      */
+  RBD_EDIM = 2,         /* size mismatch (DimensionMismatch, mechanism_algorithms.jl:250-251)                  */
+  RBD_ELOOP = 3,        /* mechanism has non-tree joints ("can currently only handle tree Mechanisms", :549)   */
+  RBD_ESTALE = 4,       /* modcount mismatch (ModificationCountMismatch, src/util.jl:56-72)                    */
+  RBD_ECUDA = 5,        /* CUDA runtime error (message in rbd_last_error)                                      */
+  RBD_EUNSUPPORTED = 6, /* model too large / dtype not built -- caller must fall back to the reference itself  */
+  RBD_ENOMEM = 7
+} rbd_status;
+
+typedef enum rbd_dtype { RBD_F32 = 0, RBD_F64 = 1 } rbd_dtype;
+
+/* Joint type codes: the eight JointTypes of src/joint_types/ (file per line). */
+typedef enum rbd_joint_type {
+  RBD_JOINT_REVOLUTE = 0,             /* revolute.jl             nq 1 nv 1, jparam[0:3] = unit axis            */
+  RBD_JOINT_PRISMATIC = 1,            /* prismatic.jl            nq 1 nv 1, jparam[0:3] = unit axis            */
+  RBD_JOINT_FIXED = 2,                /* fixed.jl                nq 0 nv 0                                     */
+  RBD_JOINT_PLANAR = 3,               /* planar.jl               nq 3 nv 3, jparam = x_axis, y_axis, rot_axis  */
+  RBD_JOINT_QUATERNION_FLOATING = 4,  /* quaternion_floating.jl  nq 7 nv 6                                     */
+  RBD_JOINT_SPQUAT_FLOATING = 5,      /* spquat_floating.jl      nq 6 nv 6                                     */
+  RBD_JOINT_QUATERNION_SPHERICAL = 6, /* quaternion_spherical.jl nq 4 nv 3                                     */
+  RBD_JOINT_SINCOS_REVOLUTE = 7       /* sin_cos_revolute.jl     nq 2 nv 1, jparam[0:3] = unit axis            */
+} rbd_joint_type;
+
+/*
+ * Flattened tree Mechanism, in tree_joints(mechanism) order (joint i's successor is non-root body i).
+ * What the shim reads from the reference objects:
+ *   parent[i]    index of the joint whose successor is predecessor(joint i), -1 if the predecessor is the
+ *                root body                                   predsucc, src/mechanism_state.jl:93-94
+ *   jtype[i]     joint_type(joint)                           src/joint.jl:43-67
+ *   X_tree[i]    joint_to_predecessor(joint): rotation (row-major 9) then translation (3)   src/joint.jl:49,77
+ *   jparam[i]    joint-type constants (axes), see rbd_joint_type
+ *   inertia[i]   spatial_inertia(successor) in the frame after the joint: moment about the frame origin
+ *                (row-major 9), cross_part = m*com (3), mass (1)     src/rigid_body.jl:63,
+ *                src/spatial/motion_force_interaction.jl:28-37
+ *   gravity      mechanism.gravitational_acceleration.v      src/mechanism.jl:10-34
+ *   modcount     modcount(mechanism)                         src/util.jl:56-72
+ * q/v offsets are NOT passed: they follow from the joint order and the per-type nq/nv exactly as the
+ * reference's qranges/vranges do (mechanism_state.jl:101-104); rbd_model_get_info returns them for checking.
+ */
+typedef struct rbd_model_desc {
+  int32_t nb;
+  int32_t num_non_tree_joints; /* > 0  =>  RBD_ELOOP, like inverse_dynamics! */
+  const int32_t* parent;       /* [nb]     */
+  const int32_t* jtype;        /* [nb]     */
+  const double* X_tree;        /* [nb][12] */
+  const double* jparam;        /* [nb][9]  */
+  const double* inertia;       /* [nb][13] */
+  double gravity[3];
+  int64_t modcount;
+} rbd_model_desc;
+
+typedef struct rbd_model rbd_model; /* opaque handle */
+
+typedef struct rbd_model_info {
+  int32_t nb, nq, nv;
+  int32_t stash_rows;        /* shared-memory rows per sample used by the ABA kernel                       */
+  int32_t max_branch_depth;  /* simultaneously open branch nodes (pending-slot count)                      */
+  int32_t general_path;      /* 1 if multi-DoF joints occur away from the first root joint                 */
+  int64_t modcount;
+  int32_t qstart[RBD_MAX_BODIES];
+  int32_t vstart[RBD_MAX_BODIES];
+  int32_t eval_order[RBD_MAX_BODIES]; /* depth-first preorder used on the device: position -> joint index */
+} rbd_model_info;
+
+/* Kernel launch statistics of the most recent call on this thread (for bench.py's gpu_launches / roofline). */
+typedef struct rbd_launch_info {
+  int32_t kernels_launched;
+  int32_t grid, block;
+  int32_t smem_bytes;
+  int32_t blocks_per_sm;
+  float last_kernel_ms; /* only filled by the *_host variants and rbd_*_timed helpers; else 0 */
+} rbd_launch_info;
+
+int32_t rbd_version(void);
+const char* rbd_last_error(void);
+const char* rbd_status_string(int32_t status);
+
+/* Flatten-once model handle: replaces constructing MechanismState/DynamicsResult caches
+ * (src/mechanism_state.jl:79-172, src/dynamics_result.jl:11-85). */
+int32_t rbd_model_create(const rbd_model_desc* desc, rbd_model** out);
+int32_t rbd_model_destroy(rbd_model* model);
+int32_t rbd_model_get_info(const rbd_model* model, rbd_model_info* info);
+/* RBD_ESTALE if `modcount` differs from the one the handle was created with (@modcountcheck, util.jl:56-72). */
+int32_t rbd_model_check_modcount(const rbd_model* model, int64_t modcount);
+int32_t rbd_get_launch_info(rbd_launch_info* info);
+
+/*
+ * dynamics!(result, state, torques, externalwrenches)         src/mechanism_algorithms.jl:845-864
+ *   q [nq x B], v [nv x B], tau [nv x B] or NULL (zero torques, the ConstVector default),
+ *   wext [6*nb x B] or NULL (row 6*i+k = component k of the root-frame wrench on body i; NullDict default)
+ *   -> vd_out [nv x B]  (result.v̇), qd_out [nq x B] or NULL (result.q̇, configuration_derivative!)
+ * The reference solves M v̇ = tau - c by CRBA + RNEA + Cholesky; this library evaluates the same v̇ with the
+ * Articulated-Body Algorithm (equal up to rounding; tolerance in tests/test_gpu_parity.py).
+ */
+int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                     const void* tau, const void* wext, void* vd_out, void* qd_out, void* stream);
+
+/* inverse_dynamics!(torquesout, jointwrenchesout, accelerations, state, v̇, externalwrenches)
+ *                                                             src/mechanism_algorithms.jl:542-553
+ *   vd [nv x B] -> tau_out [nv x B] = M(q) v̇ + c(q, v, wext)  (recursive Newton-Euler). */
+int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
+                             const void* v, const void* vd, const void* wext, void* tau_out, void* stream);
+
+/* dynamics_bias!(result, state) / dynamics_bias!(torques, biasaccelerations, wrenches, state, externalwrenches)
+ *                                                             src/mechanism_algorithms.jl:484-498
+ *   -> c_out [nv x B] = c(q, v, wext) = inverse_dynamics with v̇ = 0. */
+int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
+                          const void* v, const void* wext, void* c_out, void* stream);
+
+/* mass_matrix!(M::Symmetric, state)                           src/mechanism_algorithms.jl:248-272
+ *   -> M_out [nv*nv x B]: entry (i, j) of sample b at row i + j*nv (column-major like M.data); BOTH
+ *   triangles are written (the reference fills the lower one and wraps it in Symmetric(:L)). */
+int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
+                        void* stream);
+
+/* Host-pointer variants: same semantics, host buffers in, host buffers out, copies inside the call. */
+int32_t rbd_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                          const void* tau, const void* wext, void* vd_out, void* qd_out);
+int32_t rbd_inverse_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
+                                  const void* v, const void* vd, const void* wext, void* tau_out);
+int32_t rbd_dynamics_bias_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
+                               const void* v, const void* wext, void* c_out);
+int32_t rbd_mass_matrix_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBD_B200_H */

@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE: runs the device algorithms of csrc/rbd_device.cuh on the CPU (see hostsim.cpp)."""
+import ctypes, os, subprocess
+import numpy as np
+from rigidbodydynamics.jl_b200._cabi import RbdModelDesc, make_desc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "..", "..", "rigidbodydynamics", "jl_b200", "csrc")
+_LIB = os.path.join(_HERE, "libhostsim.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in
+            ("rbd_model.cpp", "rbd_model.h", "rbd_types.h", "rbd_device.cuh")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB,
+                               os.path.join(_HERE, "hostsim.cpp"), os.path.join(_CSRC, "rbd_model.cpp")])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def info(desc):
+    d, keep = make_desc(desc)
+    nrows, general, nslots = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    order = (ctypes.c_int * desc.nb)()
+    rc = lib().hostsim_info(ctypes.byref(d), ctypes.byref(nrows), ctypes.byref(general), ctypes.byref(nslots), order)
+    assert rc == 0, rc
+    return dict(nrows=nrows.value, general=general.value, nslots=nslots.value, order=list(order))
+
+
+def dynamics(desc, q, v, tau=None, wext=None, want_qd=False):
+    dt = q.dtype
+    d, keep = make_desc(desc)
+    q = np.ascontiguousarray(q); v = np.ascontiguousarray(v, dt)
+    tau = None if tau is None else np.ascontiguousarray(tau, dt)
+    wext = None if wext is None else np.ascontiguousarray(wext, dt)
+    B = q.shape[1]
+    vd = np.empty((desc.nv, B), dt)
+    qd = np.empty((desc.nq, B), dt) if want_qd else None
+    fn = lib().hostsim_dynamics
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc), ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
+    rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(v), _p(tau), _p(wext), _p(vd), _p(qd))
+    assert rc == 0, rc
+    return (vd, qd) if want_qd else vd
