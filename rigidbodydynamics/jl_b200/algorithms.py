@@ -1,0 +1,129 @@
+"""The hot-path operators of the reference, batched: same names, argument meaning and error behaviour.
+
+    dynamics!           -> dynamics_          src/mechanism_algorithms.jl:845-864 (ODE form :880-889)
+    inverse_dynamics!   -> inverse_dynamics_  src/mechanism_algorithms.jl:542-553   (allocating: inverse_dynamics :560-572)
+    mass_matrix!        -> mass_matrix_       src/mechanism_algorithms.jl:248-272   (allocating: mass_matrix :281)
+    dynamics_bias!      -> dynamics_bias_     src/mechanism_algorithms.jl:484-498   (allocating: dynamics_bias :505-516)
+
+Python has no ``!``; a trailing underscore marks the in-place (non-allocating) variants.  Every function is a thin call
+into ``librbd_b200.so`` (C ABI, include/rbd_b200.h) on the current CUDA stream.  There is no CPU path: on a machine
+without the built library or without a GPU these raise.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _cabi
+from .state import DynamicsResult, MechanismState, _DT
+
+__all__ = ["dynamics_", "dynamics_ode_", "inverse_dynamics_", "inverse_dynamics", "mass_matrix_", "mass_matrix",
+           "dynamics_bias_", "dynamics_bias", "DimensionMismatch"]
+
+
+class DimensionMismatch(ValueError):
+    """Julia's DimensionMismatch (mechanism_algorithms.jl:250-251)."""
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _check(t: Optional[torch.Tensor], rows: int, state: MechanismState, name: str):
+    if t is None:
+        return
+    if t.dtype != state.dtype or t.device != state.q.device:
+        raise TypeError(f"{name}: dtype/device must match the state ({state.dtype}, {state.q.device})")
+    if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != state.batch:
+        raise DimensionMismatch(f"{name} has wrong size: expected ({rows}, {state.batch}), got {tuple(t.shape)}")
+    if t.stride(1) != 1 or t.stride(0) != state.batch:
+        raise ValueError(f"{name} must be [rows, B] contiguous (batch index fastest)")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(status):
+    _cabi.check(status)
+
+
+def dynamics_(result: DynamicsResult, state: MechanismState, torques: Optional[torch.Tensor] = None,
+              externalwrenches: Optional[torch.Tensor] = None, want_qd: bool = True):
+    """``dynamics!(result, state, torques, externalwrenches)``: fills ``result.vd`` (v̇) and ``result.qd`` (q̇).
+
+    ``torques`` [nv, B] or None (zero, the ConstVector default); ``externalwrenches`` [6*nb, B] root-frame wrenches
+    (rows 6i..6i+5 = [torque; force] on the successor of tree joint i) or None (the NullDict default)."""
+    state.check_modcount()
+    lib = _cabi.load_library()
+    _check(torques, state.nv, state, "torques")
+    _check(externalwrenches, 6 * len(state.mechanism.joints), state, "externalwrenches")
+    _check(result.vd, state.nv, state, "result.vd")
+    _call(lib.rbd_dynamics(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(state.v),
+                           _ptr(torques), _ptr(externalwrenches), _ptr(result.vd),
+                           _ptr(result.qd) if want_qd else None, _stream()))
+    return result
+
+
+def dynamics_ode_(xdot: torch.Tensor, result: DynamicsResult, state: MechanismState, x: torch.Tensor,
+                  torques: Optional[torch.Tensor] = None, externalwrenches: Optional[torch.Tensor] = None):
+    """ODE form ``dynamics!(ẋ, result, state, x, torques, externalwrenches)`` (mechanism_algorithms.jl:880-889):
+    x = [q; v] -> ẋ = [q̇; v̇], all [*, B]."""
+    state.copy_from_vector_(x)
+    dynamics_(result, state, torques, externalwrenches)
+    xdot[: state.nq].copy_(result.qd)
+    xdot[state.nq:].copy_(result.vd)
+    return xdot
+
+
+def inverse_dynamics_(torquesout: torch.Tensor, state: MechanismState, vd: torch.Tensor,
+                      externalwrenches: Optional[torch.Tensor] = None):
+    """``inverse_dynamics!``: tau = M(q) v̇ + c(q, v, w_ext).  (The per-body joint wrench / acceleration outputs of the
+    reference signature are not materialised by the batched kernel.)"""
+    state.check_modcount()
+    lib = _cabi.load_library()
+    _check(vd, state.nv, state, "v̇")
+    _check(torquesout, state.nv, state, "torquesout")
+    _check(externalwrenches, 6 * len(state.mechanism.joints), state, "externalwrenches")
+    _call(lib.rbd_inverse_dynamics(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q),
+                                   _ptr(state.v), _ptr(vd), _ptr(externalwrenches), _ptr(torquesout), _stream()))
+    return torquesout
+
+
+def inverse_dynamics(state: MechanismState, vd: torch.Tensor, externalwrenches: Optional[torch.Tensor] = None):
+    return inverse_dynamics_(torch.empty_like(state.v), state, vd, externalwrenches)
+
+
+def dynamics_bias_(result_or_out, state: MechanismState, externalwrenches: Optional[torch.Tensor] = None):
+    """``dynamics_bias!(result, state)`` / 5-argument form: c(q, v, w_ext)."""
+    state.check_modcount()
+    lib = _cabi.load_library()
+    out = result_or_out.dynamicsbias if isinstance(result_or_out, DynamicsResult) else result_or_out
+    _check(out, state.nv, state, "dynamicsbias")
+    _check(externalwrenches, 6 * len(state.mechanism.joints), state, "externalwrenches")
+    _call(lib.rbd_dynamics_bias(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q),
+                                _ptr(state.v), _ptr(externalwrenches), _ptr(out), _stream()))
+    return out
+
+
+def dynamics_bias(state: MechanismState, externalwrenches: Optional[torch.Tensor] = None):
+    return dynamics_bias_(torch.empty_like(state.v), state, externalwrenches)
+
+
+def mass_matrix_(result_or_out, state: MechanismState):
+    """``mass_matrix!(M, state)`` / ``mass_matrix!(result, state)``: [nv*nv, B], entry (i, j) at row i + j*nv."""
+    state.check_modcount()
+    lib = _cabi.load_library()
+    out = result_or_out.massmatrix if isinstance(result_or_out, DynamicsResult) else result_or_out
+    if out.dim() != 2 or out.shape[0] != state.nv * state.nv or out.shape[1] != state.batch:
+        raise DimensionMismatch("mass matrix has wrong size")                 # mechanism_algorithms.jl:250
+    _check(out, state.nv * state.nv, state, "mass matrix")
+    _call(lib.rbd_mass_matrix(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(out),
+                              _stream()))
+    return out
+
+
+def mass_matrix(state: MechanismState):
+    out = torch.empty((state.nv * state.nv, state.batch), dtype=state.dtype, device=state.q.device)
+    return mass_matrix_(out, state)

@@ -1,0 +1,126 @@
+"""GPU tier: the CUDA path, called through the C ABI, against the CPU oracle on identical seeded inputs.
+
+Tolerances (stated per SURVEY 8(d) 'Accuracy', metric = max_b |x_gpu - x_oracle64|_inf / max(1, |x_oracle64|_inf)):
+  fp64: 1e-9   (the reference's own FD/ID tolerance is 1e-10 absolute on O(1) values, test_mechanism_algorithms.jl:739;
+                here |v̇| reaches 1e3-1e4 on Atlas' light distal links, hence the relative form)
+  fp32: 2e-5   (measured ~5e-7 on Atlas; the reference's fp32 CRBA + Cholesky path itself is ~3e-4, tests/test_hostsim.py)
+"""
+import numpy as np
+import pytest
+import torch
+
+import rigidbodydynamics.jl_b200 as rbd
+from oracle import Oracle
+from tests.util import rand_inputs, randmech, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float64: 1e-9, torch.float32: 2e-5}
+
+
+def gpu_dynamics(mech, q, v, tau, dtype, wext=None, want_qd=True):
+    B = q.shape[1]
+    state = rbd.MechanismState(mech, B, dtype)
+    state.q.copy_(torch.from_numpy(q).to(dtype))
+    state.v.copy_(torch.from_numpy(v).to(dtype))
+    t = None if tau is None else torch.from_numpy(tau).to(dtype).cuda()
+    w = None if wext is None else torch.from_numpy(wext).to(dtype).cuda()
+    res = rbd.DynamicsResult(mech, B, dtype)
+    rbd.dynamics_(res, state, t, w, want_qd=want_qd)
+    torch.cuda.synchronize()
+    return res.vd.double().cpu().numpy(), res.qd.double().cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name,floating", [("atlas", True), ("atlas", False), ("valkyrie", True), ("iiwa14", False),
+                                           ("double_pendulum", False)])
+def test_dynamics_matches_oracle(built, name, floating, dtype):
+    mech = rbd.load_model(name, floating=floating)
+    q, v, tau, _, _ = rand_inputs(mech, 193, 17)
+    ref, ref_qd = Oracle(mech.flatten()).dynamics(q, v, tau, want_qd=True)
+    got, got_qd = gpu_dynamics(mech, q, v, tau, dtype)
+    assert rel_err(got, ref) < TOL[dtype]
+    assert np.abs(got_qd - ref_qd).max() < (1e-12 if dtype == torch.float64 else 1e-5)
+
+
+def test_quickstart_numbers_on_gpu(built):
+    """Config 1 (examples/1 quick start): v̇ for q=(0.3,0.4), v=(1,2), tau=0 -- SURVEY 8(c)(1)."""
+    from tests.util import double_pendulum
+    mech = double_pendulum()
+    got, _ = gpu_dynamics(mech, np.array([[0.3], [0.4]]), np.array([[1.0], [2.0]]), None, torch.float64)
+    assert np.allclose(got.ravel(), [2.935110215118255, -17.068157341777777], atol=1e-11)
+
+
+@pytest.mark.parametrize("B", [1, 31, 32, 33, 1000])
+def test_ragged_batch_sizes(built, B):
+    mech = rbd.load_model("atlas", floating=True)
+    q, v, tau, _, _ = rand_inputs(mech, B, B)
+    ref = Oracle(mech.flatten()).dynamics(q, v, tau)
+    got, _ = gpu_dynamics(mech, q, v, tau, torch.float64)
+    assert got.shape == ref.shape and rel_err(got, ref) < 1e-9
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_general_trees_all_joint_types(built, seed):
+    mech = randmech(seed, shuffle=seed % 2 == 1)
+    q, v, tau, _, _ = rand_inputs(mech, 65, seed)
+    ref, ref_qd = Oracle(mech.flatten()).dynamics(q, v, tau, want_qd=True)
+    for dtype in (torch.float64, torch.float32):
+        got, got_qd = gpu_dynamics(mech, q, v, tau, dtype)
+        assert rel_err(got, ref) < (1e-9 if dtype == torch.float64 else 1e-3)
+        assert np.abs(got_qd - ref_qd).max() < (1e-12 if dtype == torch.float64 else 1e-5)
+
+
+def test_host_pointer_entry_point(built):
+    """rbd_dynamics_host (pinned host buffers in, host buffers out, chunked copies inside) == device-pointer path."""
+    mech = rbd.load_model("atlas", floating=True)
+    B = (1 << 16) + 777                       # more than one chunk, ragged tail
+    q, v, tau, _, _ = rand_inputs(mech, 64, 3)
+    reps = -(-B // 64)
+    q, v, tau = (np.tile(a, (1, reps))[:, :B].copy() for a in (q, v, tau))
+    got_dev, _ = gpu_dynamics(mech, q, v, tau, torch.float32, want_qd=False)
+    lib = rbd.load_library()
+    state = rbd.MechanismState(mech, 1, torch.float32)
+    hq, hv, ht = (torch.from_numpy(a).float().pin_memory() for a in (q, v, tau))
+    out = torch.empty((36, B), dtype=torch.float32).pin_memory()
+    rbd._cabi.check(lib.rbd_dynamics_host(state.handle.ptr, 0, B, B, hq.data_ptr(), hv.data_ptr(), ht.data_ptr(), None,
+                                          out.data_ptr(), None))
+    assert np.array_equal(out.numpy().astype(np.float64), got_dev)
+    assert rbd.launch_info().kernels_launched == 2
+
+
+def test_errors_match_reference_behaviour(built):
+    mech = rbd.load_model("iiwa14")
+    state = rbd.MechanismState(mech, 8, torch.float32)
+    res = rbd.DynamicsResult(mech, 8, torch.float32)
+    with pytest.raises(rbd.DimensionMismatch):
+        rbd.dynamics_(res, state, torch.zeros((6, 8), dtype=torch.float32, device="cuda"))
+    # a Mechanism edited after the state was built -> ModificationCountMismatch (util.jl:56-72)
+    mech.attach(mech.bodies[-1], rbd.RigidBody("tool", rbd.SpatialInertia.rand(np.random.default_rng(0))),
+                rbd.Joint("tool_joint", rbd.Fixed()))
+    with pytest.raises(rbd.RbdError) as e:
+        rbd.dynamics_(res, state)
+    assert e.value.status == rbd._cabi.RBD_ESTALE
+
+
+def test_full_size_properties(built):
+    """At BASELINE.json's full batch (2^20, fp32): size-independent checks -- every output finite, sample b's result does not
+    depend on the batch it sits in (re-evaluating slices reproduces it bit-for-bit), and a strided sub-sample matches the oracle."""
+    mech = rbd.load_model("atlas", floating=True)
+    B = 1 << 20
+    rng = np.random.default_rng(1)
+    state = rbd.MechanismState(mech, B, torch.float32)
+    rbd.rand_(state, rng)
+    tau = torch.rand((36, B), dtype=torch.float32, device="cuda")
+    res = rbd.DynamicsResult(mech, B, torch.float32)
+    rbd.dynamics_(res, state, tau, want_qd=False)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(res.vd).all())
+    idx = torch.arange(0, B, 4099, device="cuda")
+    sub = rbd.MechanismState(mech, idx.numel(), torch.float32)
+    sub.q.copy_(state.q[:, idx]); sub.v.copy_(state.v[:, idx])
+    res2 = rbd.DynamicsResult(mech, idx.numel(), torch.float32)
+    rbd.dynamics_(res2, sub, tau[:, idx].contiguous(), want_qd=False)
+    assert torch.equal(res2.vd, res.vd[:, idx])
+    ref = Oracle(mech.flatten()).dynamics(sub.q.double().cpu().numpy(), sub.v.double().cpu().numpy(),
+                                          tau[:, idx].double().cpu().numpy())
+    assert rel_err(res2.vd.double().cpu().numpy(), ref) < 2e-5

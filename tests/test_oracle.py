@@ -1,0 +1,121 @@
+"""Pins the CPU oracle (oracle/) against everything the reference's own tests hold for the hot path.
+
+  * closed-form double pendulum  -- test/test_double_pendulum.jl:2-11,51-65,72-75 (atol 1e-12)
+  * quick-start state values     -- examples/1: M, c, inverse dynamics, forward dynamics
+  * identity / property tests    -- test/test_mechanism_algorithms.jl:564-572 (KE), 729-740 (FD o ID), 742-753 (bias = ID(0)),
+                                    600-614 (columns of M = ID(e_k) - ID(0))
+The reference holds no stored numeric vectors for Atlas-sized models; for those the oracle is pinned by the
+identities plus the agreement of two independent formulations (CRBA + RNEA + Cholesky vs world-frame ABA).
+"""
+import numpy as np
+import pytest
+
+import rigidbodydynamics.jl_b200 as rbd
+from oracle import Oracle
+from tests.util import double_pendulum, rand_inputs, randmech, rel_err
+
+
+def test_double_pendulum_closed_form():
+    """The textbook M, C, G of test/test_double_pendulum.jl:51-65 with its parameters (:2-11)."""
+    lc1, l1, m1, I1, lc2, l2, m2, I2, g = -0.5, -1.0, 1.0, 0.333, -1.0, -2.0, 1.0, 1.33, -9.81
+    mech = double_pendulum(I1, I2, lc1, lc2, l1, m1, m2, g)
+    o = Oracle(mech.flatten())
+    rng = np.random.default_rng(6)
+    for _ in range(10):
+        q1, q2 = rng.standard_normal(2)
+        v1, v2 = rng.random(2)
+        vd = rng.random(2)
+        c2, s1, s2, s12 = np.cos(q2), np.sin(q1), np.sin(q2), np.sin(q1 + q2)
+        M = np.array([[I1 + I2 + m2 * l1 ** 2 + 2 * m2 * l1 * lc2 * c2, I2 + m2 * l1 * lc2 * c2],
+                      [I2 + m2 * l1 * lc2 * c2, I2]])
+        C = np.array([[-2 * m2 * l1 * lc2 * s2 * v2, -m2 * l1 * lc2 * s2 * v2], [m2 * l1 * lc2 * s2 * v1, 0]])
+        G = np.array([m1 * g * lc1 * s1 + m2 * g * (l1 * s1 + lc2 * s12), m2 * g * lc2 * s12])
+        q, v = np.array([q1, q2]), np.array([v1, v2])
+        assert np.allclose(o.mass_matrix(q).reshape(2, 2), M, rtol=0, atol=1e-12)
+        tau = o.inverse_dynamics(q, v, vd).ravel()
+        assert np.allclose(tau, M @ vd + C @ v + G, rtol=0, atol=1e-12)
+        # forward dynamics inverts it (both the reference's Cholesky path and the independent ABA)
+        for algo in ("reference", "aba"):
+            assert np.allclose(o.dynamics(q, v, tau, algo=algo).ravel(), vd, rtol=0, atol=1e-10)
+
+
+def test_quickstart_state_values():
+    """Config 1 acceptance numbers: examples/1 quick-start pendulum at q=(0.3,0.4), v=(1,2)."""
+    o = Oracle(double_pendulum().flatten())
+    q, v = np.array([0.3, 0.4]), np.array([1.0, 2.0])
+    assert np.allclose(o.mass_matrix(q).reshape(2, 2),
+                       [[2.587060994002885, 0.7935304970014425], [0.7935304970014425, 0.333]], atol=1e-12)
+    assert np.allclose(o.dynamics_bias(q, v).ravel(), [5.950794227687885, 3.3545969270552], atol=1e-12)
+    assert np.allclose(o.inverse_dynamics(q, v, np.array([1.0, 2.0])).ravel(),
+                       [10.124916215693656, 4.814127424056642], atol=1e-12)
+    assert np.allclose(o.dynamics(q, v).ravel(), [2.935110215118255, -17.068157341777777], atol=1e-12)
+
+
+def test_urdf_double_pendulum_matches_api_model():
+    """test/test_double_pendulum.jl:78-99: the URDF model gives the same M and tau (incl. the SinCosRevolute variant)."""
+    api = Oracle(double_pendulum().flatten())
+    urdf = Oracle(rbd.load_model("double_pendulum").flatten())
+    jt = rbd.default_urdf_joint_types()
+    jt["continuous"] = rbd.SinCosRevolute
+    sincos = Oracle(rbd.load_model("double_pendulum", joint_types=jt).flatten())
+    rng = np.random.default_rng(3)
+    q, v, vd = rng.standard_normal((2, 5)), rng.random((2, 5)), rng.random((2, 5))
+    qsc = np.stack([np.sin(q[0]), np.cos(q[0]), np.sin(q[1]), np.cos(q[1])])
+    assert np.allclose(api.mass_matrix(q), urdf.mass_matrix(q), atol=1e-12)
+    assert np.allclose(api.mass_matrix(q), sincos.mass_matrix(qsc), atol=1e-12)
+    assert np.allclose(api.inverse_dynamics(q, v, vd), urdf.inverse_dynamics(q, v, vd), atol=1e-12)
+    assert np.allclose(api.inverse_dynamics(q, v, vd), sincos.inverse_dynamics(qsc, v, vd), atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", [17, 25, 40, 41])
+def test_identities_random_mechanism(seed):
+    """The reference's cross-algorithm identities on its 25-joint random trees (all joint types, external wrenches)."""
+    mech = randmech(seed, shuffle=seed % 2 == 1)
+    o = Oracle(mech.flatten())
+    B = 6
+    q, v, tau, vd, w = rand_inputs(mech, B, seed, wext=True)
+    nv = o.nv
+    # dynamics / inverse dynamics round trip (test_mechanism_algorithms.jl:729-740, atol 1e-10)
+    acc = o.dynamics(q, v, tau, w)
+    assert np.abs(o.inverse_dynamics(q, v, acc, w) - tau).max() < 1e-10
+    # the independent ABA agrees with the reference's CRBA + RNEA + Cholesky path
+    assert rel_err(o.dynamics(q, v, tau, w, algo="aba"), acc) < 1e-10
+    # dynamics_bias == inverse_dynamics(v̇ = 0) (:742-753)
+    c = o.dynamics_bias(q, v, w)
+    assert np.abs(c - o.inverse_dynamics(q, v, np.zeros((nv, B)), w)).max() < 1e-12
+    # columns of M: tau(e_k) - tau(0) (:600-614), symmetry, M v̇ + c = tau
+    M = o.mass_matrix(q).reshape(nv, nv, B).transpose(1, 0, 2)      # [i, j, b]
+    assert np.abs(M - M.transpose(1, 0, 2)).max() == 0
+    for k in range(0, nv, 7):
+        e = np.zeros((nv, B)); e[k] = 1
+        assert np.abs(o.inverse_dynamics(q, v, e, w) - c - M[:, k, :]).max() < 1e-10
+    assert np.abs(np.einsum("ijb,jb->ib", M, acc) + c - tau).max() < 1e-9
+    for b in range(B):
+        assert np.linalg.eigvalsh(M[:, :, b]).min() > 0
+
+
+def test_kinetic_energy_identity_chain():
+    """1/2 v' M v equals the sum of body kinetic energies (:564-572), via the power identity on a gravity-free chain:
+    with g = 0 and zero torque, d/dt (1/2 v' M v) = 0  <=>  v . (M v̇ + Ṁ v / 2) = 0, checked through v . c = v . (C v)
+    where v'(Ṁ - 2C)v = 0 (skew symmetry, :616-652)."""
+    rng = np.random.default_rng(5)
+    mech = rbd.rand_chain_mechanism(rng, [rbd.Revolute] * 6)
+    mech.gravitational_acceleration[:] = 0
+    o = Oracle(mech.flatten())
+    q, v, _, _, _ = rand_inputs(mech, 4, 5)
+    M = lambda qq: o.mass_matrix(qq).reshape(o.nv, o.nv, -1).transpose(1, 0, 2)
+    h = 1e-6
+    Mdot = (M(q + h * v) - M(q - h * v)) / (2 * h)                   # q̇ = v for revolute joints
+    c = o.dynamics_bias(q, v)
+    lhs = np.einsum("ib,ib->b", v, c)
+    rhs = 0.5 * np.einsum("ib,ijb,jb->b", v, Mdot, v)
+    assert np.allclose(lhs, rhs, atol=1e-6)
+
+
+def test_float32_oracle_runs():
+    mech = rbd.load_model("iiwa14")
+    o = Oracle(mech.flatten())
+    q, v, tau, vd, _ = rand_inputs(mech, 8, 2)
+    a64 = o.dynamics(q, v, tau)
+    a32 = o.dynamics(q, v, tau, dtype=np.float32)
+    assert a32.dtype == np.float32 and rel_err(a32, a64) < 1e-3

@@ -1,0 +1,52 @@
+"""Shared helpers for the test-suite: models, seeded inputs, error metrics."""
+import os
+
+import numpy as np
+
+import rigidbodydynamics.jl_b200 as rbd
+
+REF_URDF = "/root/reference/test/urdf"
+ALL_JOINT_TYPES = ([rbd.QuaternionFloating] + [rbd.Revolute] * 5 + [rbd.Fixed] * 5 + [rbd.Prismatic] * 5
+                   + [rbd.Planar] * 5 + [rbd.SPQuatFloating] * 2 + [rbd.SinCosRevolute] * 2
+                   + [rbd.QuaternionSpherical] * 2)
+
+
+def randmech(seed, shuffle=False):
+    """The reference's `randmech()` fixture (test/test_mechanism_algorithms.jl:1-11) plus QuaternionSpherical joints."""
+    rng = np.random.default_rng(seed)
+    jts = list(ALL_JOINT_TYPES)
+    if shuffle:
+        jts = [jts[i] for i in rng.permutation(len(jts))]
+    return rbd.rand_tree_mechanism(rng, jts)
+
+
+def double_pendulum(I1=0.333, I2=0.333, lc1=-0.5, lc2=-0.5, l1=-1.0, m1=1.0, m2=1.0, g=-9.81):
+    """The reference's double pendulum built through the API (test/test_double_pendulum.jl:2-32, examples/1)."""
+    axis = np.array([0.0, 1.0, 0.0])
+    mech = rbd.Mechanism(rbd.RigidBody("world"), gravity=(0, 0, g))
+    b1 = rbd.RigidBody("upper_link", rbd.SpatialInertia(I1 * np.outer(axis, axis), None, m1, com=[0, 0, lc1]))
+    mech.attach(mech.root_body, b1, rbd.Joint("shoulder", rbd.Revolute(axis)))
+    b2 = rbd.RigidBody("lower_link", rbd.SpatialInertia(I2 * np.outer(axis, axis), None, m2, com=[0, 0, lc2]))
+    mech.attach(b1, b2, rbd.Joint("elbow", rbd.Revolute(axis)), joint_pose=rbd.Transform3D(None, [0, 0, l1]))
+    return mech
+
+
+def rand_inputs(mech, B, seed, wext=False):
+    rng = np.random.default_rng(seed)
+    nq, nv, nb = mech.num_positions(), mech.num_velocities(), len(mech.joints)
+    q = np.stack([mech.rand_configuration(rng) for _ in range(B)], 1) if nq else np.zeros((0, B))
+    v = rng.random((nv, B))
+    tau = rng.random((nv, B))
+    vd = rng.random((nv, B))
+    w = rng.random((6 * nb, B)) if wext else None
+    return q, v, tau, vd, w
+
+
+def rel_err(got, ref):
+    """max over the batch of |got - ref|_inf / max(1, |ref|_inf)   (SURVEY 8(d) 'Accuracy')."""
+    got, ref = np.asarray(got, float), np.asarray(ref, float)
+    return float((np.abs(got - ref).max(0) / np.maximum(1.0, np.abs(ref).max(0))).max())
+
+
+def have_reference():
+    return os.path.isdir(REF_URDF)
