@@ -110,7 +110,10 @@ template <class T> struct Mot { T w[3]; T l[3]; };
 template <class T> struct Art { T A[6]; T B[9]; T C[6]; T n[3]; T f[3]; };
 
 // index of (i, j) in the packed symmetric storage
-RBD_HD constexpr int sidx(int i, int j) { return i <= j ? (i == 0 ? j : (i == 1 ? 2 + j : 5)) : sidx(j, i); }
+RBD_HD constexpr int sidx(int i, int j) {
+  // (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5 -- no recursion: must fold to a constant after unrolling
+  return (i < j ? i : j) == 0 ? (i < j ? j : i) : ((i < j ? i : j) == 1 ? 2 + (i < j ? j : i) : 5);
+}
 
 // Motion transform parent -> child.  R: child->parent rotation, r: child origin in parent coordinates.
 //   w_c = R^T w_p ;  l_c = R^T (l_p + w_p x r)          (inverse of transform_spatial_motion, spatial/util.jl:104-108)
