@@ -81,6 +81,8 @@ template <class T> struct AbaArgs {
   int64_t ld, B;
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <class T, int NT, bool GENERAL>
 __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -88,6 +90,16 @@ __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDe
   const Stash<T, NT> st{sh + threadIdx.x};
   const int64_t ngroups = (a.B + NT - 1) / NT;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    {  // pull the NEXT group's input lines into L2 while this group is being computed (one 128-byte line per row)
+      const int64_t gn = g + gridDim.x;
+      if (gn < ngroups) {
+        const int64_t bn = gn * NT + (threadIdx.x & ~31);
+        const int lane = threadIdx.x & 31;
+        for (int r = lane; r < M.nq; r += 32) prefetch_l2(a.q + (int64_t)r * a.ld + bn);
+        for (int r = lane; r < M.nv; r += 32) prefetch_l2(a.v + (int64_t)r * a.ld + bn);
+        if (a.tau) for (int r = lane; r < M.nv; r += 32) prefetch_l2(a.tau + (int64_t)r * a.ld + bn);
+      }
+    }
     const int64_t b = g * NT + threadIdx.x;
     const bool active = b < a.B;
     const int64_t bl = active ? b : a.B - 1;     // inactive lanes recompute the last sample, stores are masked

@@ -513,9 +513,29 @@ template <class T> struct AbaIO {
   ColOut<T> vd, qd;         // qd may be invalid
 };
 
+// Scalars of one 1-DoF body that come from global memory.  They are requested one body AHEAD of their use (software
+// pipelining in aba_sample) so the load latency overlaps the previous body's arithmetic instead of stalling the warp.
+template <class T> struct Pre { T q0, q1, qd, tau; };
+template <class T, int PASS>
+RBD_HD void prefetch_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, Pre<T>& p) {
+  p.q0 = T(0); p.q1 = T(0); p.qd = T(0); p.tau = T(0);
+  if (i < 0 || i >= M.nb) return;
+  const BodyDev<T>& bd = M.body[i];
+  const int kind = bd.kind;
+  if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS) {     // multi-DoF bodies read their rows directly
+    if (PASS == 1) {
+      p.q0 = io.q(bd.qrow);
+      if (kind == K_SINCOS) p.q1 = io.q(bd.qrow + 1);
+    }
+    p.qd = io.v(bd.vrow);
+    if (PASS == 2 && io.tau.valid()) p.tau = io.tau(bd.vrow);
+  }
+}
+
 // ---- pass 1 (outward): velocities ---------------------------------------------------------------------------------
 template <class T, int STRIDE, bool GENERAL>
-RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Mot<T>& vcur) {
+RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Mot<T>& vcur,
+                           const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   Mot<T> vp;
   if (bd.flags & F_ROOT_CHILD) {
@@ -533,10 +553,10 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
   Mot<T> v;
   if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
     T s = T(0), c = T(1), d = T(0), qd = T(0);
-    if (kind == K_REV) sincos_t(io.q(bd.qrow), s, c);
-    else if (kind == K_SINCOS) { s = io.q(bd.qrow); c = io.q(bd.qrow + 1); }
-    else if (kind == K_PRIS) d = io.q(bd.qrow);
-    if (kind != K_FIXED) qd = io.v(bd.vrow);
+    if (kind == K_REV) sincos_t(pre.q0, s, c);
+    else if (kind == K_SINCOS) { s = pre.q0; c = pre.q1; }
+    else if (kind == K_PRIS) d = pre.q0;
+    if (kind != K_FIXED) qd = pre.qd;
     frame_1dof(bd, s, c, d, R, r);
     motion_to_child(R, r, vp, v);
     if (kind == K_PRIS) v.l[2] += qd; else if (kind != K_FIXED) v.w[2] += qd;
@@ -564,7 +584,8 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
 // 1-DoF / fixed body.  On exit the body's rows hold U~ (5 non-unit entries) and u~; `carry` / the parent's slot hold
 // its contribution to the parent.
 template <class T, int STRIDE>
-RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Art<T>& carry) {
+RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Art<T>& carry,
+                           const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
   Mot<T> v;
@@ -590,8 +611,8 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
     return;
   }
   const T sd = st.ld(bd.row0 + 6), c = st.ld(bd.row0 + 7);
-  const T qd = io.v(bd.vrow);
-  const T tau = io.tau.valid() ? io.tau(bd.vrow) : T(0);
+  const T qd = pre.qd;
+  const T tau = pre.tau;
   if (kind != K_PRIS) {
     // ---- revolute about e_z: S = e_{ang z} ----
     const T Ux = a.A[2], Uy = a.A[4], D = a.A[5];
@@ -810,7 +831,8 @@ RBD_HD void save_own_va(const ModelDev<T>& M, const BodyDev<T>& bd, const Stash<
 }
 
 template <class T, int STRIDE>
-RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Mot<T>& vcur, Mot<T>& acur) {
+RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Mot<T>& vcur, Mot<T>& acur,
+                           const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
   Mot<T> vp, ap, v, xa;
@@ -825,7 +847,7 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
     return;
   }
   const T sd = st.ld(bd.row0 + 6), c = st.ld(bd.row0 + 7);
-  const T qd = io.v(bd.vrow);
+  const T qd = pre.qd;
   const T t0 = st.ld(bd.row0 + 0), t1 = st.ld(bd.row0 + 1), t2 = st.ld(bd.row0 + 2), t3 = st.ld(bd.row0 + 3),
           t4 = st.ld(bd.row0 + 4), tu = st.ld(bd.row0 + 5);
   Mot<T> a;
@@ -898,8 +920,14 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const AbaIO<T>& io, const Stash<T, 
   Mot<T> vcur, acur;
 #pragma unroll
   for (int k = 0; k < 3; ++k) { vcur.w[k] = vcur.l[k] = acur.w[k] = acur.l[k] = T(0); }
-  // pass 1
-  for (int i = 0; i < nb; ++i) aba_pass1_body<T, STRIDE, GENERAL>(M, i, io, st, vcur);
+  // pass 1 (loads for body i+1 are in flight while body i is processed)
+  Pre<T> cur, nxt;
+  prefetch_body<T, 1>(M, 0, io, cur);
+  for (int i = 0; i < nb; ++i) {
+    prefetch_body<T, 1>(M, i + 1, io, nxt);
+    aba_pass1_body<T, STRIDE, GENERAL>(M, i, io, st, vcur, cur);
+    cur = nxt;
+  }
   // pass 2
   Art<T> carry;
 #pragma unroll
@@ -908,10 +936,14 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const AbaIO<T>& io, const Stash<T, 
   for (int k = 0; k < 9; ++k) carry.B[k] = T(0);
 #pragma unroll
   for (int k = 0; k < 3; ++k) { carry.n[k] = T(0); carry.f[k] = T(0); }
+  prefetch_body<T, 2>(M, nb - 1, io, cur);
   for (int i = nb - 1; i >= 1; --i) {
     const int kind = M.body[i].kind;
+    prefetch_body<T, 2>(M, i - 1, io, nxt);
+    Pre<T> now = cur;
+    cur = nxt;
     if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
-      aba_pass2_1dof(M, i, io, st, carry);
+      aba_pass2_1dof(M, i, io, st, carry, now);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
       aba_pass2_multi<T, STRIDE, 6, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
     } else if (kind == K_PLANAR) {
@@ -925,9 +957,10 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const AbaIO<T>& io, const Stash<T, 
     const BodyDev<T>& b0 = M.body[0];
     const int kind = b0.kind;
     const bool root0 = (b0.flags & F_ROOT_CHILD) != 0;   // always true for position 0
+    prefetch_body<T, 3>(M, 1, io, nxt);
     if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
-      aba_pass2_1dof(M, 0, io, st, carry);
-      aba_pass3_1dof(M, 0, io, st, vcur, acur);
+      aba_pass2_1dof(M, 0, io, st, carry, cur);
+      aba_pass3_1dof(M, 0, io, st, vcur, acur, cur);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
       aba_pass2_multi<T, STRIDE, 6, K_QFLOAT, true>(M, 0, io, st, carry, vcur, acur);
       save_own_va(M, b0, st, vcur, acur);
@@ -941,10 +974,14 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const AbaIO<T>& io, const Stash<T, 
     (void)root0;
   }
   // pass 3
+  cur = nxt;
   for (int i = 1; i < nb; ++i) {
     const int kind = M.body[i].kind;
+    prefetch_body<T, 3>(M, i + 1, io, nxt);
+    Pre<T> now = cur;
+    cur = nxt;
     if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
-      aba_pass3_1dof(M, i, io, st, vcur, acur);
+      aba_pass3_1dof(M, i, io, st, vcur, acur, now);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
       aba_pass3_multi<T, STRIDE, 6, K_QFLOAT>(M, i, io, st, vcur, acur);
     } else if (kind == K_PLANAR) {
