@@ -523,13 +523,19 @@ RBD_HD void prefetch_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, Pre<T
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
   if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS) {     // multi-DoF bodies read their rows directly
-    if (PASS == 1) {
-      p.q0 = io.q(bd.qrow);
-      if (kind == K_SINCOS) p.q1 = io.q(bd.qrow + 1);
-    }
+    p.q0 = io.q(bd.qrow);                 // the joint angle is re-read (and sin/cos recomputed) in every pass:
+    if (kind == K_SINCOS) p.q1 = io.q(bd.qrow + 1);   // two stash rows per body buy ~40 % more resident warps
     p.qd = io.v(bd.vrow);
     if (PASS == 2 && io.tau.valid()) p.tau = io.tau(bd.vrow);
   }
+}
+
+// sin / cos / displacement of a 1-DoF joint from its prefetched configuration scalars
+template <class T> RBD_HD void joint_scd(int kind, const Pre<T>& pre, T& s, T& c, T& d) {
+  s = T(0); c = T(1); d = T(0);
+  if (kind == K_REV) sincos_t(pre.q0, s, c);
+  else if (kind == K_SINCOS) { s = pre.q0; c = pre.q1; }
+  else if (kind == K_PRIS) d = pre.q0;
 }
 
 // ---- pass 1 (outward): velocities ---------------------------------------------------------------------------------
@@ -552,15 +558,12 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
   T R[9], r[3];
   Mot<T> v;
   if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
-    T s = T(0), c = T(1), d = T(0), qd = T(0);
-    if (kind == K_REV) sincos_t(pre.q0, s, c);
-    else if (kind == K_SINCOS) { s = pre.q0; c = pre.q1; }
-    else if (kind == K_PRIS) d = pre.q0;
+    T s, c, d, qd = T(0);
+    joint_scd(kind, pre, s, c, d);
     if (kind != K_FIXED) qd = pre.qd;
     frame_1dof(bd, s, c, d, R, r);
     motion_to_child(R, r, vp, v);
     if (kind == K_PRIS) v.l[2] += qd; else if (kind != K_FIXED) v.w[2] += qd;
-    if (kind != K_FIXED) { st.st(bd.row0 + 6, kind == K_PRIS ? d : s); st.st(bd.row0 + 7, c); }
   } else {
     frame_multi(bd, io.q, R, r);
     motion_to_child(R, r, vp, v);
@@ -610,7 +613,8 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
     }
     return;
   }
-  const T sd = st.ld(bd.row0 + 6), c = st.ld(bd.row0 + 7);
+  T sn, c, dd;
+  joint_scd(kind, pre, sn, c, dd);
   const T qd = pre.qd;
   const T tau = pre.tau;
   if (kind != K_PRIS) {
@@ -644,7 +648,7 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
     b.f[1] = a.f[1] + b.B[1] * cax + b.B[4] * cay + b.C[1] * clx + b.C[3] * cly + Uly * du;
     b.f[2] = a.f[2] + b.B[2] * cax + b.B[5] * cay + b.C[2] * clx + b.C[4] * cly + Ulz * du;
     T R[9], r[3];
-    frame_1dof(bd, sd, c, T(0), R, r);
+    frame_1dof(bd, sn, c, T(0), R, r);
     Art<T> k;
     art_to_parent<T, true>(R, r, b, k);
     hand_over(M, bd, st, k, carry);
@@ -677,7 +681,7 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
     b.f[1] = a.f[1] + b.C[1] * clx + b.C[3] * cly + Uly * du;
     b.f[2] = a.f[2] + u;
     T R[9], r[3];
-    frame_1dof(bd, T(0), T(1), sd, R, r);
+    frame_1dof(bd, T(0), T(1), dd, R, r);
     Art<T> k;
     art_to_parent<T, false>(R, r, b, k);
     hand_over(M, bd, st, k, carry);
@@ -846,13 +850,14 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
     save_own_va(M, bd, st, v, xa);
     return;
   }
-  const T sd = st.ld(bd.row0 + 6), c = st.ld(bd.row0 + 7);
+  T sn, c, dd;
+  joint_scd(kind, pre, sn, c, dd);
   const T qd = pre.qd;
   const T t0 = st.ld(bd.row0 + 0), t1 = st.ld(bd.row0 + 1), t2 = st.ld(bd.row0 + 2), t3 = st.ld(bd.row0 + 3),
           t4 = st.ld(bd.row0 + 4), tu = st.ld(bd.row0 + 5);
   Mot<T> a;
   if (kind != K_PRIS) {
-    frame_1dof(bd, sd, c, T(0), R, r);
+    frame_1dof(bd, sn, c, T(0), R, r);
     motion_to_child(R, r, vp, v);
     motion_to_child(R, r, ap, xa);
     v.w[2] += qd;
@@ -862,7 +867,7 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
     a.w[0] = xa.w[0] + qd * v.w[1]; a.w[1] = xa.w[1] - qd * v.w[0]; a.w[2] = xa.w[2] + vd;
     a.l[0] = xa.l[0] + qd * v.l[1]; a.l[1] = xa.l[1] - qd * v.l[0]; a.l[2] = xa.l[2];
   } else {
-    frame_1dof(bd, T(0), T(1), sd, R, r);
+    frame_1dof(bd, T(0), T(1), dd, R, r);
     motion_to_child(R, r, vp, v);
     motion_to_child(R, r, ap, xa);
     v.l[2] += qd;

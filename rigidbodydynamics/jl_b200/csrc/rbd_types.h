@@ -29,7 +29,7 @@ enum BodyFlags : int32_t {
 };
 
 // Shared-memory "stash" rows per sample.  One row = one scalar per sample (lane); rows are private to a thread.
-constexpr int kRowsOneDof = 8;      // 6 (v, later U~ and u~) + 2 (sin, cos / prismatic displacement)
+constexpr int kRowsOneDof = 6;      // v between passes 1 and 2, then U~ (5 non-unit entries) and u~
 constexpr int kSlotRowsAba = 27;    // pending articulated inertia (21) + bias force (6); reused for (v, a) = 12
 constexpr int kSlotRowsRnea = 12;   // (v, a) outward; 6 for the inward wrench
 constexpr int kSlotRowsCrba = 10;   // composite rigid-body inertia (m, h, J)
