@@ -20,7 +20,7 @@
 #include <string>
 
 #include "../../../include/rbd_b200.h"
-#include "rbd_device.cuh"
+#include "rbd_rnea_crba.cuh"
 #include "rbd_model.h"
 
 using namespace rbd;
@@ -75,42 +75,111 @@ template <> const ModelDev<double>& dev_model<double>(const HostModel& m) { retu
 // ------------------------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Pull the NEXT group's input lines into L2 while this group is being computed (one 128-byte line per row and warp).
+template <class T>
+__device__ __forceinline__ void prefetch_rows(const T* base, int rows, int64_t ld, int64_t b0) {
+  if (!base) return;
+  for (int r = threadIdx.x & 31; r < rows; r += 32) prefetch_l2(base + (int64_t)r * ld + b0);
+}
+
 template <class T> struct AbaArgs {
   const T* q; const T* v; const T* tau; const T* wext;
   T* vd; T* qd;
+  T* scratch;            // [6 * nb][gridDim.x * NT] body-frame external wrenches (EXT only)
   int64_t ld, B;
 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <class T, int NT, bool GENERAL>
+template <class T, int NT, bool GENERAL, bool EXT>
 __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   const Stash<T, NT> st{sh + threadIdx.x};
   const int64_t ngroups = (a.B + NT - 1) / NT;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    {  // pull the NEXT group's input lines into L2 while this group is being computed (one 128-byte line per row)
-      const int64_t gn = g + gridDim.x;
-      if (gn < ngroups) {
-        const int64_t bn = gn * NT + (threadIdx.x & ~31);
-        const int lane = threadIdx.x & 31;
-        for (int r = lane; r < M.nq; r += 32) prefetch_l2(a.q + (int64_t)r * a.ld + bn);
-        for (int r = lane; r < M.nv; r += 32) prefetch_l2(a.v + (int64_t)r * a.ld + bn);
-        if (a.tau) for (int r = lane; r < M.nv; r += 32) prefetch_l2(a.tau + (int64_t)r * a.ld + bn);
-      }
+    const int64_t gn = g + gridDim.x;
+    if (gn < ngroups) {
+      const int64_t bn = gn * NT + (threadIdx.x & ~31);
+      prefetch_rows(a.q, M.nq, a.ld, bn);
+      prefetch_rows(a.v, M.nv, a.ld, bn);
+      prefetch_rows(a.tau, M.nv, a.ld, bn);
+      if (EXT) prefetch_rows(a.wext, 6 * M.nb, a.ld, bn);
     }
     const int64_t b = g * NT + threadIdx.x;
     const bool active = b < a.B;
     const int64_t bl = active ? b : a.B - 1;     // inactive lanes recompute the last sample, stores are masked
-    AbaIO<T> io;
+    AbaIO<T, EXT> io;
     io.q = {a.q + bl, a.ld};
     io.v = {a.v + bl, a.ld};
     io.tau = {a.tau ? a.tau + bl : nullptr, a.ld};
-    io.wext = {a.wext ? a.wext + bl : nullptr, a.ld};
+    io.wext = {EXT ? a.wext + bl : nullptr, a.ld};
     io.vd = {a.vd + bl, a.ld, active};
     io.qd = {a.qd ? a.qd + bl : nullptr, a.ld, active};
+    io.ext = {EXT ? a.scratch + (int64_t)blockIdx.x * NT + threadIdx.x : nullptr, (int64_t)gridDim.x * NT};
+    if (EXT) ext_wrench_pass(M, io.q, io.wext, io.ext, st, M.slot_base, kSlotRowsAba);
     aba_sample<T, NT, GENERAL>(M, io, st);
+  }
+}
+
+template <class T> struct RneaArgs {
+  const T* q; const T* v; const T* vd; const T* wext;
+  T* tau;
+  T* scratch;
+  int64_t ld, B;
+};
+
+template <class T, int NT, bool EXT>
+__global__ void __launch_bounds__(NT) rnea_kernel(const __grid_constant__ ModelDev<T> M, const RneaArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sh = reinterpret_cast<T*>(smem_raw);
+  const Stash<T, NT> st{sh + threadIdx.x};
+  const int64_t ngroups = (a.B + NT - 1) / NT;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t gn = g + gridDim.x;
+    if (gn < ngroups) {
+      const int64_t bn = gn * NT + (threadIdx.x & ~31);
+      prefetch_rows(a.q, M.nq, a.ld, bn);
+      prefetch_rows(a.v, M.nv, a.ld, bn);
+      prefetch_rows(a.vd, M.nv, a.ld, bn);
+      if (EXT) prefetch_rows(a.wext, 6 * M.nb, a.ld, bn);
+    }
+    const int64_t b = g * NT + threadIdx.x;
+    const bool active = b < a.B;
+    const int64_t bl = active ? b : a.B - 1;
+    RneaIO<T> io;
+    io.q = {a.q + bl, a.ld};
+    io.v = {a.v + bl, a.ld};
+    io.vd = {a.vd ? a.vd + bl : nullptr, a.ld};
+    io.wext = {EXT ? a.wext + bl : nullptr, a.ld};
+    io.tau = {a.tau + bl, a.ld, active};
+    io.ext = {EXT ? a.scratch + (int64_t)blockIdx.x * NT + threadIdx.x : nullptr, (int64_t)gridDim.x * NT};
+    rnea_sample<T, NT>(M, io, st);
+  }
+}
+
+template <class T> struct CrbaArgs {
+  const T* q;
+  T* M;
+  int64_t ld, B;
+};
+
+template <class T, int NT, int KMAX>
+__global__ void __launch_bounds__(NT) crba_kernel(const __grid_constant__ ModelDev<T> M, const CrbaArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sh = reinterpret_cast<T*>(smem_raw);
+  const Stash<T, NT> st{sh + threadIdx.x};
+  const int64_t ngroups = (a.B + NT - 1) / NT;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t gn = g + gridDim.x;
+    if (gn < ngroups) prefetch_rows(a.q, M.nq, a.ld, gn * NT + (threadIdx.x & ~31));
+    const int64_t b = g * NT + threadIdx.x;
+    const bool active = b < a.B;
+    const int64_t bl = active ? b : a.B - 1;
+    CrbaIO<T> io;
+    io.q = {a.q + bl, a.ld};
+    io.M = {a.M + bl, a.ld, active};
+    crba_sample<T, NT, KMAX>(M, io, st);
   }
 }
 
@@ -123,31 +192,76 @@ template <class K> int configure(K kernel, int nt, size_t smem, const DeviceProp
   return RBD_OK;
 }
 
-template <class T, bool GENERAL>
-int launch_aba(const HostModel& hm, const AbaArgs<T>& a, cudaStream_t stream) {
-  constexpr int NT = 32;
+template <class T> struct AbaArgs; template <class T> struct RneaArgs; template <class T> struct CrbaArgs;
+template <class T> void set_scratch(AbaArgs<T>& a, T* s);
+template <class T> void set_scratch(RneaArgs<T>& a, T* s);
+template <class T> void set_scratch(CrbaArgs<T>&, T*);
+
+// Launch `kernel` persistently (blocks_per_SM x SMs blocks looping over groups of NT samples).  `scratch_rows` > 0
+// requests a stream-ordered scratch of that many rows per resident thread (the external-wrench path).
+template <class T, class Kern, class Args>
+int launch(Kern kernel, const ModelDev<T>& M, Args a, int nt, int rows, int scratch_rows, cudaStream_t stream) {
   DeviceProps p;
   if (int rc = get_props(p)) return rc;
-  const ModelDev<T>& M = dev_model<T>(hm);
-  const size_t smem = (size_t)M.nrows * NT * sizeof(T);
-  auto kernel = aba_kernel<T, NT, GENERAL>;
+  const size_t smem = (size_t)rows * nt * sizeof(T);
   int bps = 0;
-  if (int rc = configure(kernel, NT, smem, p, bps)) return rc;
-  const int64_t ngroups = (a.B + NT - 1) / NT;
+  if (int rc = configure(kernel, nt, smem, p, bps)) return rc;
+  const int64_t ngroups = (a.B + nt - 1) / nt;
   const int grid = (int)std::min<int64_t>(ngroups, (int64_t)bps * p.sms);
-  kernel<<<grid, NT, smem, stream>>>(M, a);
-  CUDA_TRY(cudaGetLastError());
+  void* scratch = nullptr;
+  if (scratch_rows > 0) {
+    CUDA_TRY(cudaMallocAsync(&scratch, (size_t)scratch_rows * grid * nt * sizeof(T), stream));
+    set_scratch(a, (T*)scratch);
+  }
+  kernel<<<grid, nt, smem, stream>>>(M, a);
+  cudaError_t e = cudaGetLastError();
+  if (scratch) cudaFreeAsync(scratch, stream);
+  if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
   g_launch.kernels_launched += 1;
-  g_launch.grid = grid; g_launch.block = NT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
+  g_launch.grid = grid; g_launch.block = nt; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
   return RBD_OK;
 }
+template <class T> void set_scratch(AbaArgs<T>& a, T* s) { a.scratch = s; }
+template <class T> void set_scratch(RneaArgs<T>& a, T* s) { a.scratch = s; }
+template <class T> void set_scratch(CrbaArgs<T>&, T*) {}
+
+constexpr int kNT = 32;   // threads per block: one warp; warps never synchronise with each other
 
 template <class T>
 int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, const void* v, const void* tau,
                const void* wext, void* vd, void* qd, cudaStream_t stream) {
-  AbaArgs<T> a{(const T*)q, (const T*)v, (const T*)tau, (const T*)wext, (T*)vd, (T*)qd, ld, B};
-  if (wext) return fail(RBD_EUNSUPPORTED, "external wrenches: not implemented yet");
-  return model->hm.general ? launch_aba<T, true>(model->hm, a, stream) : launch_aba<T, false>(model->hm, a, stream);
+  const HostModel& hm = model->hm;
+  const ModelDev<T>& M = dev_model<T>(hm);
+  AbaArgs<T> a{(const T*)q, (const T*)v, (const T*)tau, (const T*)wext, (T*)vd, (T*)qd, nullptr, ld, B};
+  const int rows = M.nrows, sr = wext ? 6 * hm.nb : 0;
+  if (hm.general)
+    return wext ? launch<T>(aba_kernel<T, kNT, true, true>, M, a, kNT, rows, sr, stream)
+                : launch<T>(aba_kernel<T, kNT, true, false>, M, a, kNT, rows, sr, stream);
+  return wext ? launch<T>(aba_kernel<T, kNT, false, true>, M, a, kNT, rows, sr, stream)
+              : launch<T>(aba_kernel<T, kNT, false, false>, M, a, kNT, rows, sr, stream);
+}
+
+template <class T>
+int inverse_dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, const void* v, const void* vd,
+                       const void* wext, void* tau, cudaStream_t stream) {
+  const HostModel& hm = model->hm;
+  const ModelDev<T>& M = dev_model<T>(hm);
+  RneaArgs<T> a{(const T*)q, (const T*)v, (const T*)vd, (const T*)wext, (T*)tau, nullptr, ld, B};
+  const int rows = rnea_rows(hm);
+  return wext ? launch<T>(rnea_kernel<T, kNT, true>, M, a, kNT, rows, 6 * hm.nb, stream)
+              : launch<T>(rnea_kernel<T, kNT, false>, M, a, kNT, rows, 0, stream);
+}
+
+template <class T>
+int mass_matrix_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, void* Mout, cudaStream_t stream) {
+  const HostModel& hm = model->hm;
+  const ModelDev<T>& M = dev_model<T>(hm);
+  CrbaArgs<T> a{(const T*)q, (T*)Mout, ld, B};
+  const int rows = std::max(1, crba_rows(hm));
+  bool multi = false;
+  for (int i = 0; i < hm.nb; ++i) multi |= kind_nv(M.body[i].kind) > 1;
+  return multi ? launch<T>(crba_kernel<T, kNT, 6>, M, a, kNT, rows, 0, stream)
+               : launch<T>(crba_kernel<T, kNT, 1>, M, a, kNT, rows, 0, stream);
 }
 
 int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld) {
@@ -162,6 +276,82 @@ int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld) {
 // ------------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------------
+// ---- host-pointer variants: chunked H2D -> kernel -> D2H pipeline over three internal streams ----
+namespace {
+constexpr int64_t kChunk = 1 << 16;
+
+int ensure_staging(rbd_model* m, size_t bytes_per_stream) {
+  for (int i = 0; i < 3; ++i)
+    if (!m->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
+  if (!m->ev0) { CUDA_TRY(cudaEventCreate(&m->ev0)); CUDA_TRY(cudaEventCreate(&m->ev1)); }
+  if (m->stage_bytes >= bytes_per_stream) return RBD_OK;
+  for (int i = 0; i < 3; ++i) {
+    if (m->d_stage[i]) { cudaFree(m->d_stage[i]); m->d_stage[i] = nullptr; }
+    CUDA_TRY(cudaMalloc(&m->d_stage[i], bytes_per_stream));
+  }
+  m->stage_bytes = bytes_per_stream;
+  return RBD_OK;
+}
+
+// copy rows x C block between a host array with leading dimension ld and a dense device tile (leading dimension C)
+int copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, int rows, cudaMemcpyKind kind,
+              cudaStream_t s) {
+  CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, s));
+  return RBD_OK;
+}
+}  // namespace
+
+namespace {
+struct HostArr { const void* in; void* out; int rows; };
+
+// Chunked host pipeline: chunk c uses stream c % 3 and that stream's staging buffer; H2D copies, the kernel and the D2H
+// copies of one chunk are stream-ordered, chunks on different streams overlap (copy engines in both directions + SMs).
+template <class Launch>
+int host_pipeline(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const HostArr* ins, int nin, const HostArr* outs,
+                  int nout, Launch launch_chunk) {
+  std::lock_guard<std::mutex> lk(model->host_mu);
+  const size_t es = dtype == RBD_F32 ? 4 : 8;
+  const int64_t C = std::min<int64_t>(kChunk, B);
+  size_t rows_total = 0;
+  for (int i = 0; i < nin; ++i) rows_total += ins[i].in ? ins[i].rows : 0;
+  for (int i = 0; i < nout; ++i) rows_total += outs[i].out ? outs[i].rows : 0;
+  if (int rc = ensure_staging(model, rows_total * C * es)) return rc;
+  int launches = 0, nchunk = 0;
+  rbd_launch_info last = g_launch;
+  for (int64_t b0 = 0; b0 < B; b0 += C, ++nchunk) {
+    const int64_t n = std::min<int64_t>(C, B - b0);
+    const int si = nchunk % 3;
+    cudaStream_t s = model->streams[si];
+    char* cur = (char*)model->d_stage[si];
+    const size_t off = (size_t)b0 * es;
+    const void* din[8] = {nullptr};
+    void* dout[8] = {nullptr};
+    for (int i = 0; i < nin; ++i) {
+      if (!ins[i].in) continue;
+      din[i] = cur;
+      if (int rc = copy_rows(cur, C * es, (const char*)ins[i].in + off, ld * es, n * es, ins[i].rows, cudaMemcpyHostToDevice, s)) return rc;
+      cur += (size_t)ins[i].rows * C * es;
+    }
+    for (int i = 0; i < nout; ++i) {
+      if (!outs[i].out) continue;
+      dout[i] = cur;
+      cur += (size_t)outs[i].rows * C * es;
+    }
+    if (int rc = launch_chunk(n, C, din, dout, s)) return rc;
+    launches += g_launch.kernels_launched;
+    last = g_launch;
+    for (int i = 0; i < nout; ++i) {
+      if (!outs[i].out) continue;
+      if (int rc = copy_rows((char*)outs[i].out + off, ld * es, dout[i], C * es, n * es, outs[i].rows, cudaMemcpyDeviceToHost, s)) return rc;
+    }
+  }
+  for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamSynchronize(model->streams[i]));
+  g_launch = last;
+  g_launch.kernels_launched = launches;
+  return RBD_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int32_t rbd_version(void) { return RBD_B200_VERSION; }
@@ -247,113 +437,103 @@ int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t l
 int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                              const void* v, const void* vd, const void* wext, void* tau_out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  (void)q; (void)v; (void)vd; (void)wext; (void)tau_out; (void)stream;
-  return fail(RBD_EUNSUPPORTED, "rbd_inverse_dynamics: not implemented yet");
+  if (!q || !v || !vd || !tau_out) return fail(RBD_EINVAL, "rbd_inverse_dynamics: q, v, vd and tau_out must not be NULL");
+  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (B == 0) return RBD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == RBD_F32 ? inverse_dynamics_t<float>(model, B, ld, q, v, vd, wext, tau_out, s)
+                          : inverse_dynamics_t<double>(model, B, ld, q, v, vd, wext, tau_out, s);
 }
 
 int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                           const void* v, const void* wext, void* c_out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  (void)q; (void)v; (void)wext; (void)c_out; (void)stream;
-  return fail(RBD_EUNSUPPORTED, "rbd_dynamics_bias: not implemented yet");
+  if (!q || !v || !c_out) return fail(RBD_EINVAL, "rbd_dynamics_bias: q, v and c_out must not be NULL");
+  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (B == 0) return RBD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == RBD_F32 ? inverse_dynamics_t<float>(model, B, ld, q, v, nullptr, wext, c_out, s)
+                          : inverse_dynamics_t<double>(model, B, ld, q, v, nullptr, wext, c_out, s);
 }
 
 int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
                         void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  (void)q; (void)M_out; (void)stream;
-  return fail(RBD_EUNSUPPORTED, "rbd_mass_matrix: not implemented yet");
+  if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix: q and M_out must not be NULL");
+  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (B == 0) return RBD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == RBD_F32 ? mass_matrix_t<float>(model, B, ld, q, M_out, s) : mass_matrix_t<double>(model, B, ld, q, M_out, s);
 }
 
 // ---- host-pointer variants: chunked H2D -> kernel -> D2H pipeline over three internal streams -----------------------
-namespace {
-constexpr int64_t kChunk = 1 << 16;
 
-int ensure_staging(rbd_model* m, size_t bytes_per_stream) {
-  for (int i = 0; i < 3; ++i)
-    if (!m->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
-  if (!m->ev0) { CUDA_TRY(cudaEventCreate(&m->ev0)); CUDA_TRY(cudaEventCreate(&m->ev1)); }
-  if (m->stage_bytes >= bytes_per_stream) return RBD_OK;
-  for (int i = 0; i < 3; ++i) {
-    if (m->d_stage[i]) { cudaFree(m->d_stage[i]); m->d_stage[i] = nullptr; }
-    CUDA_TRY(cudaMalloc(&m->d_stage[i], bytes_per_stream));
-  }
-  m->stage_bytes = bytes_per_stream;
-  return RBD_OK;
-}
-
-// copy rows x C block between a host array with leading dimension ld and a dense device tile (leading dimension C)
-int copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, int rows, cudaMemcpyKind kind,
-              cudaStream_t s) {
-  CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, s));
-  return RBD_OK;
-}
-}  // namespace
 
 int32_t rbd_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                           const void* tau, const void* wext, void* vd_out, void* qd_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
   if (!q || !v || !vd_out) return fail(RBD_EINVAL, "rbd_dynamics_host: q, v and vd_out must not be NULL");
-  if (wext) return fail(RBD_EUNSUPPORTED, "external wrenches: not implemented yet");
   g_launch = {0, 0, 0, 0, 0, 0.f};
   if (B == 0) return RBD_OK;
-  std::lock_guard<std::mutex> lk(model->host_mu);
   const HostModel& hm = model->hm;
-  const size_t es = dtype == RBD_F32 ? 4 : 8;
-  const int64_t C = std::min<int64_t>(kChunk, B);
-  const int rows_in = hm.nq + hm.nv + (tau ? hm.nv : 0);
-  const int rows_out = hm.nv + (qd_out ? hm.nq : 0);
-  if (int rc = ensure_staging(model, (size_t)(rows_in + rows_out) * C * es)) return rc;
-  int launches = 0;
-  rbd_launch_info last = g_launch;
-  int nchunk = 0;
-  for (int64_t b0 = 0; b0 < B; b0 += C, ++nchunk) {
-    const int64_t n = std::min<int64_t>(C, B - b0);
-    const int si = nchunk % 3;
-    cudaStream_t s = model->streams[si];
-    char* base = (char*)model->d_stage[si];
-    char* dq = base;
-    char* dv = dq + (size_t)hm.nq * C * es;
-    char* dtau = dv + (size_t)hm.nv * C * es;
-    char* dvd = dtau + (size_t)(tau ? hm.nv : 0) * C * es;
-    char* dqd = dvd + (size_t)hm.nv * C * es;
-    const size_t off = (size_t)b0 * es;
-    if (int rc = copy_rows(dq, C * es, (const char*)q + off, ld * es, n * es, hm.nq, cudaMemcpyHostToDevice, s)) return rc;
-    if (int rc = copy_rows(dv, C * es, (const char*)v + off, ld * es, n * es, hm.nv, cudaMemcpyHostToDevice, s)) return rc;
-    if (tau)
-      if (int rc = copy_rows(dtau, C * es, (const char*)tau + off, ld * es, n * es, hm.nv, cudaMemcpyHostToDevice, s)) return rc;
-    int rc = dtype == RBD_F32
-                 ? dynamics_t<float>(model, n, C, dq, dv, tau ? dtau : nullptr, nullptr, dvd, qd_out ? dqd : nullptr, s)
-                 : dynamics_t<double>(model, n, C, dq, dv, tau ? dtau : nullptr, nullptr, dvd, qd_out ? dqd : nullptr, s);
-    if (rc) return rc;
-    launches += 1;
-    last = g_launch;
-    if (int rc2 = copy_rows((char*)vd_out + off, ld * es, dvd, C * es, n * es, hm.nv, cudaMemcpyDeviceToHost, s)) return rc2;
-    if (qd_out)
-      if (int rc2 = copy_rows((char*)qd_out + off, ld * es, dqd, C * es, n * es, hm.nq, cudaMemcpyDeviceToHost, s)) return rc2;
-  }
-  for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamSynchronize(model->streams[i]));
-  g_launch = last;
-  g_launch.kernels_launched = launches;
-  return RBD_OK;
+  const HostArr ins[4] = {{q, nullptr, hm.nq}, {v, nullptr, hm.nv}, {tau, nullptr, hm.nv}, {wext, nullptr, 6 * hm.nb}};
+  const HostArr outs[2] = {{nullptr, vd_out, hm.nv}, {nullptr, qd_out, hm.nq}};
+  return host_pipeline(model, dtype, B, ld, ins, 4, outs, 2,
+                       [&](int64_t n, int64_t C, const void** di, void** dq, cudaStream_t s) {
+                         g_launch.kernels_launched = 0;
+                         return dtype == RBD_F32 ? dynamics_t<float>(model, n, C, di[0], di[1], di[2], di[3], dq[0], dq[1], s)
+                                                 : dynamics_t<double>(model, n, C, di[0], di[1], di[2], di[3], dq[0], dq[1], s);
+                       });
 }
 
 int32_t rbd_inverse_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                                   const void* v, const void* vd, const void* wext, void* tau_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  (void)q; (void)v; (void)vd; (void)wext; (void)tau_out;
-  return fail(RBD_EUNSUPPORTED, "rbd_inverse_dynamics_host: not implemented yet");
+  if (!q || !v || !vd || !tau_out) return fail(RBD_EINVAL, "rbd_inverse_dynamics_host: q, v, vd and tau_out must not be NULL");
+  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (B == 0) return RBD_OK;
+  const HostModel& hm = model->hm;
+  const HostArr ins[4] = {{q, nullptr, hm.nq}, {v, nullptr, hm.nv}, {vd, nullptr, hm.nv}, {wext, nullptr, 6 * hm.nb}};
+  const HostArr outs[1] = {{nullptr, tau_out, hm.nv}};
+  return host_pipeline(model, dtype, B, ld, ins, 4, outs, 1,
+                       [&](int64_t n, int64_t C, const void** di, void** dq, cudaStream_t s) {
+                         g_launch.kernels_launched = 0;
+                         return dtype == RBD_F32 ? inverse_dynamics_t<float>(model, n, C, di[0], di[1], di[2], di[3], dq[0], s)
+                                                 : inverse_dynamics_t<double>(model, n, C, di[0], di[1], di[2], di[3], dq[0], s);
+                       });
 }
+
 int32_t rbd_dynamics_bias_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                                const void* v, const void* wext, void* c_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  (void)q; (void)v; (void)wext; (void)c_out;
-  return fail(RBD_EUNSUPPORTED, "rbd_dynamics_bias_host: not implemented yet");
+  if (!q || !v || !c_out) return fail(RBD_EINVAL, "rbd_dynamics_bias_host: q, v and c_out must not be NULL");
+  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (B == 0) return RBD_OK;
+  const HostModel& hm = model->hm;
+  const HostArr ins[3] = {{q, nullptr, hm.nq}, {v, nullptr, hm.nv}, {wext, nullptr, 6 * hm.nb}};
+  const HostArr outs[1] = {{nullptr, c_out, hm.nv}};
+  return host_pipeline(model, dtype, B, ld, ins, 3, outs, 1,
+                       [&](int64_t n, int64_t C, const void** di, void** dq, cudaStream_t s) {
+                         g_launch.kernels_launched = 0;
+                         return dtype == RBD_F32 ? inverse_dynamics_t<float>(model, n, C, di[0], di[1], nullptr, di[2], dq[0], s)
+                                                 : inverse_dynamics_t<double>(model, n, C, di[0], di[1], nullptr, di[2], dq[0], s);
+                       });
 }
+
 int32_t rbd_mass_matrix_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  (void)q; (void)M_out;
-  return fail(RBD_EUNSUPPORTED, "rbd_mass_matrix_host: not implemented yet");
+  if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix_host: q and M_out must not be NULL");
+  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (B == 0) return RBD_OK;
+  const HostModel& hm = model->hm;
+  const HostArr ins[1] = {{q, nullptr, hm.nq}};
+  const HostArr outs[1] = {{nullptr, M_out, hm.nv * hm.nv}};
+  return host_pipeline(model, dtype, B, ld, ins, 1, outs, 1,
+                       [&](int64_t n, int64_t C, const void** di, void** dq, cudaStream_t s) {
+                         g_launch.kernels_launched = 0;
+                         return dtype == RBD_F32 ? mass_matrix_t<float>(model, n, C, di[0], dq[0], s)
+                                                 : mass_matrix_t<double>(model, n, C, di[0], dq[0], s);
+                       });
 }
 
 }  // extern "C"

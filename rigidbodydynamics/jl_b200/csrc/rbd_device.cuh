@@ -122,6 +122,15 @@ template <class T> struct ColOut {
   RBD_HD bool valid() const { return p != nullptr; }
 };
 
+// Read-write view of one sample's column in a global scratch array (same rows x batch layout).
+template <class T> struct Scr {
+  T* p;
+  int64_t ld;
+  RBD_HD T get(int row) const { return p[(int64_t)row * ld]; }
+  RBD_HD void st(int row, T v) const { p[(int64_t)row * ld] = v; }
+  RBD_HD bool valid() const { return p != nullptr; }
+};
+
 // ------------------------------------------------------------------------------------------------------------------
 // 3-vector helpers on plain arrays (constant indices only => registers)
 // ------------------------------------------------------------------------------------------------------------------
@@ -546,20 +555,28 @@ template <class T> RBD_HD void motion_cross(const Mot<T>& v, const Mot<T>& j, Mo
 // ==================================================================================================================
 // Articulated-Body Algorithm
 // ==================================================================================================================
-template <class T> struct AbaIO {
-  Col<T> q, v, tau, wext;   // tau / wext may be invalid (NULL): zero torques / no external wrenches
+template <class T, bool EXT = false> struct AbaIO {
+  static constexpr bool kExt = EXT;   // external wrenches present (compile-time so the common path carries no extra state)
+  Col<T> q, v, tau, wext;   // tau may be invalid (NULL): zero torques
   ColOut<T> vd, qd;         // qd may be invalid
+  Scr<T> ext;               // [6 * nb] body-frame external wrenches, written by ext_wrench_pass (EXT only)
 };
 
 // Scalars of one 1-DoF body that come from global memory.  They are requested one body AHEAD of their use (software
 // pipelining in aba_sample) so the load latency overlaps the previous body's arithmetic instead of stalling the warp.
-template <class T> struct Pre { T q0, q1, qd, tau; };
-template <class T, int PASS>
-RBD_HD void prefetch_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, Pre<T>& p) {
+template <class T> struct Pre { T q0, q1, qd, tau; T w[6]; };
+template <class T, int PASS, class IO>
+RBD_HD void prefetch_body(const ModelDev<T>& M, int i, const IO& io, Pre<T>& p) {
   p.q0 = T(0); p.q1 = T(0); p.qd = T(0); p.tau = T(0);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) p.w[k] = T(0);
   if (i < 0 || i >= M.nb) return;
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
+  if (PASS == 2 && IO::kExt) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p.w[k] = io.ext.get(6 * i + k);
+  }
   if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS) {     // multi-DoF bodies read their rows directly
     p.q0 = io.q(bd.qrow);                 // the joint angle is re-read (and sin/cos recomputed) in every pass:
     if (kind == K_SINCOS) p.q1 = io.q(bd.qrow + 1);   // two stash rows per body buy ~40 % more resident warps
@@ -577,8 +594,8 @@ template <class T> RBD_HD void joint_scd(int kind, const Pre<T>& pre, T& s, T& c
 }
 
 // ---- pass 1 (outward): velocities ---------------------------------------------------------------------------------
-template <class T, int STRIDE, bool GENERAL>
-RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Mot<T>& vcur,
+template <class T, int STRIDE, bool GENERAL, class IO>
+RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Mot<T>& vcur,
                            const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   Mot<T> vp;
@@ -624,8 +641,8 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
 // ---- pass 2 (inward): articulated inertias ------------------------------------------------------------------------
 // 1-DoF / fixed body.  On exit the body's rows hold U~ (5 non-unit entries) and u~; `carry` / the parent's slot hold
 // its contribution to the parent.
-template <class T, int STRIDE>
-RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Art<T>& carry,
+template <class T, int STRIDE, class IO>
+RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Art<T>& carry,
                            const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
@@ -635,8 +652,9 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
   Art<T> a;
   art_set_body(bd, a);
   bias_force(bd, v, a.n, a.f);
-  if (io.wext.valid()) {
-    // external wrench in BODY coordinates was prepared by pass 1 in the wext scratch rows (see aba_sample)
+  if (IO::kExt) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a.n[k] -= pre.w[k]; a.f[k] -= pre.w[3 + k]; }   // - w_ext in body coordinates
   }
   if (!(bd.flags & F_LEAF)) art_add(a, carry);
   if (bd.flags & F_HAS_PENDING) art_add_from(st, M.slot_base + bd.oslot * kSlotRowsAba, a);
@@ -728,8 +746,8 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
 
 // Multi-DoF body (K = 3 or 6, one-hot subspace).  ROOT0 = preorder position 0 under the world: nothing is stored or
 // propagated; instead the joint acceleration is solved right away and the outward pass starts from registers.
-template <class T, int STRIDE, int K, int FAM, bool ROOT0>
-RBD_HD void aba_pass2_multi(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Art<T>& carry,
+template <class T, int STRIDE, int K, int FAM, bool ROOT0, class IO>
+RBD_HD void aba_pass2_multi(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Art<T>& carry,
                             Mot<T>& vout, Mot<T>& aout) {
   const BodyDev<T>& bd = M.body[i];
   constexpr int ck = FAM;   // subspace index family: K_PLANAR, or K_QFLOAT (spherical = first 3 of floating)
@@ -739,6 +757,10 @@ RBD_HD void aba_pass2_multi(const ModelDev<T>& M, int i, const AbaIO<T>& io, con
   Art<T> a;
   art_set_body(bd, a);
   bias_force(bd, v, a.n, a.f);
+  if (IO::kExt) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a.n[k] -= io.ext.get(6 * i + k); a.f[k] -= io.ext.get(6 * i + 3 + k); }
+  }
   if (!(bd.flags & F_LEAF)) art_add(a, carry);
   if (bd.flags & F_HAS_PENDING) art_add_from(st, M.slot_base + bd.oslot * kSlotRowsAba, a);
   T I[6][6], p[6];
@@ -872,8 +894,8 @@ RBD_HD void save_own_va(const ModelDev<T>& M, const BodyDev<T>& bd, const Stash<
   }
 }
 
-template <class T, int STRIDE>
-RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Mot<T>& vcur, Mot<T>& acur,
+template <class T, int STRIDE, class IO>
+RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Mot<T>& vcur, Mot<T>& acur,
                            const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
@@ -919,8 +941,8 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const AbaIO<T>& io, cons
   save_own_va(M, bd, st, v, a);
 }
 
-template <class T, int STRIDE, int K, int FAM>
-RBD_HD void aba_pass3_multi(const ModelDev<T>& M, int i, const AbaIO<T>& io, const Stash<T, STRIDE>& st, Mot<T>& vcur, Mot<T>& acur) {
+template <class T, int STRIDE, int K, int FAM, class IO>
+RBD_HD void aba_pass3_multi(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Mot<T>& vcur, Mot<T>& acur) {
   const BodyDev<T>& bd = M.body[i];
   constexpr int ck = FAM;
   Mot<T> vp, ap, v, xa;
@@ -957,8 +979,8 @@ RBD_HD void aba_pass3_multi(const ModelDev<T>& M, int i, const AbaIO<T>& io, con
 
 // ---- whole algorithm for one sample -------------------------------------------------------------------------------
 // GENERAL = false: bodies 1..nb-1 are 1-DoF or fixed (multi-DoF joint allowed only at position 0 under the world).
-template <class T, int STRIDE, bool GENERAL>
-RBD_HD void aba_sample(const ModelDev<T>& M, const AbaIO<T>& io, const Stash<T, STRIDE>& st) {
+template <class T, int STRIDE, bool GENERAL, class IO>
+RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const Stash<T, STRIDE>& st) {
   const int nb = M.nb;
   Mot<T> vcur, acur;
 #pragma unroll

@@ -27,7 +27,7 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
 
 // Stash rows per sample for the three kernels.
 inline int aba_rows(const HostModel& m) { return m.dev64.nrows; }
-inline int rnea_rows(const HostModel& m) { return m.nb * 8 + m.nslots * kSlotRowsRnea; }
+inline int rnea_rows(const HostModel& m) { return m.nb * 6 + m.nslots * kSlotRowsRnea; }
 inline int crba_rows(const HostModel& m) { return m.nb * 2 + m.nslots * kSlotRowsCrba; }
 
 }  // namespace rbd

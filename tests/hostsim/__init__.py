@@ -54,3 +54,31 @@ def dynamics(desc, q, v, tau=None, wext=None, want_qd=False):
     rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(v), _p(tau), _p(wext), _p(vd), _p(qd))
     assert rc == 0, rc
     return (vd, qd) if want_qd else vd
+
+
+def inverse_dynamics(desc, q, v, vd=None, wext=None):
+    dt = q.dtype
+    d, keep = make_desc(desc)
+    q = np.ascontiguousarray(q); v = np.ascontiguousarray(v, dt)
+    vd = None if vd is None else np.ascontiguousarray(vd, dt)
+    wext = None if wext is None else np.ascontiguousarray(wext, dt)
+    B = q.shape[1]
+    tau = np.empty((desc.nv, B), dt)
+    fn = lib().hostsim_inverse_dynamics
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc), ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 5
+    rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(v), _p(vd), _p(wext), _p(tau))
+    assert rc == 0, rc
+    return tau
+
+
+def mass_matrix(desc, q):
+    dt = q.dtype
+    d, keep = make_desc(desc)
+    q = np.ascontiguousarray(q)
+    B = q.shape[1]
+    M = np.full((desc.nv * desc.nv, B), np.nan, dt)
+    fn = lib().hostsim_mass_matrix
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc), ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 2
+    rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(M))
+    assert rc == 0, rc
+    return M

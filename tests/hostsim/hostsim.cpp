@@ -5,7 +5,7 @@
 #include <string>
 #include <vector>
 
-#include "../../rigidbodydynamics/jl_b200/csrc/rbd_device.cuh"
+#include "../../rigidbodydynamics/jl_b200/csrc/rbd_rnea_crba.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_model.h"
 
 using namespace rbd;
@@ -15,18 +15,53 @@ template <class T> const ModelDev<T>& dev(const HostModel& m);
 template <> const ModelDev<float>& dev<float>(const HostModel& m) { return m.dev32; }
 template <> const ModelDev<double>& dev<double>(const HostModel& m) { return m.dev64; }
 
-template <class T>
-void run_dynamics(const HostModel& hm, int64_t B, const T* q, const T* v, const T* tau, const T* wext, T* vd, T* qd) {
+template <class T, bool EXT>
+void run_dynamics_e(const HostModel& hm, int64_t B, const T* q, const T* v, const T* tau, const T* wext, T* vd, T* qd) {
   const ModelDev<T>& M = dev<T>(hm);
-  std::vector<T> stash(M.nrows + 64);
+  std::vector<T> stash(M.nrows + 64), scratch(6 * M.nb);
   for (int64_t b = 0; b < B; ++b) {
-    AbaIO<T> io;
+    AbaIO<T, EXT> io;
     io.q = {q + b, B}; io.v = {v + b, B};
-    io.tau = {tau ? tau + b : nullptr, B}; io.wext = {wext ? wext + b : nullptr, B};
+    io.tau = {tau ? tau + b : nullptr, B}; io.wext = {EXT ? wext + b : nullptr, B};
     io.vd = {vd + b, B, true}; io.qd = {qd ? qd + b : nullptr, B, true};
+    io.ext = {EXT ? scratch.data() : nullptr, 1};
     Stash<T, 1> st{stash.data()};
+    if (EXT) ext_wrench_pass(M, io.q, io.wext, io.ext, st, M.slot_base, kSlotRowsAba);
     if (hm.general) aba_sample<T, 1, true>(M, io, st);
     else aba_sample<T, 1, false>(M, io, st);
+  }
+}
+template <class T>
+void run_dynamics(const HostModel& hm, int64_t B, const T* q, const T* v, const T* tau, const T* wext, T* vd, T* qd) {
+  if (wext) run_dynamics_e<T, true>(hm, B, q, v, tau, wext, vd, qd);
+  else run_dynamics_e<T, false>(hm, B, q, v, tau, wext, vd, qd);
+}
+
+template <class T>
+void run_rnea(const HostModel& hm, int64_t B, const T* q, const T* v, const T* vd, const T* wext, T* tau) {
+  const ModelDev<T>& M = dev<T>(hm);
+  std::vector<T> stash(rnea_rows(hm) + 64), scratch(6 * M.nb);
+  for (int64_t b = 0; b < B; ++b) {
+    RneaIO<T> io;
+    io.q = {q + b, B}; io.v = {v + b, B}; io.vd = {vd ? vd + b : nullptr, B};
+    io.wext = {wext ? wext + b : nullptr, B};
+    io.tau = {tau + b, B, true};
+    io.ext = {wext ? scratch.data() : nullptr, 1};
+    rnea_sample<T, 1>(M, io, Stash<T, 1>{stash.data()});
+  }
+}
+
+template <class T> void run_crba(const HostModel& hm, int64_t B, const T* q, T* Mout) {
+  const ModelDev<T>& M = dev<T>(hm);
+  std::vector<T> stash(crba_rows(hm) + 64);
+  bool multi = false;
+  for (int i = 0; i < M.nb; ++i) multi |= kind_nv(M.body[i].kind) > 1;
+  for (int64_t b = 0; b < B; ++b) {
+    CrbaIO<T> io;
+    io.q = {q + b, B};
+    io.M = {Mout + b, B, true};
+    if (multi) crba_sample<T, 1, 6>(M, io, Stash<T, 1>{stash.data()});
+    else crba_sample<T, 1, 1>(M, io, Stash<T, 1>{stash.data()});
   }
 }
 }  // namespace
@@ -47,6 +82,23 @@ int hostsim_dynamics(const rbd_model_desc* d, int dtype, int64_t B, const void* 
   if (rc) return rc;
   if (dtype == 0) run_dynamics<float>(hm, B, (const float*)q, (const float*)v, (const float*)tau, (const float*)wext, (float*)vd, (float*)qd);
   else run_dynamics<double>(hm, B, (const double*)q, (const double*)v, (const double*)tau, (const double*)wext, (double*)vd, (double*)qd);
+  return 0;
+}
+int hostsim_inverse_dynamics(const rbd_model_desc* d, int dtype, int64_t B, const void* q, const void* v, const void* vd,
+                             const void* wext, void* tau) {
+  HostModel hm; std::string err;
+  int rc = build_host_model(d, hm, err);
+  if (rc) return rc;
+  if (dtype == 0) run_rnea<float>(hm, B, (const float*)q, (const float*)v, (const float*)vd, (const float*)wext, (float*)tau);
+  else run_rnea<double>(hm, B, (const double*)q, (const double*)v, (const double*)vd, (const double*)wext, (double*)tau);
+  return 0;
+}
+int hostsim_mass_matrix(const rbd_model_desc* d, int dtype, int64_t B, const void* q, void* M) {
+  HostModel hm; std::string err;
+  int rc = build_host_model(d, hm, err);
+  if (rc) return rc;
+  if (dtype == 0) run_crba<float>(hm, B, (const float*)q, (float*)M);
+  else run_crba<double>(hm, B, (const double*)q, (double*)M);
   return 0;
 }
 }

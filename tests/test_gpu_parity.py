@@ -124,3 +124,98 @@ def test_full_size_properties(built):
     ref = Oracle(mech.flatten()).dynamics(sub.q.double().cpu().numpy(), sub.v.double().cpu().numpy(),
                                           tau[:, idx].double().cpu().numpy())
     assert rel_err(res2.vd.double().cpu().numpy(), ref) < 2e-5
+
+
+def _state(mech, q, v, dtype):
+    st = rbd.MechanismState(mech, q.shape[1], dtype)
+    st.q.copy_(torch.from_numpy(q).to(dtype)); st.v.copy_(torch.from_numpy(v).to(dtype))
+    return st
+
+
+def _cu(a, dtype):
+    return None if a is None else torch.from_numpy(a).to(dtype).cuda()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name,floating", [("atlas", True), ("atlas", False), ("iiwa14", False), ("double_pendulum", False)])
+def test_inverse_dynamics_bias_mass_matrix(built, name, floating, dtype):
+    """inverse_dynamics!, dynamics_bias!, mass_matrix! (+ external wrenches) vs the oracle.  fp32 tolerance 2e-5 relative."""
+    mech = rbd.load_model(name, floating=floating)
+    o = Oracle(mech.flatten())
+    q, v, tau, vd, w = rand_inputs(mech, 130, 31, wext=True)
+    st = _state(mech, q, v, dtype)
+    tol = TOL[dtype]
+    for wext in (None, w):
+        got = rbd.inverse_dynamics(st, _cu(vd, dtype), _cu(wext, dtype)).double().cpu().numpy()
+        assert rel_err(got, o.inverse_dynamics(q, v, vd, wext)) < tol
+        got = rbd.dynamics_bias(st, _cu(wext, dtype)).double().cpu().numpy()
+        assert rel_err(got, o.dynamics_bias(q, v, wext)) < tol
+        res = rbd.DynamicsResult(mech, q.shape[1], dtype)
+        rbd.dynamics_(res, st, _cu(tau, dtype), _cu(wext, dtype))
+        assert rel_err(res.vd.double().cpu().numpy(), o.dynamics(q, v, tau, wext)) < tol
+    M = rbd.mass_matrix(st).double().cpu().numpy()
+    assert rel_err(M, o.mass_matrix(q)) < tol
+
+
+def test_quickstart_closed_form_values_gpu(built):
+    """Config 1 numbers through the CUDA path: M, c, inverse dynamics of the examples/1 pendulum."""
+    from tests.util import double_pendulum
+    mech = double_pendulum()
+    st = _state(mech, np.array([[0.3], [0.4]]), np.array([[1.0], [2.0]]), torch.float64)
+    M = rbd.mass_matrix(st).cpu().numpy().reshape(2, 2)
+    assert np.allclose(M, [[2.587060994002885, 0.7935304970014425], [0.7935304970014425, 0.333]], atol=1e-12)
+    assert np.allclose(rbd.dynamics_bias(st).cpu().numpy().ravel(), [5.950794227687885, 3.3545969270552], atol=1e-12)
+    vd = torch.tensor([[1.0], [2.0]], dtype=torch.float64, device="cuda")
+    assert np.allclose(rbd.inverse_dynamics(st, vd).cpu().numpy().ravel(), [10.124916215693656, 4.814127424056642], atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_general_trees_rnea_crba_wext(built, seed):
+    mech = randmech(seed, shuffle=seed % 2 == 1)
+    o = Oracle(mech.flatten())
+    q, v, tau, vd, w = rand_inputs(mech, 40, seed, wext=True)
+    st = _state(mech, q, v, torch.float64)
+    assert rel_err(rbd.inverse_dynamics(st, _cu(vd, torch.float64), _cu(w, torch.float64)).cpu().numpy(),
+                   o.inverse_dynamics(q, v, vd, w)) < 1e-10
+    assert rel_err(rbd.mass_matrix(st).cpu().numpy(), o.mass_matrix(q)) < 1e-10
+    res = rbd.DynamicsResult(mech, q.shape[1], torch.float64)
+    rbd.dynamics_(res, st, _cu(tau, torch.float64), _cu(w, torch.float64))
+    assert rel_err(res.vd.cpu().numpy(), o.dynamics(q, v, tau, w)) < 1e-9
+
+
+def test_identities_at_scale_fp32(built):
+    """Reference identities at a large batch (2^17, fp32, iiwa14 = config 3): FD o ID round trip and M v̇ + c = tau."""
+    mech = rbd.load_model("iiwa14")
+    B = 1 << 17
+    st = rbd.MechanismState(mech, B, torch.float32)
+    rbd.rand_(st, np.random.default_rng(7))
+    tau = torch.rand((7, B), dtype=torch.float32, device="cuda")
+    res = rbd.DynamicsResult(mech, B, torch.float32)
+    rbd.dynamics_(res, st, tau)
+    back = rbd.inverse_dynamics(st, res.vd)
+    scale = 1 + tau.abs().amax(0) + back.abs().amax(0)
+    assert float(((back - tau).abs().amax(0) / scale).max()) < 1e-3
+    M = rbd.mass_matrix(st).reshape(7, 7, B)
+    c = rbd.dynamics_bias(st)
+    resid = torch.einsum("jib,jb->ib", M, res.vd) + c - tau
+    assert float((resid.abs().amax(0) / scale).max()) < 1e-3
+    assert bool(torch.equal(M, M.transpose(0, 1)))
+
+
+def test_host_entry_points_rnea_crba(built):
+    mech = rbd.load_model("iiwa14")
+    lib = rbd.load_library()
+    B = 70000
+    q, v, tau, vd, _ = rand_inputs(mech, 50, 5)
+    reps = -(-B // 50)
+    q, v, vd = (np.tile(a, (1, reps))[:, :B].copy() for a in (q, v, vd))
+    st = _state(mech, q, v, torch.float32)
+    ref_tau = rbd.inverse_dynamics(st, _cu(vd, torch.float32)).cpu()
+    ref_M = rbd.mass_matrix(st).cpu()
+    hq, hv, hvd = (torch.from_numpy(a).float().pin_memory() for a in (q, v, vd))
+    out = torch.empty((7, B), dtype=torch.float32).pin_memory()
+    rbd._cabi.check(lib.rbd_inverse_dynamics_host(st.handle.ptr, 0, B, B, hq.data_ptr(), hv.data_ptr(), hvd.data_ptr(), None, out.data_ptr()))
+    assert torch.equal(out, ref_tau)
+    outM = torch.empty((49, B), dtype=torch.float32).pin_memory()
+    rbd._cabi.check(lib.rbd_mass_matrix_host(st.handle.ptr, 0, B, B, hq.data_ptr(), outM.data_ptr()))
+    assert torch.equal(outM, ref_M)

@@ -57,3 +57,44 @@ def test_aba_single_joint_type_chains(jt):
     d = mech.flatten()
     q, v, tau, _, _ = rand_inputs(mech, 4, 9)
     assert rel_err(hostsim.dynamics(d, q, v, tau), Oracle(d).dynamics(q, v, tau)) < 1e-10
+
+
+@pytest.mark.parametrize("name,floating", MODELS)
+def test_rnea_crba_wext_match_oracle(name, floating):
+    """inverse_dynamics!, dynamics_bias!, mass_matrix! and external wrenches (root-frame wrench on every body, as in
+    perf/runbenchmarks.jl:49-67) through the device code."""
+    mech = rbd.load_model(name, floating=floating)
+    d = mech.flatten()
+    o = Oracle(d)
+    q, v, tau, vd, w = rand_inputs(mech, 7, 29, wext=True)
+    assert rel_err(hostsim.inverse_dynamics(d, q, v, vd), o.inverse_dynamics(q, v, vd)) < 1e-13
+    assert rel_err(hostsim.inverse_dynamics(d, q, v, vd, w), o.inverse_dynamics(q, v, vd, w)) < 1e-13
+    assert rel_err(hostsim.inverse_dynamics(d, q, v, None, w), o.dynamics_bias(q, v, w)) < 1e-13
+    M = hostsim.mass_matrix(d, q)
+    assert not np.isnan(M).any()                 # every entry written, including the structural zeros
+    assert rel_err(M, o.mass_matrix(q)) < 1e-13
+    assert rel_err(hostsim.dynamics(d, q, v, tau, w), o.dynamics(q, v, tau, w)) < 1e-10
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_rnea_crba_wext_general_trees(seed):
+    mech = randmech(seed, shuffle=seed % 2 == 1)
+    d = mech.flatten()
+    o = Oracle(d)
+    q, v, tau, vd, w = rand_inputs(mech, 4, seed, wext=True)
+    assert rel_err(hostsim.inverse_dynamics(d, q, v, vd, w), o.inverse_dynamics(q, v, vd, w)) < 1e-12
+    M = hostsim.mass_matrix(d, q)
+    assert not np.isnan(M).any() and rel_err(M, o.mass_matrix(q)) < 1e-12
+    assert rel_err(hostsim.dynamics(d, q, v, tau, w), o.dynamics(q, v, tau, w)) < 1e-10
+
+
+def test_device_identities_fd_id_roundtrip():
+    """dynamics / inverse dynamics round trip (test_mechanism_algorithms.jl:729-740) and M v̇ + c = tau, device code only."""
+    mech = rbd.load_model("atlas", floating=True)
+    d = mech.flatten()
+    q, v, tau, _, w = rand_inputs(mech, 5, 40, wext=True)
+    acc = hostsim.dynamics(d, q, v, tau, w)
+    assert np.abs(hostsim.inverse_dynamics(d, q, v, acc, w) - tau).max() < 1e-9
+    M = hostsim.mass_matrix(d, q).reshape(d.nv, d.nv, -1)
+    c = hostsim.inverse_dynamics(d, q, v, None, w)
+    assert np.abs(np.einsum("jib,jb->ib", M, acc) + c - tau).max() < 1e-8
