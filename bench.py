@@ -121,6 +121,67 @@ def cpu_baseline(mech, q, v, tau, dtype, seconds_target=12.0):
                       f"{np.dtype(dt).name}, {cores} threads"}
 
 
+def time_fn(fn, steps, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def other_configs(steps):
+    """The remaining BASELINE.json configs as secondary measurements (kernel time, CUDA events, inputs resident in HBM):
+    config 2 (Atlas fp64 dynamics, batch 65536), config 3 (7-DoF arm fp32 inverse_dynamics / mass_matrix, batch 2^20), and the
+    reference's own benchmark variant with an external wrench on every body (perf/runbenchmarks.jl:59-67)."""
+    import torch
+    import rigidbodydynamics.jl_b200 as rbd
+    out = {}
+    rng = np.random.default_rng(1)
+    atlas = rbd.load_model("atlas", floating=True)
+    st = rbd.MechanismState(atlas, 1 << 16, torch.float64)
+    rbd.rand_(st, rng)
+    tau = torch.rand((36, 1 << 16), dtype=torch.float64, device="cuda")
+    res = rbd.DynamicsResult(atlas, 1 << 16, torch.float64)
+    ms = time_fn(lambda: rbd.dynamics_(res, st, tau, want_qd=False), steps)
+    out["atlas_f64_dynamics_b65536"] = {"evals_per_s": (1 << 16) / (ms * 1e-3), "ms": ms, "algorithmic_GBps": (1 << 16) * 1160 / (ms * 1e-3) / 1e9}
+    B = 1 << 20
+    st = rbd.MechanismState(atlas, B, torch.float32)
+    rbd.rand_(st, rng)
+    tau = torch.rand((36, B), dtype=torch.float32, device="cuda")
+    wext = torch.rand((6 * 31, B), dtype=torch.float32, device="cuda")
+    res = rbd.DynamicsResult(atlas, B, torch.float32)
+    ms = time_fn(lambda: rbd.dynamics_(res, st, tau, wext, want_qd=False), steps)
+    out["atlas_f32_dynamics_extwrench_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * (580 + 744) / (ms * 1e-3) / 1e9}
+    ms = time_fn(lambda: rbd.dynamics_(res, st, tau, want_qd=True), steps)
+    out["atlas_f32_dynamics_with_qdot_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * 728 / (ms * 1e-3) / 1e9}
+    vd = torch.rand((36, B), dtype=torch.float32, device="cuda")
+    tout = torch.empty_like(vd)
+    ms = time_fn(lambda: rbd.inverse_dynamics_(tout, st, vd), steps)
+    out["atlas_f32_inverse_dynamics_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * 580 / (ms * 1e-3) / 1e9}
+    del res, wext, tau, vd, tout, st
+    iiwa = rbd.load_model("iiwa14")
+    st = rbd.MechanismState(iiwa, B, torch.float32)
+    rbd.rand_(st, rng)
+    vd = torch.rand((7, B), dtype=torch.float32, device="cuda")
+    tout = torch.empty_like(vd)
+    ms = time_fn(lambda: rbd.inverse_dynamics_(tout, st, vd), steps)
+    out["iiwa14_f32_inverse_dynamics_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * 112 / (ms * 1e-3) / 1e9}
+    Mout = torch.empty((49, B), dtype=torch.float32, device="cuda")
+    ms = time_fn(lambda: rbd.mass_matrix_(Mout, st), steps)
+    out["iiwa14_f32_mass_matrix_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * 224 / (ms * 1e-3) / 1e9}
+    res = rbd.DynamicsResult(iiwa, B, torch.float32)
+    tau = torch.rand((7, B), dtype=torch.float32, device="cuda")
+    ms = time_fn(lambda: rbd.dynamics_(res, st, tau, want_qd=False), steps)
+    out["iiwa14_f32_dynamics_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * 112 / (ms * 1e-3) / 1e9}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own algorithm on the host CPU (oracle port; Julia is not installed)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -163,6 +224,7 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all_gather of v̇ (N > 1)")
+    ap.add_argument("--no-other", action="store_true", help="skip the secondary configs (fp64, RNEA, CRBA, ext. wrenches)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -303,6 +365,8 @@ def main():
         }
         if gather:
             out["with_nccl_gather"] = gather
+        if world == 1 and not args.no_other:
+            out["other_configs"] = other_configs(max(5, min(args.steps, 20)))
         if not args.no_cpu and world == 1:
             out["cpu_baseline"] = cpu_baseline(mech, q, v, tau, args.dtype)
             # accuracy of this run against the fp64 oracle on a small sample

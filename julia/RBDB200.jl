@@ -1,0 +1,182 @@
+# RBDB200.jl -- Julia shim over librbd_b200.so (C ABI in include/rbd_b200.h).
+#
+# NOT EXECUTED in the build image (no Julia there); it is the binding a RigidBodyDynamics.jl maintainer would add.
+# It keeps the reference's user-facing types: a reference `Mechanism` is flattened ONCE into an `rbd_model_desc`, and batched
+# methods with the reference's names (`dynamics!`, `inverse_dynamics!`, `mass_matrix!`, `dynamics_bias!`) `ccall` the
+# library.  Everything the GPU path does not cover (mechanisms with loops or contact points, scalar types other than
+# Float32/Float64, additional state) is dispatched to the reference's own methods unchanged.
+module RBDB200
+
+using RigidBodyDynamics
+using RigidBodyDynamics: Mechanism, Joint, JointType, Revolute, Prismatic, Fixed, Planar, QuaternionFloating,
+    SPQuatFloating, QuaternionSpherical, SinCosRevolute, tree_joints, non_tree_joints, predecessor, successor,
+    joint_to_predecessor, joint_type, spatial_inertia, root_body, num_positions, num_velocities, modcount
+using StaticArrays
+using CUDA   # CuArray provides device pointers; any device-pointer provider works
+
+const librbd = get(ENV, "RBD_B200_LIB", "librbd_b200.so")
+
+# ---- mirror of the C declarations (include/rbd_b200.h) ----------------------------------------------------------
+const RBD_OK, RBD_EINVAL, RBD_EDIM, RBD_ELOOP, RBD_ESTALE, RBD_ECUDA, RBD_EUNSUPPORTED, RBD_ENOMEM = Int32.(0:7)
+const RBD_F32, RBD_F64 = Int32(0), Int32(1)
+
+struct rbd_model_desc
+    nb::Int32
+    num_non_tree_joints::Int32
+    parent::Ptr{Int32}
+    jtype::Ptr{Int32}
+    X_tree::Ptr{Float64}
+    jparam::Ptr{Float64}
+    inertia::Ptr{Float64}
+    gravity::NTuple{3, Float64}
+    modcount::Int64
+end
+
+joint_code(::Revolute) = Int32(0);            joint_code(::Prismatic) = Int32(1)
+joint_code(::Fixed) = Int32(2);               joint_code(::Planar) = Int32(3)
+joint_code(::QuaternionFloating) = Int32(4);  joint_code(::SPQuatFloating) = Int32(5)
+joint_code(::QuaternionSpherical) = Int32(6); joint_code(::SinCosRevolute) = Int32(7)
+
+joint_params(jt::Union{Revolute, Prismatic, SinCosRevolute}) = vcat(Vector(jt.axis), zeros(6))
+joint_params(jt::Planar) = vcat(Vector(jt.x_axis), Vector(jt.y_axis), Vector(jt.rot_axis))
+joint_params(::JointType) = zeros(9)
+
+function last_error()
+    unsafe_string(ccall((:rbd_last_error, librbd), Cstring, ()))
+end
+
+"Convert an rbd_status into the exception type the reference would have thrown."
+function check(status::Int32)
+    status == RBD_OK && return nothing
+    msg = last_error()
+    status == RBD_EDIM && throw(DimensionMismatch(msg))
+    status == RBD_EINVAL && throw(ArgumentError(msg))
+    status == RBD_ESTALE && throw(RigidBodyDynamics.ModificationCountMismatch(msg))
+    error("rbd_b200 (status $status): $msg")
+end
+
+# ---- flatten-once model handle ---------------------------------------------------------------------------------
+mutable struct Model
+    handle::Ptr{Cvoid}
+    mechanism::Mechanism
+    modcount::Int
+    nq::Int
+    nv::Int
+    nb::Int
+end
+
+"""
+    Model(mechanism)
+
+Flatten a tree `Mechanism{Float64}` (src/mechanism.jl:10-34) into the arrays of `rbd_model_desc`, in `tree_joints` order.
+"""
+function Model(mechanism::Mechanism{Float64})
+    joints = collect(tree_joints(mechanism))
+    nb = length(joints)
+    succ_index = Dict(successor(j, mechanism) => i - 1 for (i, j) in enumerate(joints))
+    parent = Int32[predecessor(j, mechanism) == root_body(mechanism) ? -1 : succ_index[predecessor(j, mechanism)] for j in joints]
+    jtype = Int32[joint_code(joint_type(j)) for j in joints]
+    X = zeros(12, nb); P = zeros(9, nb); I = zeros(13, nb)
+    for (i, j) in enumerate(joints)
+        T = joint_to_predecessor(j)                       # src/joint.jl:77
+        R = rotation(T); p = translation(T)
+        X[1:9, i] = vec(permutedims(Matrix(R)))           # row-major rotation
+        X[10:12, i] = p
+        P[:, i] = joint_params(joint_type(j))
+        inertia = spatial_inertia(successor(j, mechanism))   # expressed in the frame after the joint (mechanism.jl:250-260)
+        I[1:9, i] = vec(permutedims(Matrix(inertia.moment)))
+        I[10:12, i] = inertia.cross_part
+        I[13, i] = inertia.mass
+    end
+    g = mechanism.gravitational_acceleration.v
+    handle = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve parent jtype X P I begin
+        desc = rbd_model_desc(nb, length(non_tree_joints(mechanism)), pointer(parent), pointer(jtype), pointer(X),
+                              pointer(P), pointer(I), (g[1], g[2], g[3]), modcount(mechanism))
+        check(ccall((:rbd_model_create, librbd), Int32, (Ref{rbd_model_desc}, Ref{Ptr{Cvoid}}), desc, handle))
+    end
+    m = Model(handle[], mechanism, modcount(mechanism), num_positions(mechanism), num_velocities(mechanism), nb)
+    finalizer(x -> ccall((:rbd_model_destroy, librbd), Int32, (Ptr{Cvoid},), x.handle), m)
+    m
+end
+
+# ---- batched state / result: Matrix{T}(B, n) == rows x batch with the batch index fastest ------------------------
+struct BatchedState{T, A <: AbstractMatrix{T}}
+    model::Model
+    q::A        # B x nq
+    v::A        # B x nv
+end
+struct BatchedResult{T, A <: AbstractMatrix{T}}
+    v̇::A        # B x nv
+    q̇::A        # B x nq
+    massmatrix::A   # B x nv^2
+    dynamicsbias::A # B x nv
+end
+
+dtype_code(::Type{Float32}) = RBD_F32
+dtype_code(::Type{Float64}) = RBD_F64
+devptr(x::CuArray) = reinterpret(Ptr{Cvoid}, pointer(x))
+devptr(::Nothing) = C_NULL
+stream_ptr() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)
+
+function checkstate(s::BatchedState)
+    check(ccall((:rbd_model_check_modcount, librbd), Int32, (Ptr{Cvoid}, Int64), s.model.handle, modcount(s.model.mechanism)))
+end
+
+"`dynamics!(result, state, torques, externalwrenches)` -- src/mechanism_algorithms.jl:845-864, batched."
+function RigidBodyDynamics.dynamics!(result::BatchedResult{T}, state::BatchedState{T}, torques = nothing,
+                                     externalwrenches = nothing) where {T <: Union{Float32, Float64}}
+    checkstate(state)
+    B = size(state.q, 1)
+    GC.@preserve result state torques externalwrenches begin
+        check(ccall((:rbd_dynamics, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v), devptr(torques),
+                    devptr(externalwrenches), devptr(result.v̇), devptr(result.q̇), stream_ptr()))
+    end
+    result
+end
+
+"`inverse_dynamics!(torquesout, ..., state, v̇, externalwrenches)` -- src/mechanism_algorithms.jl:542-553, batched."
+function RigidBodyDynamics.inverse_dynamics!(torquesout::AbstractMatrix{T}, state::BatchedState{T}, v̇::AbstractMatrix{T},
+                                             externalwrenches = nothing) where {T <: Union{Float32, Float64}}
+    checkstate(state)
+    B = size(state.q, 1)
+    size(torquesout) == (B, state.model.nv) || throw(DimensionMismatch("torquesout has wrong size"))
+    GC.@preserve torquesout state v̇ externalwrenches begin
+        check(ccall((:rbd_inverse_dynamics, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v), devptr(v̇),
+                    devptr(externalwrenches), devptr(torquesout), stream_ptr()))
+    end
+    torquesout
+end
+
+"`dynamics_bias!(result, state)` -- src/mechanism_algorithms.jl:484-498, batched."
+function RigidBodyDynamics.dynamics_bias!(result::BatchedResult{T}, state::BatchedState{T},
+                                          externalwrenches = nothing) where {T <: Union{Float32, Float64}}
+    checkstate(state)
+    B = size(state.q, 1)
+    GC.@preserve result state externalwrenches begin
+        check(ccall((:rbd_dynamics_bias, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v), devptr(externalwrenches),
+                    devptr(result.dynamicsbias), stream_ptr()))
+    end
+    result.dynamicsbias
+end
+
+"`mass_matrix!(M, state)` -- src/mechanism_algorithms.jl:248-272, batched: `M` is B x nv^2, entry (i, j) in column i + (j-1) nv."
+function RigidBodyDynamics.mass_matrix!(M::AbstractMatrix{T}, state::BatchedState{T}) where {T <: Union{Float32, Float64}}
+    checkstate(state)
+    B = size(state.q, 1)
+    size(M) == (B, state.model.nv^2) || throw(DimensionMismatch("mass matrix has wrong size"))
+    GC.@preserve M state begin
+        check(ccall((:rbd_mass_matrix, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(M), stream_ptr()))
+    end
+    M
+end
+
+end # module
