@@ -14,10 +14,12 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include "../../../include/rbd_b200.h"
 #include "rbd_rnea_crba.cuh"
@@ -62,6 +64,13 @@ int get_props(DeviceProps& p) {
   CUDA_TRY(cudaDeviceGetAttribute(&q.sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&q.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&q.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+  {  // scratch for slots / external wrenches comes from the stream-ordered pool: keep freed blocks cached in the pool
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   q.ok = true;
   if (dev >= 0 && dev < 64) cache[dev] = q;
   p = q;
@@ -91,11 +100,21 @@ template <class T> struct AbaArgs {
   int64_t ld, B;
 };
 
-template <class T, int NT, bool GENERAL, bool EXT>
+// GSLOT: pending slots in the global scratch (rows [ext_rows, ext_rows + nslots * 27) of the per-thread scratch column),
+// body rows in shared memory.
+template <class T, int NT, bool GENERAL, bool EXT, bool GSLOT>
 __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
-  const Stash<T, NT> st{sh + threadIdx.x};
+  using ST = typename std::conditional<GSLOT, StashGS<T, NT>, Stash<T, NT>>::type;
+  const int64_t nthreads = (int64_t)gridDim.x * NT;
+  const int64_t tid = (int64_t)blockIdx.x * NT + threadIdx.x;
+  ST st;
+  if constexpr (GSLOT) {
+    st = ST{sh + threadIdx.x, a.scratch + (EXT ? 6 * M.nb : 0) * nthreads + tid, nthreads, M.slot_base};
+  } else {
+    st = ST{sh + threadIdx.x};
+  }
   const int64_t ngroups = (a.B + NT - 1) / NT;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t gn = g + gridDim.x;
@@ -116,9 +135,37 @@ __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDe
     io.wext = {EXT ? a.wext + bl : nullptr, a.ld};
     io.vd = {a.vd + bl, a.ld, active};
     io.qd = {a.qd ? a.qd + bl : nullptr, a.ld, active};
-    io.ext = {EXT ? a.scratch + (int64_t)blockIdx.x * NT + threadIdx.x : nullptr, (int64_t)gridDim.x * NT};
+    io.ext = {EXT ? a.scratch + tid : nullptr, nthreads};
     if (EXT) ext_wrench_pass(M, io.q, io.wext, io.ext, st, M.slot_base, kSlotRowsAba);
-    aba_sample<T, NT, GENERAL>(M, io, st);
+    aba_sample<T, ST, GENERAL>(M, io, st);
+  }
+}
+
+// Experimental variant: the stash lives in global memory (L2-resident scratch), occupancy is register-limited.
+template <class T, int NT, bool GENERAL>
+__global__ void __launch_bounds__(NT) aba_kernel_gstash(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
+  const Stash<T, 0> st{a.scratch + (int64_t)blockIdx.x * NT + threadIdx.x, (int64_t)gridDim.x * NT};
+  const int64_t ngroups = (a.B + NT - 1) / NT;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t gn = g + gridDim.x;
+    if (gn < ngroups) {
+      const int64_t bn = gn * NT + (threadIdx.x & ~31);
+      prefetch_rows(a.q, M.nq, a.ld, bn);
+      prefetch_rows(a.v, M.nv, a.ld, bn);
+      prefetch_rows(a.tau, M.nv, a.ld, bn);
+    }
+    const int64_t b = g * NT + threadIdx.x;
+    const bool active = b < a.B;
+    const int64_t bl = active ? b : a.B - 1;
+    AbaIO<T, false> io;
+    io.q = {a.q + bl, a.ld};
+    io.v = {a.v + bl, a.ld};
+    io.tau = {a.tau ? a.tau + bl : nullptr, a.ld};
+    io.wext = {nullptr, a.ld};
+    io.vd = {a.vd + bl, a.ld, active};
+    io.qd = {a.qd ? a.qd + bl : nullptr, a.ld, active};
+    io.ext = {nullptr, 0};
+    aba_sample<T, Stash<T, 0>, GENERAL>(M, io, st);
   }
 }
 
@@ -233,12 +280,19 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   const HostModel& hm = model->hm;
   const ModelDev<T>& M = dev_model<T>(hm);
   AbaArgs<T> a{(const T*)q, (const T*)v, (const T*)tau, (const T*)wext, (T*)vd, (T*)qd, nullptr, ld, B};
-  const int rows = M.nrows, sr = wext ? 6 * hm.nb : 0;
-  if (hm.general)
-    return wext ? launch<T>(aba_kernel<T, kNT, true, true>, M, a, kNT, rows, sr, stream)
-                : launch<T>(aba_kernel<T, kNT, true, false>, M, a, kNT, rows, sr, stream);
-  return wext ? launch<T>(aba_kernel<T, kNT, false, true>, M, a, kNT, rows, sr, stream)
-              : launch<T>(aba_kernel<T, kNT, false, false>, M, a, kNT, rows, sr, stream);
+  // Pending slots go to the global scratch when that buys at least one more resident warp per SM.
+  const bool gslot = M.nslots > 0 && !getenv("RBD_SMEM_SLOTS");
+  const int rows = gslot ? M.slot_base : M.nrows;
+  const int sr = (wext ? 6 * hm.nb : 0) + (gslot ? M.nslots * kSlotRowsAba : 0);
+  if (!wext && !hm.general && getenv("RBD_GSTASH")) return launch<T>(aba_kernel_gstash<T, kNT, false>, M, a, kNT, 0, M.nrows, stream);
+#define RBD_ABA(G, E, S) launch<T>(aba_kernel<T, kNT, G, E, S>, M, a, kNT, rows, sr, stream)
+  if (hm.general) {
+    if (wext) return gslot ? RBD_ABA(true, true, true) : RBD_ABA(true, true, false);
+    return gslot ? RBD_ABA(true, false, true) : RBD_ABA(true, false, false);
+  }
+  if (wext) return gslot ? RBD_ABA(false, true, true) : RBD_ABA(false, true, false);
+  return gslot ? RBD_ABA(false, false, true) : RBD_ABA(false, false, false);
+#undef RBD_ABA
 }
 
 template <class T>

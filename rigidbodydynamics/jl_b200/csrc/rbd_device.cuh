@@ -99,6 +99,34 @@ template <class T, int STRIDE> struct Stash {
   RBD_HD T ld(int row) const { return p[row * STRIDE]; }
   RBD_HD void st(int row, T v) const { p[row * STRIDE] = v; }
   RBD_HD void add(int row, T v) const { p[row * STRIDE] += v; }
+  RBD_HD const Stash& slots() const { return *this; }     // pending slots live in the same array
+};
+// STRIDE == 0: runtime stride (the stash lives in a global-memory scratch, one column per resident thread)
+template <class T> struct Stash<T, 0> {
+  T* p;
+  int64_t stride;
+  RBD_HD T ld(int row) const { return p[(int64_t)row * stride]; }
+  RBD_HD void st(int row, T v) const { p[(int64_t)row * stride] = v; }
+  RBD_HD void add(int row, T v) const { p[(int64_t)row * stride] += v; }
+  RBD_HD const Stash& slots() const { return *this; }
+};
+// Body rows in shared memory ([row][lane]); the pending slots -- touched only a handful of times per sample -- in a
+// global scratch column that stays L2-resident.  Frees 2 x 27 rows of shared memory per sample on Atlas (7 -> 9 warps/SM).
+template <class T, int STRIDE> struct StashGS {
+  T* p;
+  T* g;               // slot row r of this thread at g[(r - slot_base) * gstride]
+  int64_t gstride;
+  int slot_base;
+  RBD_HD T ld(int row) const { return p[row * STRIDE]; }
+  RBD_HD void st(int row, T v) const { p[row * STRIDE] = v; }
+  RBD_HD void add(int row, T v) const { p[row * STRIDE] += v; }
+  struct Slots {
+    T* g; int64_t gstride; int base;
+    RBD_HD T ld(int row) const { return g[(int64_t)(row - base) * gstride]; }
+    RBD_HD void st(int row, T v) const { g[(int64_t)(row - base) * gstride] = v; }
+    RBD_HD void add(int row, T v) const { g[(int64_t)(row - base) * gstride] += v; }
+  };
+  RBD_HD Slots slots() const { return Slots{g, gstride, slot_base}; }
 };
 
 // Read-only view of one sample's column in a rows x batch array (element (k, b) at base[k * ld + b]).
@@ -358,7 +386,7 @@ template <class T> RBD_HD void art_add(Art<T>& a, const Art<T>& b) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) { a.n[k] += b.n[k]; a.f[k] += b.f[k]; }
 }
-template <class T, int STRIDE> RBD_HD void art_store(const Stash<T, STRIDE>& st, int row, const Art<T>& a) {
+template <class T, class S> RBD_HD void art_store(const S& st, int row, const Art<T>& a) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) { st.st(row + k, a.A[k]); st.st(row + 15 + k, a.C[k]); }
 #pragma unroll
@@ -366,15 +394,22 @@ template <class T, int STRIDE> RBD_HD void art_store(const Stash<T, STRIDE>& st,
 #pragma unroll
   for (int k = 0; k < 3; ++k) { st.st(row + 21 + k, a.n[k]); st.st(row + 24 + k, a.f[k]); }
 }
-template <class T, int STRIDE> RBD_HD void art_accum(const Stash<T, STRIDE>& st, int row, const Art<T>& a) {
+template <class T, class S> RBD_HD void art_accum(const S& st, int row, const Art<T>& a) {
+  // all loads first, then all stores: a store to the stash may alias a later load as far as the compiler can tell, and
+  // interleaving them would serialise 27 memory round trips
+  T t[27];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { st.add(row + k, a.A[k]); st.add(row + 15 + k, a.C[k]); }
+  for (int k = 0; k < 27; ++k) t[k] = st.ld(row + k);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) st.add(row + 6 + k, a.B[k]);
+  for (int k = 0; k < 6; ++k) { t[k] += a.A[k]; t[15 + k] += a.C[k]; }
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { st.add(row + 21 + k, a.n[k]); st.add(row + 24 + k, a.f[k]); }
+  for (int k = 0; k < 9; ++k) t[6 + k] += a.B[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { t[21 + k] += a.n[k]; t[24 + k] += a.f[k]; }
+#pragma unroll
+  for (int k = 0; k < 27; ++k) st.st(row + k, t[k]);
 }
-template <class T, int STRIDE> RBD_HD void art_add_from(const Stash<T, STRIDE>& st, int row, Art<T>& a) {
+template <class T, class S> RBD_HD void art_add_from(const S& st, int row, Art<T>& a) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) { a.A[k] += st.ld(row + k); a.C[k] += st.ld(row + 15 + k); }
 #pragma unroll
@@ -470,14 +505,14 @@ template <class T, bool ZAZ> RBD_HD void art_to_parent(const T* R, const T* r, c
 }
 
 // Hand a finished child contribution to its parent: registers (first child), or the parent's pending slot.
-template <class T, int STRIDE>
-RBD_HD void hand_over(const ModelDev<T>& M, const BodyDev<T>& bd, const Stash<T, STRIDE>& st, const Art<T>& k, Art<T>& carry) {
+template <class T, class ST>
+RBD_HD void hand_over(const ModelDev<T>& M, const BodyDev<T>& bd, const ST& st, const Art<T>& k, Art<T>& carry) {
   if (bd.flags & F_FIRST_CHILD) {
     carry = k;
   } else {
     const int row = M.slot_base + bd.pslot * kSlotRowsAba;
-    if (bd.flags & F_SLOT_INIT) art_store(st, row, k);
-    else art_accum(st, row, k);
+    if (bd.flags & F_SLOT_INIT) art_store(st.slots(), row, k);
+    else art_accum(st.slots(), row, k);
   }
 }
 
@@ -594,8 +629,8 @@ template <class T> RBD_HD void joint_scd(int kind, const Pre<T>& pre, T& s, T& c
 }
 
 // ---- pass 1 (outward): velocities ---------------------------------------------------------------------------------
-template <class T, int STRIDE, bool GENERAL, class IO>
-RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Mot<T>& vcur,
+template <class T, class ST, bool GENERAL, class IO>
+RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const ST& st, Mot<T>& vcur,
                            const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   Mot<T> vp;
@@ -641,8 +676,8 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const Stas
 // ---- pass 2 (inward): articulated inertias ------------------------------------------------------------------------
 // 1-DoF / fixed body.  On exit the body's rows hold U~ (5 non-unit entries) and u~; `carry` / the parent's slot hold
 // its contribution to the parent.
-template <class T, int STRIDE, class IO>
-RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Art<T>& carry,
+template <class T, class ST, class IO>
+RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& st, Art<T>& carry,
                            const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
@@ -657,7 +692,7 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const Stas
     for (int k = 0; k < 3; ++k) { a.n[k] -= pre.w[k]; a.f[k] -= pre.w[3 + k]; }   // - w_ext in body coordinates
   }
   if (!(bd.flags & F_LEAF)) art_add(a, carry);
-  if (bd.flags & F_HAS_PENDING) art_add_from(st, M.slot_base + bd.oslot * kSlotRowsAba, a);
+  if (bd.flags & F_HAS_PENDING) art_add_from(st.slots(), M.slot_base + bd.oslot * kSlotRowsAba, a);
 
   if (kind == K_FIXED) {
     if (!(bd.flags & F_ROOT_CHILD)) {
@@ -746,8 +781,8 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const Stas
 
 // Multi-DoF body (K = 3 or 6, one-hot subspace).  ROOT0 = preorder position 0 under the world: nothing is stored or
 // propagated; instead the joint acceleration is solved right away and the outward pass starts from registers.
-template <class T, int STRIDE, int K, int FAM, bool ROOT0, class IO>
-RBD_HD void aba_pass2_multi(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Art<T>& carry,
+template <class T, class ST, int K, int FAM, bool ROOT0, class IO>
+RBD_HD void aba_pass2_multi(const ModelDev<T>& M, int i, const IO& io, const ST& st, Art<T>& carry,
                             Mot<T>& vout, Mot<T>& aout) {
   const BodyDev<T>& bd = M.body[i];
   constexpr int ck = FAM;   // subspace index family: K_PLANAR, or K_QFLOAT (spherical = first 3 of floating)
@@ -762,7 +797,7 @@ RBD_HD void aba_pass2_multi(const ModelDev<T>& M, int i, const IO& io, const Sta
     for (int k = 0; k < 3; ++k) { a.n[k] -= io.ext.get(6 * i + k); a.f[k] -= io.ext.get(6 * i + 3 + k); }
   }
   if (!(bd.flags & F_LEAF)) art_add(a, carry);
-  if (bd.flags & F_HAS_PENDING) art_add_from(st, M.slot_base + bd.oslot * kSlotRowsAba, a);
+  if (bd.flags & F_HAS_PENDING) art_add_from(st.slots(), M.slot_base + bd.oslot * kSlotRowsAba, a);
   T I[6][6], p[6];
   art_to_full(a, I, p);
   T x[6];
@@ -865,8 +900,8 @@ RBD_HD void aba_pass2_multi(const ModelDev<T>& M, int i, const IO& io, const Sta
 }
 
 // ---- pass 3 (outward): accelerations ------------------------------------------------------------------------------
-template <class T, int STRIDE>
-RBD_HD void load_parent_va(const ModelDev<T>& M, const BodyDev<T>& bd, const Stash<T, STRIDE>& st, const Mot<T>& vcur,
+template <class T, class ST>
+RBD_HD void load_parent_va(const ModelDev<T>& M, const BodyDev<T>& bd, const ST& st, const Mot<T>& vcur,
                            const Mot<T>& acur, Mot<T>& vp, Mot<T>& ap) {
   if (bd.flags & F_ROOT_CHILD) {
 #pragma unroll
@@ -875,27 +910,29 @@ RBD_HD void load_parent_va(const ModelDev<T>& M, const BodyDev<T>& bd, const Sta
     vp = vcur; ap = acur;
   } else {
     const int row = M.slot_base + bd.pslot * kSlotRowsAba;
+    const auto sl = st.slots();
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      vp.w[k] = st.ld(row + k); vp.l[k] = st.ld(row + 3 + k);
-      ap.w[k] = st.ld(row + 6 + k); ap.l[k] = st.ld(row + 9 + k);
+      vp.w[k] = sl.ld(row + k); vp.l[k] = sl.ld(row + 3 + k);
+      ap.w[k] = sl.ld(row + 6 + k); ap.l[k] = sl.ld(row + 9 + k);
     }
   }
 }
-template <class T, int STRIDE>
-RBD_HD void save_own_va(const ModelDev<T>& M, const BodyDev<T>& bd, const Stash<T, STRIDE>& st, const Mot<T>& v, const Mot<T>& a) {
+template <class T, class ST>
+RBD_HD void save_own_va(const ModelDev<T>& M, const BodyDev<T>& bd, const ST& st, const Mot<T>& v, const Mot<T>& a) {
   if (bd.flags & F_HAS_PENDING) {
     const int row = M.slot_base + bd.oslot * kSlotRowsAba;
+    const auto sl = st.slots();
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      st.st(row + k, v.w[k]); st.st(row + 3 + k, v.l[k]);
-      st.st(row + 6 + k, a.w[k]); st.st(row + 9 + k, a.l[k]);
+      sl.st(row + k, v.w[k]); sl.st(row + 3 + k, v.l[k]);
+      sl.st(row + 6 + k, a.w[k]); sl.st(row + 9 + k, a.l[k]);
     }
   }
 }
 
-template <class T, int STRIDE, class IO>
-RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Mot<T>& vcur, Mot<T>& acur,
+template <class T, class ST, class IO>
+RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& st, Mot<T>& vcur, Mot<T>& acur,
                            const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
@@ -941,8 +978,8 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const IO& io, const Stas
   save_own_va(M, bd, st, v, a);
 }
 
-template <class T, int STRIDE, int K, int FAM, class IO>
-RBD_HD void aba_pass3_multi(const ModelDev<T>& M, int i, const IO& io, const Stash<T, STRIDE>& st, Mot<T>& vcur, Mot<T>& acur) {
+template <class T, class ST, int K, int FAM, class IO>
+RBD_HD void aba_pass3_multi(const ModelDev<T>& M, int i, const IO& io, const ST& st, Mot<T>& vcur, Mot<T>& acur) {
   const BodyDev<T>& bd = M.body[i];
   constexpr int ck = FAM;
   Mot<T> vp, ap, v, xa;
@@ -979,8 +1016,8 @@ RBD_HD void aba_pass3_multi(const ModelDev<T>& M, int i, const IO& io, const Sta
 
 // ---- whole algorithm for one sample -------------------------------------------------------------------------------
 // GENERAL = false: bodies 1..nb-1 are 1-DoF or fixed (multi-DoF joint allowed only at position 0 under the world).
-template <class T, int STRIDE, bool GENERAL, class IO>
-RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const Stash<T, STRIDE>& st) {
+template <class T, class ST, bool GENERAL, class IO>
+RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
   const int nb = M.nb;
   Mot<T> vcur, acur;
 #pragma unroll
@@ -990,7 +1027,7 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const Stash<T, STRIDE
   prefetch_body<T, 1>(M, 0, io, cur);
   for (int i = 0; i < nb; ++i) {
     prefetch_body<T, 1>(M, i + 1, io, nxt);
-    aba_pass1_body<T, STRIDE, GENERAL>(M, i, io, st, vcur, cur);
+    aba_pass1_body<T, ST, GENERAL>(M, i, io, st, vcur, cur);
     cur = nxt;
   }
   // pass 2
@@ -1010,11 +1047,11 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const Stash<T, STRIDE
     if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass2_1dof(M, i, io, st, carry, now);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
-      aba_pass2_multi<T, STRIDE, 6, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
+      aba_pass2_multi<T, ST, 6, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
     } else if (kind == K_PLANAR) {
-      aba_pass2_multi<T, STRIDE, 3, K_PLANAR, false>(M, i, io, st, carry, vcur, acur);
+      aba_pass2_multi<T, ST, 3, K_PLANAR, false>(M, i, io, st, carry, vcur, acur);
     } else {
-      aba_pass2_multi<T, STRIDE, 3, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
+      aba_pass2_multi<T, ST, 3, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
     }
   }
   // body 0: inward step, then the outward pass starts here
@@ -1027,13 +1064,13 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const Stash<T, STRIDE
       aba_pass2_1dof(M, 0, io, st, carry, cur);
       aba_pass3_1dof(M, 0, io, st, vcur, acur, cur);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
-      aba_pass2_multi<T, STRIDE, 6, K_QFLOAT, true>(M, 0, io, st, carry, vcur, acur);
+      aba_pass2_multi<T, ST, 6, K_QFLOAT, true>(M, 0, io, st, carry, vcur, acur);
       save_own_va(M, b0, st, vcur, acur);
     } else if (kind == K_PLANAR) {
-      aba_pass2_multi<T, STRIDE, 3, K_PLANAR, true>(M, 0, io, st, carry, vcur, acur);
+      aba_pass2_multi<T, ST, 3, K_PLANAR, true>(M, 0, io, st, carry, vcur, acur);
       save_own_va(M, b0, st, vcur, acur);
     } else {
-      aba_pass2_multi<T, STRIDE, 3, K_QFLOAT, true>(M, 0, io, st, carry, vcur, acur);
+      aba_pass2_multi<T, ST, 3, K_QFLOAT, true>(M, 0, io, st, carry, vcur, acur);
       save_own_va(M, b0, st, vcur, acur);
     }
     (void)root0;
@@ -1048,11 +1085,11 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const Stash<T, STRIDE
     if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass3_1dof(M, i, io, st, vcur, acur, now);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
-      aba_pass3_multi<T, STRIDE, 6, K_QFLOAT>(M, i, io, st, vcur, acur);
+      aba_pass3_multi<T, ST, 6, K_QFLOAT>(M, i, io, st, vcur, acur);
     } else if (kind == K_PLANAR) {
-      aba_pass3_multi<T, STRIDE, 3, K_PLANAR>(M, i, io, st, vcur, acur);
+      aba_pass3_multi<T, ST, 3, K_PLANAR>(M, i, io, st, vcur, acur);
     } else {
-      aba_pass3_multi<T, STRIDE, 3, K_QFLOAT>(M, i, io, st, vcur, acur);
+      aba_pass3_multi<T, ST, 3, K_QFLOAT>(M, i, io, st, vcur, acur);
     }
   }
 }

@@ -44,9 +44,10 @@ template <class T> RBD_HD void frame_any(const BodyDev<T>& bd, const Col<T>& q, 
 // Outward sweep that tracks each body's world pose in registers (branch nodes park theirs in their pending slot) and
 // writes  f_b = Rw^T f ,  n_b = Rw^T (n - pw x f)  for every body into the scratch column (rows 6 i .. 6 i + 5,
 // i = preorder position).  Wrench loads for body i+1 are issued while body i is processed.
-template <class T, int STRIDE>
+template <class T, class ST>
 RBD_HD void ext_wrench_pass(const ModelDev<T>& M, const Col<T>& q, const Col<T>& wext, const Scr<T>& ext,
-                            const Stash<T, STRIDE>& st, int slot_base, int slot_rows) {
+                            const ST& stash, int slot_base, int slot_rows) {
+  const auto st = stash.slots();     // only the pending slots are used here (world poses of branch nodes)
   Pose<T> cur;
   pose_identity(cur);
   T wn[6], wc[6];

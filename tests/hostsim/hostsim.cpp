@@ -27,8 +27,8 @@ void run_dynamics_e(const HostModel& hm, int64_t B, const T* q, const T* v, cons
     io.ext = {EXT ? scratch.data() : nullptr, 1};
     Stash<T, 1> st{stash.data()};
     if (EXT) ext_wrench_pass(M, io.q, io.wext, io.ext, st, M.slot_base, kSlotRowsAba);
-    if (hm.general) aba_sample<T, 1, true>(M, io, st);
-    else aba_sample<T, 1, false>(M, io, st);
+    if (hm.general) aba_sample<T, Stash<T, 1>, true>(M, io, st);
+    else aba_sample<T, Stash<T, 1>, false>(M, io, st);
   }
 }
 template <class T>
