@@ -280,8 +280,8 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   const HostModel& hm = model->hm;
   const ModelDev<T>& M = dev_model<T>(hm);
   AbaArgs<T> a{(const T*)q, (const T*)v, (const T*)tau, (const T*)wext, (T*)vd, (T*)qd, nullptr, ld, B};
-  // Pending slots go to the global scratch when that buys at least one more resident warp per SM.
-  const bool gslot = M.nslots > 0 && !getenv("RBD_SMEM_SLOTS");
+  // Pending slots CAN live in the global scratch (one more resident warp on Atlas) -- experiment switch only.
+  const bool gslot = M.nslots > 0 && getenv("RBD_GLOBAL_SLOTS");   // measured slower: off by default
   const int rows = gslot ? M.slot_base : M.nrows;
   const int sr = (wext ? 6 * hm.nb : 0) + (gslot ? M.nslots * kSlotRowsAba : 0);
   if (!wext && !hm.general && getenv("RBD_GSTASH")) return launch<T>(aba_kernel_gstash<T, kNT, false>, M, a, kNT, 0, M.nrows, stream);

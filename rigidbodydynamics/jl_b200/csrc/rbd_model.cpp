@@ -20,6 +20,7 @@
 //  3. Stash-row allocation for the shared-memory working set of the ABA kernel.
 #include "rbd_model.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -140,6 +141,26 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
   std::vector<std::vector<int>> children(nb);
   std::vector<int> roots;
   for (int i = 0; i < nb; ++i) (desc->parent[i] < 0 ? roots : children[desc->parent[i]]).push_back(i);
+  // Child order is free.  A branch node's pending slot is idle while its LAST child's subtree is processed (inward: that
+  // subtree runs first; outward: it runs last), so -- as in Sethi-Ullman numbering -- the child whose subtree needs the
+  // most slots goes last:  need(X) = max(need(c_last), 1 + max need(other children)).
+  {
+    std::vector<int> need(nb, 0);
+    for (int i = nb - 1; i >= 0; --i) {
+      auto& ch = children[i];
+      if (ch.size() == 1) need[i] = need[ch[0]];
+      else if (ch.size() >= 2) {
+        size_t best = 0;
+        for (size_t k = 1; k < ch.size(); ++k) if (need[ch[k]] > need[ch[best]]) best = k;
+        int c = ch[best];
+        ch.erase(ch.begin() + best);
+        ch.push_back(c);
+        int other = 0;
+        for (size_t k = 0; k + 1 < ch.size(); ++k) other = std::max(other, need[ch[k]]);
+        need[i] = std::max(need[c], 1 + other);
+      }
+    }
+  }
   out.order.clear();
   out.pos.assign(nb, -1);
   {
@@ -157,7 +178,9 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
   M.nb = nb; M.nq = nq; M.nv = nv;
   for (int k = 0; k < 3; ++k) M.g[k] = desc->gravity[k];
 
-  std::vector<int> branch_level(nb, 0);   // preorder-indexed: number of branch-node proper ancestors
+  std::vector<int> subtree_size(nb, 1);   // reference-indexed
+  for (int i = nb - 1; i >= 0; --i) if (desc->parent[i] >= 0) subtree_size[desc->parent[i]] += subtree_size[i];
+  std::vector<int> slot_free_at;          // slot -> first preorder position at which it may be re-used
   int nslots = 0, row = 0;
   bool general = false;
   for (int p = 0; p < nb; ++p) {
@@ -194,12 +217,27 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
     else {
       if (par == p - 1) flags |= F_FIRST_CHILD;
       else if (children[par_ref].back() == j) flags |= F_SLOT_INIT;
-      branch_level[p] = branch_level[par] + ((M.body[par].flags & F_HAS_PENDING) ? 1 : 0);
     }
     b.flags = flags;
-    b.oslot = (flags & F_HAS_PENDING) ? branch_level[p] : -1;
+    // Pending slot of a branch node: live over the preorder interval [p, position of its last child] in BOTH directions
+    // (inward: written when the last child's subtree is done, read at p; outward: written at p, last read by the last
+    // child).  Greedy interval colouring in order of increasing p.
+    b.oslot = -1;
+    if (flags & F_HAS_PENDING) {
+      int s = 0;
+      for (;; ++s) {
+        if (s == (int)slot_free_at.size()) slot_free_at.push_back(-1);
+        if (slot_free_at[s] <= p) break;
+      }
+      // children[j] is in evaluation order; the last child's position is not known yet in preorder numbering, but it is
+      // p + (size of the subtrees of all earlier children) + 1
+      int last_pos = p + 1;
+      for (size_t k = 0; k + 1 < children[j].size(); ++k) last_pos += subtree_size[children[j][k]];
+      slot_free_at[s] = last_pos;   // reusable by a branch node that starts at or after the last child
+      b.oslot = s;
+      nslots = std::max(nslots, s + 1);
+    }
     b.pslot = (par >= 0 && !(flags & F_FIRST_CHILD)) ? M.body[par].oslot : -1;
-    if (flags & F_HAS_PENDING) nslots = nslots > branch_level[p] + 1 ? nslots : branch_level[p] + 1;
     // ABA stash rows
     const int k = kind_nv(b.kind);
     const bool multi = k > 1;
