@@ -51,7 +51,10 @@ typedef enum rbd_status {
   RBD_ENOMEM = 7
 } rbd_status;
 
-typedef enum rbd_dtype { RBD_F32 = 0, RBD_F64 = 1 } rbd_dtype;
+/* RBD_DUAL64X6: arrays of ForwardDiff.Dual{Tag,Float64,6} = 7 contiguous doubles (value, 6 partials) per element, i.e.
+ * element (row k, sample b) starts at ((k * ld + b) * 7) doubles -- the memory layout of a Julia Matrix{Dual}(B, n).
+ * Supported by rbd_dynamics (tau optional, no wext / q̇ output); other entry points return RBD_EUNSUPPORTED. */
+typedef enum rbd_dtype { RBD_F32 = 0, RBD_F64 = 1, RBD_DUAL64X6 = 2 } rbd_dtype;
 
 /* Joint type codes: the eight JointTypes of src/joint_types/ (file per line). */
 typedef enum rbd_joint_type {

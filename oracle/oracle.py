@@ -30,6 +30,7 @@ def _load():
     lib.rbdo_nq.argtypes = [vp]
     lib.rbdo_nv.argtypes = [vp]
     lib.rbdo_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32, i32]
+    lib.rbdo_dynamics_dual6.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32]
     lib.rbdo_inverse_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32]
     lib.rbdo_mass_matrix.argtypes = [vp, i32, i64, vp, vp, i32]
     return lib
@@ -92,6 +93,18 @@ class Oracle:
         if rc != 0:
             raise np.linalg.LinAlgError("mass matrix not positive definite")
         return (vd, qd) if want_qd else vd
+
+    def dynamics_dual6(self, q, v, tau=None, *, algo="reference", nthreads=1):
+        """dynamics! on Dual{Float64,6} inputs: arrays [rows, B, 7] float64 (value, 6 partials)."""
+        q = np.ascontiguousarray(q, np.float64); v = np.ascontiguousarray(v, np.float64)
+        tau = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        assert q.shape[0] == self.nq and q.shape[2] == 7 and v.shape[0] == self.nv
+        B = q.shape[1]
+        vd = np.empty((self.nv, B, 7))
+        rc = _lib.rbdo_dynamics_dual6(self._h, B, _ptr(q), _ptr(v), _ptr(tau), _ptr(vd), 0 if algo == "reference" else 1, nthreads)
+        if rc != 0:
+            raise np.linalg.LinAlgError("mass matrix not positive definite")
+        return vd
 
     def inverse_dynamics(self, q, v, vd, wext=None, *, nthreads=1, dtype=None):
         dt = np.dtype(dtype or np.asarray(q).dtype)

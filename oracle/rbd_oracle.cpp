@@ -96,6 +96,39 @@ template <class T> int mass_matrix_t(const Model& m, int64_t B, const T* q, T* M
   return 0;
 }
 
+// Dual{Float64,6} arrays: [rows][B][7] doubles (value, 6 partials) -- Julia's memory layout of Matrix{Dual}(B, n)
+int dynamics_dual6(const Model& m, int64_t B, const double* q, const double* v, const double* tau, double* vd, int algo,
+                   int nthreads) {
+  using D = DualN<6>;
+  std::vector<int> status(std::max(1, nthreads), 0);
+  auto gatherd = [](const double* src, int64_t B, int64_t b, int n, D* dst) {
+    for (int k = 0; k < n; ++k) {
+      const double* e = src + ((int64_t)k * B + b) * 7;
+      dst[k].v = e[0];
+      for (int i = 0; i < 6; ++i) dst[k].d[i] = e[1 + i];
+    }
+  };
+  parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int tid) {
+    Workspace<D> w(m);
+    std::vector<D> ql(m.nq), vl(m.nv), tl(m.nv), vdl(m.nv);
+    for (int64_t b = lo; b < hi; ++b) {
+      gatherd(q, B, b, m.nq, ql.data());
+      gatherd(v, B, b, m.nv, vl.data());
+      if (tau) gatherd(tau, B, b, m.nv, tl.data());
+      bool ok = algo == 0 ? dynamics(w, ql.data(), vl.data(), tau ? tl.data() : nullptr, (const D*)nullptr, vdl.data(), (D*)nullptr)
+                          : aba(w, ql.data(), vl.data(), tau ? tl.data() : nullptr, (const D*)nullptr, vdl.data());
+      if (!ok) status[tid] = 1;
+      for (int k = 0; k < m.nv; ++k) {
+        double* e = vd + ((int64_t)k * B + b) * 7;
+        e[0] = vdl[k].v;
+        for (int i = 0; i < 6; ++i) e[1 + i] = vdl[k].d[i];
+      }
+    }
+  });
+  for (int s : status) if (s) return 1;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -131,6 +164,10 @@ int rbdo_dynamics(void* mp, int dtype, int64_t B, const void* q, const void* v, 
   const Model& m = *static_cast<Model*>(mp);
   if (dtype == 0) return dynamics_t<float>(m, B, (const float*)q, (const float*)v, (const float*)tau, (const float*)wext, (float*)vd, (float*)qd, algo, nthreads);
   return dynamics_t<double>(m, B, (const double*)q, (const double*)v, (const double*)tau, (const double*)wext, (double*)vd, (double*)qd, algo, nthreads);
+}
+int rbdo_dynamics_dual6(void* mp, int64_t B, const double* q, const double* v, const double* tau, double* vd, int algo,
+                        int nthreads) {
+  return dynamics_dual6(*static_cast<Model*>(mp), B, q, v, tau, vd, algo, nthreads);
 }
 // vd == NULL  =>  dynamics_bias
 int rbdo_inverse_dynamics(void* mp, int dtype, int64_t B, const void* q, const void* v, const void* vd, const void* wext,

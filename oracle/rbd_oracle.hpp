@@ -41,6 +41,26 @@ enum JointType : int32_t {
   JT_SPQUAT_FLOATING = 5, JT_QUAT_SPHERICAL = 6, JT_SINCOS_REVOLUTE = 7
 };
 
+// Forward-mode dual number with N partials (the ForwardDiff.Dual{Tag,Float64,N} the reference's generic-scalar path sees;
+// examples/5, test "generic scalar dynamics").  Only what the templated code below needs.
+template <int N> struct DualN {
+  double v;
+  double d[N];
+  DualN() : v(0) { for (int i = 0; i < N; ++i) d[i] = 0; }
+  DualN(double a) : v(a) { for (int i = 0; i < N; ++i) d[i] = 0; }
+};
+template <int N> inline DualN<N> operator+(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int N> inline DualN<N> operator-(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int N> inline DualN<N> operator-(const DualN<N>& a) { DualN<N> r; r.v = -a.v; for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
+template <int N> inline DualN<N> operator*(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.v * b.d[i] + a.d[i] * b.v; return r; }
+template <int N> inline DualN<N> operator/(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v / b.v; for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v; return r; }
+template <int N> inline DualN<N>& operator+=(DualN<N>& a, const DualN<N>& b) { a = a + b; return a; }
+template <int N> inline DualN<N>& operator-=(DualN<N>& a, const DualN<N>& b) { a = a - b; return a; }
+template <int N> inline bool operator>(const DualN<N>& a, const DualN<N>& b) { return a.v > b.v; }
+template <int N> inline DualN<N> sin(const DualN<N>& a) { DualN<N> r; r.v = std::sin(a.v); double c = std::cos(a.v); for (int i = 0; i < N; ++i) r.d[i] = c * a.d[i]; return r; }
+template <int N> inline DualN<N> cos(const DualN<N>& a) { DualN<N> r; r.v = std::cos(a.v); double s = -std::sin(a.v); for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i]; return r; }
+template <int N> inline DualN<N> sqrt(const DualN<N>& a) { DualN<N> r; r.v = std::sqrt(a.v); for (int i = 0; i < N; ++i) r.d[i] = a.d[i] / (2 * r.v); return r; }
+
 inline int joint_nq(int t) { static const int n[8] = {1, 1, 0, 3, 7, 6, 4, 2}; return n[t]; }
 inline int joint_nv(int t) { static const int n[8] = {1, 1, 0, 3, 6, 6, 3, 1}; return n[t]; }
 

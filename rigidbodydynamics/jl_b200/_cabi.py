@@ -14,7 +14,7 @@ import numpy as np
 RBD_MAX_BODIES = 64
 
 RBD_OK, RBD_EINVAL, RBD_EDIM, RBD_ELOOP, RBD_ESTALE, RBD_ECUDA, RBD_EUNSUPPORTED, RBD_ENOMEM = range(8)
-RBD_F32, RBD_F64 = 0, 1
+RBD_F32, RBD_F64, RBD_DUAL64X6 = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librbd_b200.so")

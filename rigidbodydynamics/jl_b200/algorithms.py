@@ -18,7 +18,7 @@ import torch
 from . import _cabi
 from .state import DynamicsResult, MechanismState, _DT
 
-__all__ = ["dynamics_", "dynamics_ode_", "inverse_dynamics_", "inverse_dynamics", "mass_matrix_", "mass_matrix",
+__all__ = ["dynamics_", "dynamics_dual_", "dynamics_ode_", "inverse_dynamics_", "inverse_dynamics", "mass_matrix_", "mass_matrix",
            "dynamics_bias_", "dynamics_bias", "DimensionMismatch"]
 
 
@@ -64,6 +64,26 @@ def dynamics_(result: DynamicsResult, state: MechanismState, torques: Optional[t
                            _ptr(torques), _ptr(externalwrenches), _ptr(result.vd),
                            _ptr(result.qd) if want_qd else None, _stream()))
     return result
+
+
+def dynamics_dual_(vd_out: torch.Tensor, state: MechanismState, q: torch.Tensor, v: torch.Tensor,
+                   torques: Optional[torch.Tensor] = None):
+    """``dynamics!`` on ``ForwardDiff.Dual{Tag,Float64,6}`` inputs (BASELINE config 4; the reference reaches this through
+    its generic-scalar path, examples/5 + src/caches.jl:46-64).  Arrays are float64 ``[rows, B, 7]`` = (value, 6 partials)
+    per element, which is the memory layout of a Julia ``Matrix{Dual}(B, n)``.  ``state`` only supplies the model handle."""
+    state.check_modcount()
+    lib = _cabi.load_library()
+    B = q.shape[1]
+    for name, t, rows in (("q", q, state.nq), ("v", v, state.nv), ("torques", torques, state.nv), ("vd_out", vd_out, state.nv)):
+        if t is None:
+            continue
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+            raise TypeError(f"{name}: expected a contiguous float64 CUDA tensor")
+        if tuple(t.shape) != (rows, B, 7):
+            raise DimensionMismatch(f"{name} has wrong size: expected ({rows}, {B}, 7), got {tuple(t.shape)}")
+    _call(lib.rbd_dynamics(state.handle.ptr, _cabi.RBD_DUAL64X6, B, B, _ptr(q), _ptr(v), _ptr(torques), None,
+                           _ptr(vd_out), None, _stream()))
+    return vd_out
 
 
 def dynamics_ode_(xdot: torch.Tensor, result: DynamicsResult, state: MechanismState, x: torch.Tensor,

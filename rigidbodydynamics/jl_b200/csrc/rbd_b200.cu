@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -23,6 +24,7 @@
 
 #include "../../../include/rbd_b200.h"
 #include "rbd_rnea_crba.cuh"
+#include "rbd_dual.cuh"
 #include "rbd_model.h"
 
 using namespace rbd;
@@ -166,6 +168,37 @@ __global__ void __launch_bounds__(NT) aba_kernel_gstash(const __grid_constant__ 
     io.qd = {a.qd ? a.qd + bl : nullptr, a.ld, active};
     io.ext = {nullptr, 0};
     aba_sample<T, Stash<T, 0>, GENERAL>(M, io, st);
+  }
+}
+
+// dynamics! on Dual{Float64,6} arrays: thread t of the launch owns (sample t / 6, partial direction t % 6).
+struct DualArgs {
+  const double* q; const double* v; const double* tau;
+  double* vd;
+  int64_t ld, B;
+};
+template <int NT, bool GENERAL>
+__global__ void __launch_bounds__(NT) aba_dual_kernel(const __grid_constant__ ModelDev<Dual64> M, const DualArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Dual64* sh = reinterpret_cast<Dual64*>(smem_raw);
+  const Stash<Dual64, NT> st{sh + threadIdx.x};
+  const int64_t total = a.B * 6;
+  const int64_t ngroups = (total + NT - 1) / NT;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t t = g * NT + threadIdx.x;
+    const bool active = t < total;
+    const int64_t tl = active ? t : total - 1;
+    const int64_t b = tl / 6;
+    const int dir = (int)(tl - b * 6);
+    AbaIO<Dual64, false> io;
+    io.q = {a.q + b * kDualWidth, a.ld, dir};
+    io.v = {a.v + b * kDualWidth, a.ld, dir};
+    io.tau = {a.tau ? a.tau + b * kDualWidth : nullptr, a.ld, dir};
+    io.wext = {nullptr, a.ld, dir};
+    io.vd = {a.vd + b * kDualWidth, a.ld, dir, active};
+    io.qd = {nullptr, a.ld, dir, active};
+    io.ext = {nullptr, 0};
+    aba_sample<Dual64, Stash<Dual64, NT>, GENERAL>(M, io, st);
   }
 }
 
@@ -318,9 +351,46 @@ int mass_matrix_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, 
                : launch<T>(crba_kernel<T, kNT, 1>, M, a, kNT, rows, 0, stream);
 }
 
+// dynamics! on Dual{Float64,6} arrays (config 4).  The Dual model (constants with zero partials, 25 KB) is built per call
+// from the fp64 one; this path is not the hot one.
+int dynamics_dual(const rbd_model* model, int64_t B, int64_t ld, const void* q, const void* v, const void* tau, void* vd,
+                  cudaStream_t stream) {
+  const HostModel& hm = model->hm;
+  const ModelDev<double>& S = hm.dev64;
+  std::unique_ptr<ModelDev<Dual64>> Mp(new ModelDev<Dual64>());
+  Mp->nb = S.nb; Mp->nq = S.nq; Mp->nv = S.nv; Mp->nrows = S.nrows; Mp->slot_base = S.slot_base; Mp->nslots = S.nslots;
+  for (int k = 0; k < 3; ++k) Mp->g[k] = Dual64(S.g[k]);
+  for (int i = 0; i < S.nb; ++i) {
+    const BodyDev<double>& s = S.body[i];
+    BodyDev<Dual64>& d = Mp->body[i];
+    for (int k = 0; k < 9; ++k) d.Rt[k] = Dual64(s.Rt[k]);
+    for (int k = 0; k < 3; ++k) { d.pt[k] = Dual64(s.pt[k]); d.h[k] = Dual64(s.h[k]); }
+    for (int k = 0; k < 6; ++k) d.J[k] = Dual64(s.J[k]);
+    d.m = Dual64(s.m);
+    d.kind = s.kind; d.parent = s.parent; d.qrow = s.qrow; d.vrow = s.vrow; d.row0 = s.row0;
+    d.oslot = s.oslot; d.pslot = s.pslot; d.flags = s.flags; d.refidx = s.refidx;
+  }
+  const DualArgs a{(const double*)q, (const double*)v, (const double*)tau, (double*)vd, ld, B};
+  DeviceProps p;
+  if (int rc = get_props(p)) return rc;
+  const size_t smem = (size_t)S.nrows * kNT * sizeof(Dual64);
+  int bps = 0;
+  if (int rc = hm.general ? configure(aba_dual_kernel<kNT, true>, kNT, smem, p, bps)
+                          : configure(aba_dual_kernel<kNT, false>, kNT, smem, p, bps)) return rc;
+  const int64_t ngroups = (B * 6 + kNT - 1) / kNT;      // one thread per (sample, partial direction)
+  const int grid = (int)std::min<int64_t>(ngroups, (int64_t)bps * p.sms);
+  if (hm.general) aba_dual_kernel<kNT, true><<<grid, kNT, smem, stream>>>(*Mp, a);
+  else aba_dual_kernel<kNT, false><<<grid, kNT, smem, stream>>>(*Mp, a);
+  CUDA_TRY(cudaGetLastError());
+  g_launch.kernels_launched += 1;
+  g_launch.grid = grid; g_launch.block = kNT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
+  return RBD_OK;
+}
+
 int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld) {
   if (!model) return fail(RBD_EINVAL, "model handle is NULL");
-  if (dtype != RBD_F32 && dtype != RBD_F64) return fail(RBD_EINVAL, "dtype must be RBD_F32 or RBD_F64");
+  if (dtype != RBD_F32 && dtype != RBD_F64 && dtype != RBD_DUAL64X6)
+    return fail(RBD_EINVAL, "dtype must be RBD_F32, RBD_F64 or RBD_DUAL64X6");
   if (B < 0 || ld < B) return fail(RBD_EDIM, "batch size / leading dimension mismatch (need ld >= B >= 0)");
   return RBD_OK;
 }
@@ -484,6 +554,10 @@ int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t l
   g_launch = {0, 0, 0, 0, 0, 0.f};
   if (B == 0) return RBD_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == RBD_DUAL64X6) {
+    if (wext || qd_out) return fail(RBD_EUNSUPPORTED, "RBD_DUAL64X6: external wrenches / q̇ output are not implemented");
+    return dynamics_dual(model, B, ld, q, v, tau, vd_out, s);
+  }
   return dtype == RBD_F32 ? dynamics_t<float>(model, B, ld, q, v, tau, wext, vd_out, qd_out, s)
                           : dynamics_t<double>(model, B, ld, q, v, tau, wext, vd_out, qd_out, s);
 }

@@ -82,3 +82,17 @@ def mass_matrix(desc, q):
     rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(M))
     assert rc == 0, rc
     return M
+
+
+def dynamics_dual(desc, q, v, tau=None):
+    """Dual{Float64,6} arrays [rows, B, 7]."""
+    d, keep = make_desc(desc)
+    q = np.ascontiguousarray(q, np.float64); v = np.ascontiguousarray(v, np.float64)
+    tau = None if tau is None else np.ascontiguousarray(tau, np.float64)
+    B = q.shape[1]
+    vd = np.full((desc.nv, B, 7), np.nan)
+    fn = lib().hostsim_dynamics_dual
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc), ctypes.c_int64] + [ctypes.c_void_p] * 4
+    rc = fn(ctypes.byref(d), B, _p(q), _p(v), _p(tau), _p(vd))
+    assert rc == 0, rc
+    return vd

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_rnea_crba.cuh"
+#include "../../rigidbodydynamics/jl_b200/csrc/rbd_dual.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_model.h"
 
 using namespace rbd;
@@ -82,6 +83,43 @@ int hostsim_dynamics(const rbd_model_desc* d, int dtype, int64_t B, const void* 
   if (rc) return rc;
   if (dtype == 0) run_dynamics<float>(hm, B, (const float*)q, (const float*)v, (const float*)tau, (const float*)wext, (float*)vd, (float*)qd);
   else run_dynamics<double>(hm, B, (const double*)q, (const double*)v, (const double*)tau, (const double*)wext, (double*)vd, (double*)qd);
+  return 0;
+}
+// dynamics! on Dual{Float64,6} arrays [rows][B][7]: one pass of the device code per (sample, partial direction)
+int hostsim_dynamics_dual(const rbd_model_desc* d, int64_t B, const double* q, const double* v, const double* tau, double* vd) {
+  HostModel hm; std::string err;
+  int rc = build_host_model(d, hm, err);
+  if (rc) return rc;
+  const ModelDev<double>& S = hm.dev64;
+  std::vector<ModelDev<Dual64>> Mv(1);
+  ModelDev<Dual64>& M = Mv[0];
+  M.nb = S.nb; M.nq = S.nq; M.nv = S.nv; M.nrows = S.nrows; M.slot_base = S.slot_base; M.nslots = S.nslots;
+  for (int k = 0; k < 3; ++k) M.g[k] = Dual64(S.g[k]);
+  for (int i = 0; i < S.nb; ++i) {
+    const BodyDev<double>& s = S.body[i];
+    BodyDev<Dual64>& b = M.body[i];
+    for (int k = 0; k < 9; ++k) b.Rt[k] = Dual64(s.Rt[k]);
+    for (int k = 0; k < 3; ++k) { b.pt[k] = Dual64(s.pt[k]); b.h[k] = Dual64(s.h[k]); }
+    for (int k = 0; k < 6; ++k) b.J[k] = Dual64(s.J[k]);
+    b.m = Dual64(s.m);
+    b.kind = s.kind; b.parent = s.parent; b.qrow = s.qrow; b.vrow = s.vrow; b.row0 = s.row0;
+    b.oslot = s.oslot; b.pslot = s.pslot; b.flags = s.flags; b.refidx = s.refidx;
+  }
+  std::vector<Dual64> stash(M.nrows + 64);
+  for (int64_t b = 0; b < B; ++b)
+    for (int dir = 0; dir < 6; ++dir) {
+      AbaIO<Dual64, false> io;
+      io.q = {q + b * kDualWidth, B, dir};
+      io.v = {v + b * kDualWidth, B, dir};
+      io.tau = {tau ? tau + b * kDualWidth : nullptr, B, dir};
+      io.wext = {nullptr, B, dir};
+      io.vd = {vd + b * kDualWidth, B, dir, true};
+      io.qd = {nullptr, B, dir, true};
+      io.ext = {nullptr, 0};
+      Stash<Dual64, 1> st{stash.data()};
+      if (hm.general) aba_sample<Dual64, Stash<Dual64, 1>, true>(M, io, st);
+      else aba_sample<Dual64, Stash<Dual64, 1>, false>(M, io, st);
+    }
   return 0;
 }
 int hostsim_inverse_dynamics(const rbd_model_desc* d, int dtype, int64_t B, const void* q, const void* v, const void* vd,

@@ -11,7 +11,7 @@ import torch
 
 import rigidbodydynamics.jl_b200 as rbd
 from oracle import Oracle
-from tests.util import rand_inputs, randmech, rel_err
+from tests.util import make_duals, rand_inputs, randmech, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = {torch.float64: 1e-9, torch.float32: 2e-5}
@@ -219,3 +219,29 @@ def test_host_entry_points_rnea_crba(built):
     outM = torch.empty((49, B), dtype=torch.float32).pin_memory()
     rbd._cabi.check(lib.rbd_mass_matrix_host(st.handle.ptr, 0, B, B, hq.data_ptr(), outM.data_ptr()))
     assert torch.equal(outM, ref_M)
+
+
+@pytest.mark.parametrize("name,floating,B", [("atlas", True, 8192), ("iiwa14", False, 1000)])
+def test_dual_number_dynamics_gpu(built, name, floating, B):
+    """Config 4 (Atlas ABA with ForwardDiff.Dual{Tag,Float64,6} inputs, batch 8192): values and all 6 partials vs the oracle's
+    dual-number run of the reference's algorithm on a sub-sample, plus finite differences; tolerance 1e-8 relative."""
+    mech = rbd.load_model(name, floating=floating)
+    o = Oracle(mech.flatten())
+    q, v, tau, _, _ = rand_inputs(mech, 64, 4)
+    reps = -(-B // 64)
+    q, v, tau = (np.tile(a, (1, reps))[:, :B].copy() for a in (q, v, tau))
+    Q, V, T = make_duals(mech, q, v, tau, 5)
+    st = rbd.MechanismState(mech, 1, torch.float64)
+    out = torch.full((st.nv, B, 7), float("nan"), dtype=torch.float64, device="cuda")
+    rbd.dynamics_dual_(out, st, torch.from_numpy(Q).cuda(), torch.from_numpy(V).cuda(), torch.from_numpy(T).cuda())
+    got = out.cpu().numpy()
+    assert not np.isnan(got).any()
+    n = 96
+    ref = o.dynamics_dual6(Q[:, :n], V[:, :n], T[:, :n])
+    assert np.abs(got[:, :n, 0] - ref[..., 0]).max() / np.abs(ref[..., 0]).max() < 1e-10
+    assert np.abs(got[:, :n, 1:] - ref[..., 1:]).max() / np.abs(ref[..., 1:]).max() < 1e-8
+    # the value part equals the plain fp64 kernel bit-for-bit
+    st2 = _state(mech, q, v, torch.float64)
+    res = rbd.DynamicsResult(mech, B, torch.float64)
+    rbd.dynamics_(res, st2, _cu(tau, torch.float64), want_qd=False)
+    assert torch.equal(res.vd, out[..., 0])

@@ -6,7 +6,7 @@ import pytest
 import rigidbodydynamics.jl_b200 as rbd
 from oracle import Oracle
 from tests import hostsim
-from tests.util import rand_inputs, randmech, rel_err
+from tests.util import make_duals, rand_inputs, randmech, rel_err
 
 MODELS = [("atlas", True), ("atlas", False), ("valkyrie", True), ("iiwa14", False), ("double_pendulum", False)]
 
@@ -98,3 +98,23 @@ def test_device_identities_fd_id_roundtrip():
     M = hostsim.mass_matrix(d, q).reshape(d.nv, d.nv, -1)
     c = hostsim.inverse_dynamics(d, q, v, None, w)
     assert np.abs(np.einsum("jib,jb->ib", M, acc) + c - tau).max() < 1e-8
+
+
+@pytest.mark.parametrize("name,floating", [("atlas", True), ("iiwa14", False)])
+def test_dual_number_dynamics(name, floating):
+    """Config 4: dynamics! on Dual{Float64,6} inputs through the device code == the oracle's dual-number run of the
+    reference's CRBA + RNEA + Cholesky path, and == central finite differences of the fp64 path."""
+    mech = rbd.load_model(name, floating=floating)
+    d = mech.flatten()
+    o = Oracle(d)
+    q, v, tau, _, _ = rand_inputs(mech, 3, 4)
+    Q, V, T = make_duals(mech, q, v, tau, 5)
+    ref = o.dynamics_dual6(Q, V, T)
+    got = hostsim.dynamics_dual(d, Q, V, T)
+    assert not np.isnan(got).any()
+    assert np.abs(got[..., 0] - ref[..., 0]).max() / np.abs(ref[..., 0]).max() < 1e-11
+    assert np.abs(got[..., 1:] - ref[..., 1:]).max() / np.abs(ref[..., 1:]).max() < 1e-9
+    h = 1e-6
+    fd = (o.dynamics(q + h * Q[..., 3], v + h * V[..., 3], tau + h * T[..., 3])
+          - o.dynamics(q - h * Q[..., 3], v - h * V[..., 3], tau - h * T[..., 3])) / (2 * h)
+    assert np.abs(fd - got[..., 3]).max() / np.abs(fd).max() < 1e-6

@@ -50,3 +50,31 @@ def rel_err(got, ref):
 
 def have_reference():
     return os.path.isdir(REF_URDF)
+
+
+def make_duals(mech, q, v, tau, seed):
+    """Dual{Float64,6} versions [rows, B, 7] of (q, v, tau): value + 6 random partials.  Partials of unit-quaternion
+    coordinates are projected onto the tangent space of the unit sphere: off-manifold derivatives depend on how an algorithm
+    happens to extend R(q) to non-unit quaternions and are not comparable between formulations (parity unpinned)."""
+    rng = np.random.default_rng(seed)
+
+    def dual(x):
+        a = np.zeros(x.shape + (7,))
+        a[..., 0] = x
+        a[..., 1:] = rng.standard_normal(x.shape + (6,))
+        return a
+    Q, V, T = dual(q), dual(v), dual(tau)
+    qs = 0
+    for j in mech.joints:
+        if isinstance(j.joint_type, (rbd.QuaternionFloating, rbd.QuaternionSpherical)):
+            qq = Q[qs:qs + 4, :, 0]
+            for k in range(6):
+                dq = Q[qs:qs + 4, :, 1 + k]
+                dq -= qq * (qq * dq).sum(0)
+        elif isinstance(j.joint_type, rbd.SinCosRevolute):
+            qq = Q[qs:qs + 2, :, 0]
+            for k in range(6):
+                dq = Q[qs:qs + 2, :, 1 + k]
+                dq -= qq * (qq * dq).sum(0)
+        qs += j.nq
+    return Q, V, T
