@@ -25,11 +25,24 @@ template <class F> void parallel_for(int64_t B, int nthreads, F f) {
   for (auto& x : th) x.join();
 }
 
-template <class T> inline void gather(const T* src, int64_t B, int64_t b, int n, T* dst) {
-  for (int k = 0; k < n; ++k) dst[k] = src[(int64_t)k * B + b];
+// The batch arrays are rows x batch with the batch fastest (the GPU layout).  Walking ONE sample through them touches a
+// different page per row; the drivers below therefore move TILES of kTile consecutive samples (contiguous row segments)
+// into a sample-major local buffer, evaluate, and move results back the same way, so the CPU baseline is not penalised by
+// a layout chosen for the GPU.
+constexpr int64_t kTile = 128;
+template <class T> inline void tile_in(const T* src, int64_t B, int64_t b0, int64_t nt, int n, T* dst /*[nt][n]*/) {
+  if (!src) return;
+  for (int k = 0; k < n; ++k) {
+    const T* row = src + (int64_t)k * B + b0;
+    for (int64_t j = 0; j < nt; ++j) dst[j * n + k] = row[j];
+  }
 }
-template <class T> inline void scatter(T* dst, int64_t B, int64_t b, int n, const T* src) {
-  for (int k = 0; k < n; ++k) dst[(int64_t)k * B + b] = src[k];
+template <class T> inline void tile_out(T* dst, int64_t B, int64_t b0, int64_t nt, int n, const T* src /*[nt][n]*/) {
+  if (!dst) return;
+  for (int k = 0; k < n; ++k) {
+    T* row = dst + (int64_t)k * B + b0;
+    for (int64_t j = 0; j < nt; ++j) row[j] = src[j * n + k];
+  }
 }
 
 template <class T>
@@ -38,23 +51,28 @@ int dynamics_t(const Model& m, int64_t B, const T* q, const T* v, const T* tau, 
   std::vector<int> status(std::max(1, nthreads), 0);
   parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int tid) {
     Workspace<T> w(m);
-    std::vector<T> ql(m.nq), vl(m.nv), tl(m.nv), wl((size_t)m.nb * 6), vdl(m.nv), qdl(m.nq);
-    for (int64_t b = lo; b < hi; ++b) {
-      gather(q, B, b, m.nq, ql.data());
-      gather(v, B, b, m.nv, vl.data());
-      if (tau) gather(tau, B, b, m.nv, tl.data());
-      if (wext) gather(wext, B, b, m.nb * 6, wl.data());
-      bool ok;
-      if (algo == 0) {
-        ok = dynamics(w, ql.data(), vl.data(), tau ? tl.data() : nullptr, wext ? wl.data() : nullptr, vdl.data(),
-                      qd ? qdl.data() : nullptr);
-      } else {
-        ok = aba(w, ql.data(), vl.data(), tau ? tl.data() : nullptr, wext ? wl.data() : nullptr, vdl.data());
-        if (qd) configuration_derivative(m, ql.data(), vl.data(), qdl.data());
+    const int nw = m.nb * 6;
+    std::vector<T> ql(kTile * m.nq), vl(kTile * m.nv), tl(kTile * m.nv), wl(kTile * nw), vdl(kTile * m.nv), qdl(kTile * m.nq);
+    for (int64_t b0 = lo; b0 < hi; b0 += kTile) {
+      const int64_t nt = std::min<int64_t>(kTile, hi - b0);
+      tile_in(q, B, b0, nt, m.nq, ql.data());
+      tile_in(v, B, b0, nt, m.nv, vl.data());
+      tile_in(tau, B, b0, nt, m.nv, tl.data());
+      tile_in(wext, B, b0, nt, nw, wl.data());
+      for (int64_t j = 0; j < nt; ++j) {
+        const T* tj = tau ? &tl[j * m.nv] : nullptr;
+        const T* wj = wext ? &wl[j * nw] : nullptr;
+        bool ok;
+        if (algo == 0) {
+          ok = dynamics(w, &ql[j * m.nq], &vl[j * m.nv], tj, wj, &vdl[j * m.nv], qd ? &qdl[j * m.nq] : nullptr);
+        } else {
+          ok = aba(w, &ql[j * m.nq], &vl[j * m.nv], tj, wj, &vdl[j * m.nv]);
+          if (qd) configuration_derivative(m, &ql[j * m.nq], &vl[j * m.nv], &qdl[j * m.nq]);
+        }
+        if (!ok) status[tid] = 1;
       }
-      if (!ok) status[tid] = 1;
-      scatter(vd, B, b, m.nv, vdl.data());
-      if (qd) scatter(qd, B, b, m.nq, qdl.data());
+      tile_out(vd, B, b0, nt, m.nv, vdl.data());
+      tile_out(qd, B, b0, nt, m.nq, qdl.data());
     }
   });
   for (int s : status) if (s) return 1;
@@ -65,15 +83,20 @@ template <class T>
 int inverse_dynamics_t(const Model& m, int64_t B, const T* q, const T* v, const T* vd, const T* wext, T* tau, int nthreads) {
   parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
     Workspace<T> w(m);
-    std::vector<T> ql(m.nq), vl(m.nv), vdl(m.nv), wl((size_t)m.nb * 6), tl(m.nv);
-    for (int64_t b = lo; b < hi; ++b) {
-      gather(q, B, b, m.nq, ql.data());
-      gather(v, B, b, m.nv, vl.data());
-      if (vd) gather(vd, B, b, m.nv, vdl.data());
-      if (wext) gather(wext, B, b, m.nb * 6, wl.data());
-      if (vd) inverse_dynamics(w, ql.data(), vl.data(), vdl.data(), wext ? wl.data() : nullptr, tl.data());
-      else dynamics_bias(w, ql.data(), vl.data(), wext ? wl.data() : nullptr, tl.data());
-      scatter(tau, B, b, m.nv, tl.data());
+    const int nw = m.nb * 6;
+    std::vector<T> ql(kTile * m.nq), vl(kTile * m.nv), vdl(kTile * m.nv), wl(kTile * nw), tl(kTile * m.nv);
+    for (int64_t b0 = lo; b0 < hi; b0 += kTile) {
+      const int64_t nt = std::min<int64_t>(kTile, hi - b0);
+      tile_in(q, B, b0, nt, m.nq, ql.data());
+      tile_in(v, B, b0, nt, m.nv, vl.data());
+      tile_in(vd, B, b0, nt, m.nv, vdl.data());
+      tile_in(wext, B, b0, nt, nw, wl.data());
+      for (int64_t j = 0; j < nt; ++j) {
+        const T* wj = wext ? &wl[j * nw] : nullptr;
+        if (vd) inverse_dynamics(w, &ql[j * m.nq], &vl[j * m.nv], &vdl[j * m.nv], wj, &tl[j * m.nv]);
+        else dynamics_bias(w, &ql[j * m.nq], &vl[j * m.nv], wj, &tl[j * m.nv]);
+      }
+      tile_out(tau, B, b0, nt, m.nv, tl.data());
     }
   });
   return 0;
@@ -82,15 +105,19 @@ int inverse_dynamics_t(const Model& m, int64_t B, const T* q, const T* v, const 
 template <class T> int mass_matrix_t(const Model& m, int64_t B, const T* q, T* M, int nthreads) {
   parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
     Workspace<T> w(m);
-    std::vector<T> ql(m.nq), Ml((size_t)m.nv * m.nv);
-    for (int64_t b = lo; b < hi; ++b) {
-      gather(q, B, b, m.nq, ql.data());
-      update_transforms(w, ql.data());
-      update_motion_subspaces(w);
-      update_spatial_inertias(w);
-      update_crb_inertias(w);
-      mass_matrix(w, Ml.data());
-      scatter(M, B, b, m.nv * m.nv, Ml.data());
+    const int nm = m.nv * m.nv;
+    std::vector<T> ql(kTile * m.nq), Ml((size_t)kTile * nm);
+    for (int64_t b0 = lo; b0 < hi; b0 += kTile) {
+      const int64_t nt = std::min<int64_t>(kTile, hi - b0);
+      tile_in(q, B, b0, nt, m.nq, ql.data());
+      for (int64_t j = 0; j < nt; ++j) {
+        update_transforms(w, &ql[j * m.nq]);
+        update_motion_subspaces(w);
+        update_spatial_inertias(w);
+        update_crb_inertias(w);
+        mass_matrix(w, &Ml[j * nm]);
+      }
+      tile_out(M, B, b0, nt, nm, Ml.data());
     }
   });
   return 0;

@@ -504,15 +504,16 @@ template <class T, bool ZAZ> RBD_HD void art_to_parent(const T* R, const T* r, c
   force_to_parent(R, r, c.n, c.f, o.n, o.f);
 }
 
-// Hand a finished child contribution to its parent: registers (first child), or the parent's pending slot.
+// Hand a finished child contribution (already in `carry`, written there by art_to_parent) to its parent: a first child's
+// stays in registers; any other child's goes to the parent's pending slot.  Writing every contribution into `carry` is safe
+// because a non-first child is followed (in reverse preorder) by the last body of a sibling subtree, a leaf, which does not
+// read `carry` -- and it saves a 27-register copy per body.
 template <class T, class ST>
-RBD_HD void hand_over(const ModelDev<T>& M, const BodyDev<T>& bd, const ST& st, const Art<T>& k, Art<T>& carry) {
-  if (bd.flags & F_FIRST_CHILD) {
-    carry = k;
-  } else {
+RBD_HD void hand_over(const ModelDev<T>& M, const BodyDev<T>& bd, const ST& st, const Art<T>& carry) {
+  if (!(bd.flags & F_FIRST_CHILD)) {
     const int row = M.slot_base + bd.pslot * kSlotRowsAba;
-    if (bd.flags & F_SLOT_INIT) art_store(st.slots(), row, k);
-    else art_accum(st.slots(), row, k);
+    if (bd.flags & F_SLOT_INIT) art_store(st.slots(), row, carry);
+    else art_accum(st.slots(), row, carry);
   }
 }
 
@@ -698,9 +699,9 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
     if (!(bd.flags & F_ROOT_CHILD)) {
       T R[9], r[3];
       frame_1dof(bd, T(0), T(1), T(0), R, r);
-      Art<T> k;
-      art_to_parent<T, false>(R, r, a, k);
-      hand_over(M, bd, st, k, carry);
+      const Art<T> src = a;
+      art_to_parent<T, false>(R, r, src, carry);
+      hand_over(M, bd, st, carry);
     }
     return;
   }
@@ -740,9 +741,8 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
     b.f[2] = a.f[2] + b.B[2] * cax + b.B[5] * cay + b.C[2] * clx + b.C[4] * cly + Ulz * du;
     T R[9], r[3];
     frame_1dof(bd, sn, c, T(0), R, r);
-    Art<T> k;
-    art_to_parent<T, true>(R, r, b, k);
-    hand_over(M, bd, st, k, carry);
+    art_to_parent<T, true>(R, r, b, carry);
+    hand_over(M, bd, st, carry);
   } else {
     // ---- prismatic along e_z: S = e_{lin z} ----
     const T Ux = a.B[2], Uy = a.B[5], Uz = a.B[8];
@@ -773,9 +773,8 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
     b.f[2] = a.f[2] + u;
     T R[9], r[3];
     frame_1dof(bd, T(0), T(1), dd, R, r);
-    Art<T> k;
-    art_to_parent<T, false>(R, r, b, k);
-    hand_over(M, bd, st, k, carry);
+    art_to_parent<T, false>(R, r, b, carry);
+    hand_over(M, bd, st, carry);
   }
 }
 
@@ -883,12 +882,12 @@ RBD_HD void aba_pass2_multi(const ModelDev<T>& M, int i, const IO& io, const ST&
       for (int k = 0; k < K; ++k) s += tU[rr][k] * u[k];
       pa[rr] = s;
     }
-    Art<T> b, kk;
+    Art<T> b;
     full_to_art(Ia, pa, b);
     T R[9], r[3];
     frame_multi(bd, io.q, R, r);
-    art_to_parent<T, false>(R, r, b, kk);
-    hand_over(M, bd, st, kk, carry);
+    art_to_parent<T, false>(R, r, b, carry);
+    hand_over(M, bd, st, carry);
   }
   // rows: U~ (6K, row-major [r][k]) then u~ (K)
 #pragma unroll
