@@ -345,6 +345,14 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         bpe = BYTES_PER_EVAL[args.dtype]
         achieved = (B * args.steps / (ms * 1e-3)) * bpe / 1e9       # per GPU
+        traffic = None
+        try:        # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                for rec in json.load(f).values():
+                    if rec["samples"] == B and args.dtype == "f32":
+                        traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+        except (OSError, KeyError, ValueError):
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -359,9 +367,10 @@ def main():
             "launch": {"grid": linfo.grid, "block": linfo.block, "smem_bytes": linfo.smem_bytes,
                        "blocks_per_sm": linfo.blocks_per_sm},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
-                         "note": "algorithmic bytes/eval x evals/s per GPU; the fused kernel is FP32-issue-bound "
-                                 "(~20k instr/eval), not HBM-bound: see DESIGN.md"},
+                         "traffic": traffic, "algorithmic_bytes_per_launch": B * bpe, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                         "note": "algorithmic bytes/eval x evals/s per GPU; traffic = ncu dram bytes per launch "
+                                 "(profiles/r1_traffic.json). The fused kernel is instruction-issue bound (~970 instr/sample, "
+                                 "56 % issue-active), not HBM-bound: DESIGN.md section 4.1"},
         }
         if gather:
             out["with_nccl_gather"] = gather
