@@ -102,21 +102,15 @@ template <class T> struct AbaArgs {
   int64_t ld, B;
 };
 
-// GSLOT: pending slots in the global scratch (rows [ext_rows, ext_rows + nslots * 27) of the per-thread scratch column),
-// body rows in shared memory.
-template <class T, int NT, bool GENERAL, bool EXT, bool GSLOT>
+// KINDS: compile-time promise about the 1-DoF kinds present (kAllKinds, or 0 = revolute / sin-cos-revolute only).
+template <class T, int NT, bool GENERAL, bool EXT, int KINDS>
 __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
-  using ST = typename std::conditional<GSLOT, StashGS<T, NT>, Stash<T, NT>>::type;
+  using ST = Stash<T, NT>;
   const int64_t nthreads = (int64_t)gridDim.x * NT;
   const int64_t tid = (int64_t)blockIdx.x * NT + threadIdx.x;
-  ST st;
-  if constexpr (GSLOT) {
-    st = ST{sh + threadIdx.x, a.scratch + (EXT ? 6 * M.nb : 0) * nthreads + tid, nthreads, M.slot_base};
-  } else {
-    st = ST{sh + threadIdx.x};
-  }
+  const ST st{sh + threadIdx.x};
   const int64_t ngroups = (a.B + NT - 1) / NT;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t gn = g + gridDim.x;
@@ -130,7 +124,7 @@ __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDe
     const int64_t b = g * NT + threadIdx.x;
     const bool active = b < a.B;
     const int64_t bl = active ? b : a.B - 1;     // inactive lanes recompute the last sample, stores are masked
-    AbaIO<T, EXT> io;
+    AbaIO<T, EXT, KINDS> io;
     io.q = {a.q + bl, a.ld};
     io.v = {a.v + bl, a.ld};
     io.tau = {a.tau ? a.tau + bl : nullptr, a.ld};
@@ -143,6 +137,7 @@ __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDe
   }
 }
 
+#if defined(RBD_EXPERIMENTS)
 // Experimental variant: the stash lives in global memory (L2-resident scratch), occupancy is register-limited.
 template <class T, int NT, bool GENERAL>
 __global__ void __launch_bounds__(NT) aba_kernel_gstash(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
@@ -170,6 +165,8 @@ __global__ void __launch_bounds__(NT) aba_kernel_gstash(const __grid_constant__ 
     aba_sample<T, Stash<T, 0>, GENERAL>(M, io, st);
   }
 }
+
+#endif  // RBD_EXPERIMENTS
 
 // dynamics! on Dual{Float64,6} arrays: thread t of the launch owns (sample t / 6, partial direction t % 6).
 struct DualArgs {
@@ -313,18 +310,14 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   const HostModel& hm = model->hm;
   const ModelDev<T>& M = dev_model<T>(hm);
   AbaArgs<T> a{(const T*)q, (const T*)v, (const T*)tau, (const T*)wext, (T*)vd, (T*)qd, nullptr, ld, B};
-  // Pending slots CAN live in the global scratch (one more resident warp on Atlas) -- experiment switch only.
-  const bool gslot = M.nslots > 0 && getenv("RBD_GLOBAL_SLOTS");   // measured slower: off by default
-  const int rows = gslot ? M.slot_base : M.nrows;
-  const int sr = (wext ? 6 * hm.nb : 0) + (gslot ? M.nslots * kSlotRowsAba : 0);
-  if (!wext && !hm.general && getenv("RBD_GSTASH")) return launch<T>(aba_kernel_gstash<T, kNT, false>, M, a, kNT, 0, M.nrows, stream);
-#define RBD_ABA(G, E, S) launch<T>(aba_kernel<T, kNT, G, E, S>, M, a, kNT, rows, sr, stream)
-  if (hm.general) {
-    if (wext) return gslot ? RBD_ABA(true, true, true) : RBD_ABA(true, true, false);
-    return gslot ? RBD_ABA(true, false, true) : RBD_ABA(true, false, false);
-  }
-  if (wext) return gslot ? RBD_ABA(false, true, true) : RBD_ABA(false, true, false);
-  return gslot ? RBD_ABA(false, false, true) : RBD_ABA(false, false, false);
+  const int rows = M.nrows;
+  const int sr = wext ? 6 * hm.nb : 0;
+  bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
+  for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
+#define RBD_ABA(G, E, K) launch<T>(aba_kernel<T, kNT, G, E, K>, M, a, kNT, rows, sr, stream)
+  if (hm.general) return wext ? RBD_ABA(true, true, kAllKinds) : RBD_ABA(true, false, kAllKinds);
+  if (other_kinds) return wext ? RBD_ABA(false, true, kAllKinds) : RBD_ABA(false, false, kAllKinds);
+  return wext ? RBD_ABA(false, true, 0) : RBD_ABA(false, false, 0);
 #undef RBD_ABA
 }
 
@@ -369,7 +362,9 @@ int dynamics_dual(const rbd_model* model, int64_t B, int64_t ld, const void* q, 
     d.m = Dual64(s.m);
     d.kind = s.kind; d.parent = s.parent; d.qrow = s.qrow; d.vrow = s.vrow; d.row0 = s.row0;
     d.oslot = s.oslot; d.pslot = s.pslot; d.flags = s.flags; d.refidx = s.refidx;
+    d.pair = s.pair; d.next_fwd = s.next_fwd; d.next_rev = s.next_rev;
   }
+  Mp->last_head = S.last_head; Mp->npairs = S.npairs;
   const DualArgs a{(const double*)q, (const double*)v, (const double*)tau, (double*)vd, ld, B};
   DeviceProps p;
   if (int rc = get_props(p)) return rc;

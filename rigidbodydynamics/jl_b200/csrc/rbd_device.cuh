@@ -591,8 +591,13 @@ template <class T> RBD_HD void motion_cross(const Mot<T>& v, const Mot<T>& j, Mo
 // ==================================================================================================================
 // Articulated-Body Algorithm
 // ==================================================================================================================
-template <class T, bool EXT = false> struct AbaIO {
+// Compile-time promise about the 1-DoF kinds a model contains, so kernels for all-revolute robots (the common case) carry
+// no prismatic / fixed code in their hot loops (smaller instruction footprint).
+constexpr int kHasPris = 1, kHasFixed = 2, kAllKinds = 3;
+
+template <class T, bool EXT = false, int KINDS = kAllKinds> struct AbaIO {
   static constexpr bool kExt = EXT;   // external wrenches present (compile-time so the common path carries no extra state)
+  static constexpr int kKinds = KINDS;
   Col<T> q, v, tau, wext;   // tau may be invalid (NULL): zero torques
   ColOut<T> vd, qd;         // qd may be invalid
   Scr<T> ext;               // [6 * nb] body-frame external wrenches, written by ext_wrench_pass (EXT only)
@@ -651,10 +656,11 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const ST& 
   if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
     T s, c, d, qd = T(0);
     joint_scd(kind, pre, s, c, d);
-    if (kind != K_FIXED) qd = pre.qd;
+    if (!(IO::kKinds & kHasFixed) || kind != K_FIXED) qd = pre.qd;
     frame_1dof(bd, s, c, d, R, r);
     motion_to_child(R, r, vp, v);
-    if (kind == K_PRIS) v.l[2] += qd; else if (kind != K_FIXED) v.w[2] += qd;
+    if ((IO::kKinds & kHasPris) && kind == K_PRIS) v.l[2] += qd;
+    else if (!(IO::kKinds & kHasFixed) || kind != K_FIXED) v.w[2] += qd;
   } else {
     frame_multi(bd, io.q, R, r);
     motion_to_child(R, r, vp, v);
@@ -672,6 +678,38 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const ST& 
   for (int k = 0; k < 3; ++k) { st.st(bd.row0 + k, v.w[k]); st.st(bd.row0 + 3 + k, v.l[k]); }
   vcur = v;
   if (io.qd.valid()) qdot_joint(bd, io.q, io.v, io.qd);
+}
+
+// Eliminate a revolute-z DoF from the assembled articulated quantities `a` of a body moving with `v`:
+//   U = IA e_z (a column), D = U_z, u = tau - pA_z;  U~ = U / D (returned without its unit entry: ang x, ang y, lin x, lin y,
+//   lin z), u~ = (u - U.c) / D with c = v x (e_z qd);  b = (Ia, pa) = (IA - U U~^T, pA + Ia c + U u / D), whose angular-z
+//   row / column vanish.  Straight-line code (no branches) so two calls in one block interleave.
+template <class T>
+RBD_HD void rev_eliminate(const Art<T>& a, const Mot<T>& v, T qd, T tau, T (&tU)[5], T& tu, Art<T>& b) {
+  const T Ux = a.A[2], Uy = a.A[4], D = a.A[5];
+  const T Ulx = a.B[6], Uly = a.B[7], Ulz = a.B[8];
+  const T Dinv = T(1) / D;
+  const T cax = qd * v.w[1], cay = -qd * v.w[0];     // c = v x (e_z qd): [w x e_z qd ; l x e_z qd]
+  const T clx = qd * v.l[1], cly = -qd * v.l[0];
+  const T u = tau - a.n[2];
+  const T Uc = Ux * cax + Uy * cay + Ulx * clx + Uly * cly;
+  const T tUx = Ux * Dinv, tUy = Uy * Dinv, tLx = Ulx * Dinv, tLy = Uly * Dinv, tLz = Ulz * Dinv;
+  tU[0] = tUx; tU[1] = tUy; tU[2] = tLx; tU[3] = tLy; tU[4] = tLz;
+  tu = (u - Uc) * Dinv;
+  b.A[0] = a.A[0] - Ux * tUx; b.A[1] = a.A[1] - Ux * tUy; b.A[3] = a.A[3] - Uy * tUy;
+  b.A[2] = T(0); b.A[4] = T(0); b.A[5] = T(0);
+  b.B[0] = a.B[0] - Ux * tLx; b.B[1] = a.B[1] - Ux * tLy; b.B[2] = a.B[2] - Ux * tLz;
+  b.B[3] = a.B[3] - Uy * tLx; b.B[4] = a.B[4] - Uy * tLy; b.B[5] = a.B[5] - Uy * tLz;
+  b.B[6] = T(0); b.B[7] = T(0); b.B[8] = T(0);
+  b.C[0] = a.C[0] - Ulx * tLx; b.C[1] = a.C[1] - Ulx * tLy; b.C[2] = a.C[2] - Ulx * tLz;
+  b.C[3] = a.C[3] - Uly * tLy; b.C[4] = a.C[4] - Uly * tLz; b.C[5] = a.C[5] - Ulz * tLz;
+  const T du = u * Dinv;
+  b.n[0] = a.n[0] + b.A[0] * cax + b.A[1] * cay + b.B[0] * clx + b.B[1] * cly + Ux * du;
+  b.n[1] = a.n[1] + b.A[1] * cax + b.A[3] * cay + b.B[3] * clx + b.B[4] * cly + Uy * du;
+  b.n[2] = a.n[2] + u;
+  b.f[0] = a.f[0] + b.B[0] * cax + b.B[3] * cay + b.C[0] * clx + b.C[1] * cly + Ulx * du;
+  b.f[1] = a.f[1] + b.B[1] * cax + b.B[4] * cay + b.C[1] * clx + b.C[3] * cly + Uly * du;
+  b.f[2] = a.f[2] + b.B[2] * cax + b.B[5] * cay + b.C[2] * clx + b.C[4] * cly + Ulz * du;
 }
 
 // ---- pass 2 (inward): articulated inertias ------------------------------------------------------------------------
@@ -695,7 +733,7 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
   if (!(bd.flags & F_LEAF)) art_add(a, carry);
   if (bd.flags & F_HAS_PENDING) art_add_from(st.slots(), M.slot_base + bd.oslot * kSlotRowsAba, a);
 
-  if (kind == K_FIXED) {
+  if ((IO::kKinds & kHasFixed) && kind == K_FIXED) {
     if (!(bd.flags & F_ROOT_CHILD)) {
       T R[9], r[3];
       frame_1dof(bd, T(0), T(1), T(0), R, r);
@@ -709,36 +747,15 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
   joint_scd(kind, pre, sn, c, dd);
   const T qd = pre.qd;
   const T tau = pre.tau;
-  if (kind != K_PRIS) {
+  if (!(IO::kKinds & kHasPris) || kind != K_PRIS) {
     // ---- revolute about e_z: S = e_{ang z} ----
-    const T Ux = a.A[2], Uy = a.A[4], D = a.A[5];
-    const T Ulx = a.B[6], Uly = a.B[7], Ulz = a.B[8];
-    const T Dinv = T(1) / D;
-    const T cax = qd * v.w[1], cay = -qd * v.w[0];     // c = v x (e_z qd): [w x e_z qd ; l x e_z qd]
-    const T clx = qd * v.l[1], cly = -qd * v.l[0];
-    const T u = tau - a.n[2];
-    const T Uc = Ux * cax + Uy * cay + Ulx * clx + Uly * cly;
-    const T tUx = Ux * Dinv, tUy = Uy * Dinv, tLx = Ulx * Dinv, tLy = Uly * Dinv, tLz = Ulz * Dinv;
-    st.st(bd.row0 + 0, tUx); st.st(bd.row0 + 1, tUy); st.st(bd.row0 + 2, tLx); st.st(bd.row0 + 3, tLy);
-    st.st(bd.row0 + 4, tLz); st.st(bd.row0 + 5, (u - Uc) * Dinv);
-    if (bd.flags & F_ROOT_CHILD) return;
-    // Ia = IA - U U~^T  (angular-z row / column vanish)
+    T tU[5], tu;
     Art<T> b;
-    b.A[0] = a.A[0] - Ux * tUx; b.A[1] = a.A[1] - Ux * tUy; b.A[3] = a.A[3] - Uy * tUy;
-    b.A[2] = T(0); b.A[4] = T(0); b.A[5] = T(0);
-    b.B[0] = a.B[0] - Ux * tLx; b.B[1] = a.B[1] - Ux * tLy; b.B[2] = a.B[2] - Ux * tLz;
-    b.B[3] = a.B[3] - Uy * tLx; b.B[4] = a.B[4] - Uy * tLy; b.B[5] = a.B[5] - Uy * tLz;
-    b.B[6] = T(0); b.B[7] = T(0); b.B[8] = T(0);
-    b.C[0] = a.C[0] - Ulx * tLx; b.C[1] = a.C[1] - Ulx * tLy; b.C[2] = a.C[2] - Ulx * tLz;
-    b.C[3] = a.C[3] - Uly * tLy; b.C[4] = a.C[4] - Uly * tLz; b.C[5] = a.C[5] - Ulz * tLz;
-    // pa = pA + Ia c + U D^-1 u
-    const T du = u * Dinv;
-    b.n[0] = a.n[0] + b.A[0] * cax + b.A[1] * cay + b.B[0] * clx + b.B[1] * cly + Ux * du;
-    b.n[1] = a.n[1] + b.A[1] * cax + b.A[3] * cay + b.B[3] * clx + b.B[4] * cly + Uy * du;
-    b.n[2] = a.n[2] + u;
-    b.f[0] = a.f[0] + b.B[0] * cax + b.B[3] * cay + b.C[0] * clx + b.C[1] * cly + Ulx * du;
-    b.f[1] = a.f[1] + b.B[1] * cax + b.B[4] * cay + b.C[1] * clx + b.C[3] * cly + Uly * du;
-    b.f[2] = a.f[2] + b.B[2] * cax + b.B[5] * cay + b.C[2] * clx + b.C[4] * cly + Ulz * du;
+    rev_eliminate(a, v, qd, tau, tU, tu, b);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) st.st(bd.row0 + k, tU[k]);
+    st.st(bd.row0 + 5, tu);
+    if (bd.flags & F_ROOT_CHILD) return;
     T R[9], r[3];
     frame_1dof(bd, sn, c, T(0), R, r);
     art_to_parent<T, true>(R, r, b, carry);
@@ -938,7 +955,7 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
   Mot<T> vp, ap, v, xa;
   load_parent_va(M, bd, st, vcur, acur, vp, ap);
   T R[9], r[3];
-  if (kind == K_FIXED) {
+  if ((IO::kKinds & kHasFixed) && kind == K_FIXED) {
     frame_1dof(bd, T(0), T(1), T(0), R, r);
     motion_to_child(R, r, vp, v);
     motion_to_child(R, r, ap, xa);
@@ -952,7 +969,7 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
   const T t0 = st.ld(bd.row0 + 0), t1 = st.ld(bd.row0 + 1), t2 = st.ld(bd.row0 + 2), t3 = st.ld(bd.row0 + 3),
           t4 = st.ld(bd.row0 + 4), tu = st.ld(bd.row0 + 5);
   Mot<T> a;
-  if (kind != K_PRIS) {
+  if (!(IO::kKinds & kHasPris) || kind != K_PRIS) {
     frame_1dof(bd, sn, c, T(0), R, r);
     motion_to_child(R, r, vp, v);
     motion_to_child(R, r, ap, xa);
@@ -1013,37 +1030,173 @@ RBD_HD void aba_pass3_multi(const ModelDev<T>& M, int i, const IO& io, const ST&
   save_own_va(M, bd, st, v, a);
 }
 
+// ---- paired steps: two sibling revolute chains walked in lock-step -----------------------------------------------
+// Both bodies of a pair are K_REV / K_SINCOS, have a real parent, sit at the same depth of equal-length chains (so they are
+// leaves together) and carry the serial flags of rbd_model.cpp; lane 0 (`i0`) shares the chain registers of the single
+// steps, lane 1 (`i1`, later in preorder, never a first child at its top) has its own.  The arithmetic of the two lanes is
+// written as straight-line code in ONE block so the scheduler interleaves the two independent dependency chains.
+template <class T, class ST, class IO>
+RBD_HD void aba_pass1_pair(const ModelDev<T>& M, int i0, int i1, const IO& io, const ST& st, Mot<T>& v0, Mot<T>& v1,
+                           const Pre<T>& p0, const Pre<T>& p1) {
+  const BodyDev<T>& b0 = M.body[i0];
+  const BodyDev<T>& b1 = M.body[i1];
+  Mot<T> vp0, vp1;
+  if (b0.flags & F_FIRST_CHILD) vp0 = v0;
+  else {
+    const int pr = M.body[b0.parent].row0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { vp0.w[k] = st.ld(pr + k); vp0.l[k] = st.ld(pr + 3 + k); }
+  }
+  if (b1.flags & F_FIRST_CHILD) vp1 = v1;
+  else {
+    const int pr = M.body[b1.parent].row0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { vp1.w[k] = st.ld(pr + k); vp1.l[k] = st.ld(pr + 3 + k); }
+  }
+  T s0, c0, d0, s1, c1, d1, R0[9], r0[3], R1[9], r1[3];
+  joint_scd(b0.kind, p0, s0, c0, d0);
+  joint_scd(b1.kind, p1, s1, c1, d1);
+  frame_1dof(b0, s0, c0, T(0), R0, r0);
+  frame_1dof(b1, s1, c1, T(0), R1, r1);
+  Mot<T> a, b;
+  motion_to_child(R0, r0, vp0, a);
+  motion_to_child(R1, r1, vp1, b);
+  a.w[2] += p0.qd;
+  b.w[2] += p1.qd;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    st.st(b0.row0 + k, a.w[k]); st.st(b0.row0 + 3 + k, a.l[k]);
+    st.st(b1.row0 + k, b.w[k]); st.st(b1.row0 + 3 + k, b.l[k]);
+  }
+  v0 = a; v1 = b;
+  if (io.qd.valid()) { qdot_joint(b0, io.q, io.v, io.qd); qdot_joint(b1, io.q, io.v, io.qd); }
+}
+
+template <class T, class ST, class IO>
+RBD_HD void aba_pass2_pair(const ModelDev<T>& M, int i0, int i1, const IO& io, const ST& st, Art<T>& c0, Art<T>& c1,
+                           const Pre<T>& p0, const Pre<T>& p1) {
+  const BodyDev<T>& b0 = M.body[i0];
+  const BodyDev<T>& b1 = M.body[i1];
+  Mot<T> v0, v1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    v0.w[k] = st.ld(b0.row0 + k); v0.l[k] = st.ld(b0.row0 + 3 + k);
+    v1.w[k] = st.ld(b1.row0 + k); v1.l[k] = st.ld(b1.row0 + 3 + k);
+  }
+  Art<T> a0, a1;
+  art_set_body(b0, a0);
+  art_set_body(b1, a1);
+  bias_force(b0, v0, a0.n, a0.f);
+  bias_force(b1, v1, a1.n, a1.f);
+  if (!(b0.flags & F_LEAF)) { art_add(a0, c0); art_add(a1, c1); }      // equal-length chains: leaves together
+  T tU0[5], tu0, tU1[5], tu1;
+  Art<T> e0, e1;
+  rev_eliminate(a0, v0, p0.qd, p0.tau, tU0, tu0, e0);
+  rev_eliminate(a1, v1, p1.qd, p1.tau, tU1, tu1, e1);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { st.st(b0.row0 + k, tU0[k]); st.st(b1.row0 + k, tU1[k]); }
+  st.st(b0.row0 + 5, tu0);
+  st.st(b1.row0 + 5, tu1);
+  T s0, cc0, d0, s1, cc1, d1, R0[9], r0[3], R1[9], r1[3];
+  joint_scd(b0.kind, p0, s0, cc0, d0);
+  joint_scd(b1.kind, p1, s1, cc1, d1);
+  frame_1dof(b0, s0, cc0, T(0), R0, r0);
+  frame_1dof(b1, s1, cc1, T(0), R1, r1);
+  art_to_parent<T, true>(R0, r0, e0, c0);
+  art_to_parent<T, true>(R1, r1, e1, c1);
+  hand_over(M, b1, st, c1);     // serial order: the later chain reaches the parent's slot first
+  hand_over(M, b0, st, c0);
+}
+
+// outward step of a revolute-z body from (vp, ap) of its parent: v, a, and the joint acceleration (stored)
+template <class T, class ST, class IO>
+RBD_HD void rev_pass3_core(const BodyDev<T>& bd, const IO& io, const ST& st, const Pre<T>& pre, const Mot<T>& vp,
+                           const Mot<T>& ap, Mot<T>& v, Mot<T>& a) {
+  T sn, c, dd, R[9], r[3];
+  joint_scd(bd.kind, pre, sn, c, dd);
+  const T qd = pre.qd;
+  const T t0 = st.ld(bd.row0 + 0), t1 = st.ld(bd.row0 + 1), t2 = st.ld(bd.row0 + 2), t3 = st.ld(bd.row0 + 3),
+          t4 = st.ld(bd.row0 + 4), tu = st.ld(bd.row0 + 5);
+  Mot<T> xa;
+  frame_1dof(bd, sn, c, T(0), R, r);
+  motion_to_child(R, r, vp, v);
+  motion_to_child(R, r, ap, xa);
+  v.w[2] += qd;
+  const T vd = tu - (t0 * xa.w[0] + t1 * xa.w[1] + xa.w[2] + t2 * xa.l[0] + t3 * xa.l[1] + t4 * xa.l[2]);
+  io.vd.st(bd.vrow, vd);
+  a.w[0] = xa.w[0] + qd * v.w[1]; a.w[1] = xa.w[1] - qd * v.w[0]; a.w[2] = xa.w[2] + vd;
+  a.l[0] = xa.l[0] + qd * v.l[1]; a.l[1] = xa.l[1] - qd * v.l[0]; a.l[2] = xa.l[2];
+}
+
+template <class T, class ST, class IO>
+RBD_HD void aba_pass3_pair(const ModelDev<T>& M, int i0, int i1, const IO& io, const ST& st, Mot<T>& v0, Mot<T>& a0,
+                           Mot<T>& v1, Mot<T>& a1, const Pre<T>& p0, const Pre<T>& p1) {
+  const BodyDev<T>& b0 = M.body[i0];
+  const BodyDev<T>& b1 = M.body[i1];
+  Mot<T> vp0, ap0, vp1, ap1, nv0, na0, nv1, na1;
+  load_parent_va(M, b0, st, v0, a0, vp0, ap0);
+  load_parent_va(M, b1, st, v1, a1, vp1, ap1);
+  rev_pass3_core(b0, io, st, p0, vp0, ap0, nv0, na0);
+  rev_pass3_core(b1, io, st, p1, vp1, ap1, nv1, na1);
+  v0 = nv0; a0 = na0; v1 = nv1; a1 = na1;
+}
+
 // ---- whole algorithm for one sample -------------------------------------------------------------------------------
-// GENERAL = false: bodies 1..nb-1 are 1-DoF or fixed (multi-DoF joint allowed only at position 0 under the world).
+// GENERAL = false: bodies 1..nb-1 are 1-DoF or fixed (multi-DoF joint allowed only at position 0 under the world); in that
+// case paired steps (see above) are honoured.  GENERAL = true walks every body singly.
 template <class T, class ST, bool GENERAL, class IO>
 RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
+  // Paired steps are implemented and pass every parity test, but measured SLOWER on B200 (601 M vs 666 M evals/s on Atlas):
+  // the second copy of the inlined step bodies pushes the hot code past the instruction cache (no_instruction stalls
+  // 0.17 -> 0.43 per issue) and the gain in ILP does not make up for it.  Compiled out unless RBD_ENABLE_PAIRS is defined.
+#if defined(RBD_ENABLE_PAIRS)
+  constexpr bool PAIRS = !GENERAL && !IO::kExt;
+#else
+  constexpr bool PAIRS = false;
+#endif
   const int nb = M.nb;
-  Mot<T> vcur, acur;
+  Mot<T> vcur, acur, vB, aB;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { vcur.w[k] = vcur.l[k] = acur.w[k] = acur.l[k] = T(0); }
-  // pass 1 (loads for body i+1 are in flight while body i is processed)
-  Pre<T> cur, nxt;
-  prefetch_body<T, 1>(M, 0, io, cur);
-  for (int i = 0; i < nb; ++i) {
-    prefetch_body<T, 1>(M, i + 1, io, nxt);
-    aba_pass1_body<T, ST, GENERAL>(M, i, io, st, vcur, cur);
-    cur = nxt;
+  for (int k = 0; k < 3; ++k) {
+    vcur.w[k] = vcur.l[k] = acur.w[k] = acur.l[k] = T(0);
+    vB.w[k] = vB.l[k] = aB.w[k] = aB.l[k] = T(0);
   }
-  // pass 2
-  Art<T> carry;
+  // ---- pass 1 (loads for the next step are in flight while this step is processed) ----
+  Pre<T> cur, nxt, curB, nxtB;
+  prefetch_body<T, 1>(M, 0, io, cur);
+  prefetch_body<T, 1>(M, PAIRS ? M.body[0].pair : -1, io, curB);
+  for (int i = 0; i < nb;) {
+    const int j = PAIRS ? M.body[i].pair : -1;
+    const int in = PAIRS ? M.body[i].next_fwd : i + 1;
+    prefetch_body<T, 1>(M, in, io, nxt);
+    if (PAIRS) prefetch_body<T, 1>(M, in < nb ? M.body[in].pair : -1, io, nxtB);
+    if (PAIRS && j >= 0) aba_pass1_pair(M, i, j, io, st, vcur, vB, cur, curB);
+    else aba_pass1_body<T, ST, GENERAL>(M, i, io, st, vcur, cur);
+    cur = nxt; curB = nxtB;
+    i = in;
+  }
+  // ---- pass 2 ----
+  Art<T> carry, carryB;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { carry.A[k] = T(0); carry.C[k] = T(0); }
+  for (int k = 0; k < 6; ++k) { carry.A[k] = T(0); carry.C[k] = T(0); carryB.A[k] = T(0); carryB.C[k] = T(0); }
 #pragma unroll
-  for (int k = 0; k < 9; ++k) carry.B[k] = T(0);
+  for (int k = 0; k < 9; ++k) { carry.B[k] = T(0); carryB.B[k] = T(0); }
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { carry.n[k] = T(0); carry.f[k] = T(0); }
-  prefetch_body<T, 2>(M, nb - 1, io, cur);
-  for (int i = nb - 1; i >= 1; --i) {
+  for (int k = 0; k < 3; ++k) { carry.n[k] = T(0); carry.f[k] = T(0); carryB.n[k] = T(0); carryB.f[k] = T(0); }
+  const int last = PAIRS ? M.last_head : nb - 1;
+  prefetch_body<T, 2>(M, last, io, cur);
+  prefetch_body<T, 2>(M, PAIRS ? M.body[last].pair : -1, io, curB);
+  for (int i = last; i >= 1;) {
     const int kind = M.body[i].kind;
-    prefetch_body<T, 2>(M, i - 1, io, nxt);
-    Pre<T> now = cur;
-    cur = nxt;
-    if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
+    const int j = PAIRS ? M.body[i].pair : -1;
+    const int ip = PAIRS ? M.body[i].next_rev : i - 1;
+    prefetch_body<T, 2>(M, ip, io, nxt);
+    if (PAIRS) prefetch_body<T, 2>(M, ip >= 0 ? M.body[ip].pair : -1, io, nxtB);
+    const Pre<T> now = cur, nowB = curB;
+    cur = nxt; curB = nxtB;
+    if (PAIRS && j >= 0) {
+      aba_pass2_pair(M, i, j, io, st, carry, carryB, now, nowB);
+    } else if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass2_1dof(M, i, io, st, carry, now);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
       aba_pass2_multi<T, ST, 6, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
@@ -1052,13 +1205,15 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
     } else {
       aba_pass2_multi<T, ST, 3, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
     }
+    i = ip;
   }
   // body 0: inward step, then the outward pass starts here
+  const int first = PAIRS ? M.body[0].next_fwd : 1;
   {
     const BodyDev<T>& b0 = M.body[0];
     const int kind = b0.kind;
-    const bool root0 = (b0.flags & F_ROOT_CHILD) != 0;   // always true for position 0
-    prefetch_body<T, 3>(M, 1, io, nxt);
+    prefetch_body<T, 3>(M, first, io, nxt);
+    if (PAIRS) prefetch_body<T, 3>(M, first < nb ? M.body[first].pair : -1, io, nxtB);
     if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass2_1dof(M, 0, io, st, carry, cur);
       aba_pass3_1dof(M, 0, io, st, vcur, acur, cur);
@@ -1072,16 +1227,20 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
       aba_pass2_multi<T, ST, 3, K_QFLOAT, true>(M, 0, io, st, carry, vcur, acur);
       save_own_va(M, b0, st, vcur, acur);
     }
-    (void)root0;
   }
-  // pass 3
-  cur = nxt;
-  for (int i = 1; i < nb; ++i) {
+  // ---- pass 3 ----
+  cur = nxt; curB = nxtB;
+  for (int i = first; i < nb;) {
     const int kind = M.body[i].kind;
-    prefetch_body<T, 3>(M, i + 1, io, nxt);
-    Pre<T> now = cur;
-    cur = nxt;
-    if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
+    const int j = PAIRS ? M.body[i].pair : -1;
+    const int in = PAIRS ? M.body[i].next_fwd : i + 1;
+    prefetch_body<T, 3>(M, in, io, nxt);
+    if (PAIRS) prefetch_body<T, 3>(M, in < nb ? M.body[in].pair : -1, io, nxtB);
+    const Pre<T> now = cur, nowB = curB;
+    cur = nxt; curB = nxtB;
+    if (PAIRS && j >= 0) {
+      aba_pass3_pair(M, i, j, io, st, vcur, acur, vB, aB, now, nowB);
+    } else if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass3_1dof(M, i, io, st, vcur, acur, now);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
       aba_pass3_multi<T, ST, 6, K_QFLOAT>(M, i, io, st, vcur, acur);
@@ -1090,6 +1249,7 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
     } else {
       aba_pass3_multi<T, ST, 3, K_QFLOAT>(M, i, io, st, vcur, acur);
     }
+    i = in;
   }
 }
 

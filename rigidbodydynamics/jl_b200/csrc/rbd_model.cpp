@@ -84,7 +84,9 @@ template <class T> void fill_dev(const HostModel& hm, const ModelDev<double>& sr
     d.m = (T)s.m;
     d.kind = s.kind; d.parent = s.parent; d.qrow = s.qrow; d.vrow = s.vrow; d.row0 = s.row0;
     d.oslot = s.oslot; d.pslot = s.pslot; d.flags = s.flags; d.refidx = s.refidx;
+    d.pair = s.pair; d.next_fwd = s.next_fwd; d.next_rev = s.next_rev;
   }
+  dst.last_head = src.last_head; dst.npairs = src.npairs;
   (void)hm;
 }
 
@@ -141,6 +143,38 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
   std::vector<std::vector<int>> children(nb);
   std::vector<int> roots;
   for (int i = 0; i < nb; ++i) (desc->parent[i] < 0 ? roots : children[desc->parent[i]]).push_back(i);
+  // Limb pairing: sibling subtrees that are pure revolute chains of equal length (the legs / arms of a humanoid) are walked
+  // in lock-step by the ABA kernel.  Paired children are placed first and adjacent (L then R).
+  struct PairRec { int L, R, len; };
+  std::vector<PairRec> pairs;
+  {
+    std::vector<int> chain_len(nb, 0);
+    for (int i = nb - 1; i >= 0; --i) {
+      const bool rev = desc->jtype[i] == K_REV || desc->jtype[i] == K_SINCOS;
+      if (!rev) continue;
+      if (children[i].empty()) chain_len[i] = 1;
+      else if (children[i].size() == 1 && chain_len[children[i][0]] > 0) chain_len[i] = 1 + chain_len[children[i][0]];
+    }
+    for (int x = 0; x < nb; ++x) {
+      auto& ch = children[x];
+      if (ch.size() < 2) continue;
+      std::vector<int> paired, rest;
+      std::vector<char> used(ch.size(), 0);
+      for (size_t a = 0; a < ch.size(); ++a) {
+        if (used[a] || chain_len[ch[a]] == 0) continue;
+        for (size_t b = a + 1; b < ch.size(); ++b) {
+          if (used[b] || chain_len[ch[b]] != chain_len[ch[a]]) continue;
+          used[a] = used[b] = 1;
+          paired.push_back(ch[a]); paired.push_back(ch[b]);
+          pairs.push_back({ch[a], ch[b], chain_len[ch[a]]});
+          break;
+        }
+      }
+      for (size_t a = 0; a < ch.size(); ++a) if (!used[a]) rest.push_back(ch[a]);
+      paired.insert(paired.end(), rest.begin(), rest.end());
+      ch = paired;
+    }
+  }
   // Child order is free.  A branch node's pending slot is idle while its LAST child's subtree is processed (inward: that
   // subtree runs first; outward: it runs last), so -- as in Sethi-Ullman numbering -- the child whose subtree needs the
   // most slots goes last:  need(X) = max(need(c_last), 1 + max need(other children)).
@@ -153,8 +187,12 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
         size_t best = 0;
         for (size_t k = 1; k < ch.size(); ++k) if (need[ch[k]] > need[ch[best]]) best = k;
         int c = ch[best];
-        ch.erase(ch.begin() + best);
-        ch.push_back(c);
+        if (need[c] > 0) {               // (paired chains need 0 slots and are never moved)
+          ch.erase(ch.begin() + best);
+          ch.push_back(c);
+        } else {
+          c = ch.back();
+        }
         int other = 0;
         for (size_t k = 0; k + 1 < ch.size(); ++k) other = std::max(other, need[ch[k]]);
         need[i] = std::max(need[c], 1 + other);
@@ -248,6 +286,25 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
     else row += 7 * k;                                    // U~ (6k) + u~ (k), also holds v (6) between passes 1 and 2
   }
   // (a non-first child implies >= 2 children, so its parent always owns a slot)
+  // paired steps and the step-head links
+  for (int p = 0; p < nb; ++p) M.body[p].pair = -1;
+  for (const PairRec& pr : pairs) {
+    const int lp = out.pos[pr.L], rp = out.pos[pr.R];
+    if (rp != lp + pr.len) continue;     // not adjacent after ordering: leave both chains as single steps
+    for (int k = 0; k < pr.len; ++k) { M.body[lp + k].pair = rp + k; M.body[rp + k].pair = -2; }
+    M.npairs += pr.len;
+  }
+  {
+    int prev = -1;
+    for (int p = 0; p < nb; ++p) {
+      if (M.body[p].pair == -2) { M.body[p].next_fwd = nb; M.body[p].next_rev = -1; continue; }
+      M.body[p].next_rev = prev;
+      if (prev >= 0) M.body[prev].next_fwd = p;
+      prev = p;
+    }
+    if (prev >= 0) M.body[prev].next_fwd = nb;
+    M.last_head = prev;
+  }
   M.slot_base = row;
   M.nslots = nslots;
   M.nrows = row + nslots * kSlotRowsAba;
