@@ -25,6 +25,7 @@
 #include "../../../include/rbd_b200.h"
 #include "rbd_rnea_crba.cuh"
 #include "rbd_dual.cuh"
+#include "rbd_tmem.cuh"
 #include "rbd_model.h"
 
 using namespace rbd;
@@ -39,6 +40,8 @@ struct rbd_model {
   void* d_stage[3] = {nullptr, nullptr, nullptr};
   size_t stage_bytes = 0;
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t side_stream = nullptr;   // Tensor-Memory kernel runs here, next to the shared-memory kernel
+  std::mutex side_mu;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -135,6 +138,58 @@ __global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDe
     if (EXT) ext_wrench_pass(M, io.q, io.wext, io.ext, st, M.slot_base, kSlotRowsAba);
     aba_sample<T, ST, GENERAL>(M, io, st);
   }
+}
+
+// Work-queue variants for running the shared-memory kernel and the Tensor-Memory kernel SIDE BY SIDE on every SM (two
+// launches on two streams; groups of 32 samples are claimed from one atomic counter, so the kernels balance themselves).
+__device__ __forceinline__ int64_t claim_group(unsigned long long* counter) {
+  unsigned long long g = 0;
+  if ((threadIdx.x & 31) == 0) g = atomicAdd(counter, 1ull);
+  return (int64_t)__shfl_sync(0xffffffffu, g, 0);
+}
+template <class ST, int KINDS>
+__device__ __forceinline__ void aba_queue_loop(const ModelDev<float>& M, const AbaArgs<float>& a, const ST& st) {
+  constexpr int NT = 32;
+  const int lane = threadIdx.x & 31;
+  unsigned long long* counter = reinterpret_cast<unsigned long long*>(a.scratch);
+  const int64_t ngroups = (a.B + NT - 1) / NT;
+  int64_t g = claim_group(counter);
+  while (g < ngroups) {
+    const int64_t gn = claim_group(counter);
+    if (gn < ngroups) {
+      const int64_t bn = gn * NT;
+      prefetch_rows(a.q, M.nq, a.ld, bn);
+      prefetch_rows(a.v, M.nv, a.ld, bn);
+      prefetch_rows(a.tau, M.nv, a.ld, bn);
+    }
+    const int64_t b = g * NT + lane;
+    const bool active = b < a.B;
+    const int64_t bl = active ? b : a.B - 1;
+    AbaIO<float, false, KINDS> io;
+    io.q = {a.q + bl, a.ld};
+    io.v = {a.v + bl, a.ld};
+    io.tau = {a.tau ? a.tau + bl : nullptr, a.ld};
+    io.wext = {nullptr, a.ld};
+    io.vd = {a.vd + bl, a.ld, active};
+    io.qd = {a.qd ? a.qd + bl : nullptr, a.ld, active};
+    io.ext = {nullptr, 0};
+    aba_sample<float, ST, false>(M, io, st);
+    g = gn;
+  }
+}
+template <int KINDS>
+__global__ void __launch_bounds__(32) aba_kernel_smem_q(const __grid_constant__ ModelDev<float> M, const AbaArgs<float> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  aba_queue_loop<Stash<float, 32>, KINDS>(M, a, Stash<float, 32>{reinterpret_cast<float*>(smem_raw) + threadIdx.x});
+}
+// CTA of 4 * WG warps: warp w owns TMEM lane quadrant w % 4 and the column range [(w / 4) * COLS / WG, ...).
+template <int COLS, int WG, int KINDS>
+__global__ void __launch_bounds__(128 * WG) aba_kernel_tmem_q(const __grid_constant__ ModelDev<float> M, const AbaArgs<float> a) {
+  __shared__ uint32_t tm_slot;
+  const uint32_t tm_base = tmem_alloc_cta<COLS>(&tm_slot);
+  const uint32_t warp = threadIdx.x >> 5;
+  aba_queue_loop<StashTM, KINDS>(M, a, StashTM{tm_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (COLS / WG)});
+  tmem_free_cta<COLS>(tm_base);
 }
 
 #if defined(RBD_EXPERIMENTS)
@@ -314,6 +369,57 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   const int sr = wext ? 6 * hm.nb : 0;
   bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
   for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
+  if constexpr (std::is_same<T, float>::value) {
+    // Default fp32 path for all-revolute trees whose stash fits 256 TMEM columns: the shared-memory kernel (8 warps/SM on
+    // Atlas) on `stream` plus the Tensor-Memory kernel (one 4-warp CTA per SM, stash in TMEM, no shared memory) on the
+    // handle's side stream, both claiming groups from one atomic counter.  12 resident warps/SM instead of 8.
+    const int64_t ngroups = (B + kNT - 1) / kNT;
+    if (!wext && !hm.general && !other_kinds && rows <= 256 && !getenv("RBD_NO_TMEM")) {
+      DeviceProps p;
+      if (int rc = get_props(p)) return rc;
+      auto ks = aba_kernel_smem_q<0>;
+      auto kt = aba_kernel_tmem_q<256, 1, 0>;
+      const size_t smem = (size_t)rows * kNT * sizeof(float);
+      int bps = 0;
+      if (int rc = configure(ks, kNT, smem, p, bps)) return rc;
+      if (ngroups >= (int64_t)(bps + 4) * p.sms) {        // enough work for every resident warp of both kernels
+        rbd_model* mm = const_cast<rbd_model*>(model);
+        cudaStream_t side = nullptr;
+        {
+          std::lock_guard<std::mutex> lk(mm->side_mu);
+          if (!mm->side_stream) CUDA_TRY(cudaStreamCreateWithFlags(&mm->side_stream, cudaStreamNonBlocking));
+          side = mm->side_stream;
+          static bool carveout_set = false;
+          if (!carveout_set) {
+            CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            carveout_set = true;
+          }
+        }
+        cudaEvent_t fork = nullptr, join = nullptr;
+        CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        void* counter = nullptr;
+        CUDA_TRY(cudaMallocAsync(&counter, 8, stream));
+        CUDA_TRY(cudaMemsetAsync(counter, 0, 8, stream));
+        AbaArgs<float> ah = a;
+        ah.scratch = (float*)counter;
+        CUDA_TRY(cudaEventRecord(fork, stream));
+        CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
+        ks<<<bps * p.sms, kNT, smem, stream>>>(M, ah);
+        kt<<<p.sms, 128, 0, side>>>(M, ah);
+        cudaError_t e = cudaGetLastError();
+        cudaEventRecord(join, side);
+        cudaStreamWaitEvent(stream, join, 0);
+        cudaFreeAsync(counter, stream);
+        cudaEventDestroy(fork);
+        cudaEventDestroy(join);
+        if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+        g_launch.kernels_launched += 2;
+        g_launch.grid = bps * p.sms; g_launch.block = kNT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
+        return RBD_OK;
+      }
+    }
+  }
 #define RBD_ABA(G, E, K) launch<T>(aba_kernel<T, kNT, G, E, K>, M, a, kNT, rows, sr, stream)
   if (hm.general) return wext ? RBD_ABA(true, true, kAllKinds) : RBD_ABA(true, false, kAllKinds);
   if (other_kinds) return wext ? RBD_ABA(false, true, kAllKinds) : RBD_ABA(false, false, kAllKinds);
@@ -507,6 +613,7 @@ int32_t rbd_model_destroy(rbd_model* m) {
     if (m->d_stage[i]) cudaFree(m->d_stage[i]);
     if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
   }
+  if (m->side_stream) cudaStreamDestroy(m->side_stream);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   delete m;

@@ -1,0 +1,50 @@
+// Tensor Memory as a per-thread scratchpad (sm_100a only).
+//
+// Each SM has 256 KB of TMEM (512 columns x 128 lanes x 32 bit) next to its 228 KB of shared memory.  It exists to hold
+// tcgen05.mma accumulators, but tcgen05.ld / tcgen05.st move 32-bit words between registers and TMEM with the "32x32b"
+// shape: lane l of warp w touches TMEM lane 32*(w % 4) + l, one column per register.  That is exactly the access pattern of
+// this library's stash (one private scalar per thread and row), so a CTA of 128 threads that allocates N columns gets N
+// private words per thread -- a second on-chip home for the per-sample working set, doubling the number of samples an SM
+// can keep in flight for this latency-bound kernel.
+#pragma once
+#include <stdint.h>
+
+namespace rbd {
+
+#if defined(__CUDACC__)
+struct StashTM {
+  uint32_t base;     // TMEM address of row 0 for this warp: (lane quadrant << 16) | first column
+
+  __device__ __forceinline__ float ld(int row) const {
+    uint32_t r;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(base + (uint32_t)row) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
+  }
+  __device__ __forceinline__ void st(int row, float v) const {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(base + (uint32_t)row), "r"(__float_as_uint(v)) : "memory");
+  }
+  __device__ __forceinline__ void add(int row, float v) const { st(row, ld(row) + v); }
+  __device__ __forceinline__ const StashTM& slots() const { return *this; }
+};
+
+// Allocate `cols` (power of two >= 32) TMEM columns for the CTA; every thread returns the base address.
+template <uint32_t COLS> __device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t* smem_slot) {
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *smem_slot;
+}
+template <uint32_t COLS> __device__ __forceinline__ void tmem_free_cta(uint32_t addr) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+#endif
+
+}  // namespace rbd
