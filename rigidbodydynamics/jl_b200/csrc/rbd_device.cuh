@@ -99,6 +99,11 @@ template <class T, int STRIDE> struct Stash {
   RBD_HD T ld(int row) const { return p[row * STRIDE]; }
   RBD_HD void st(int row, T v) const { p[row * STRIDE] = v; }
   RBD_HD void add(int row, T v) const { p[row * STRIDE] += v; }
+  template <int N> RBD_HD void ldv(int row, T* out) const {
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = p[(row + k) * STRIDE];
+  }
+  RBD_HD void fence_st() const {}                          // stores are visible to later loads of the same thread
   RBD_HD const Stash& slots() const { return *this; }     // pending slots live in the same array
 };
 // STRIDE == 0: runtime stride (the stash lives in a global-memory scratch, one column per resident thread)
@@ -108,6 +113,11 @@ template <class T> struct Stash<T, 0> {
   RBD_HD T ld(int row) const { return p[(int64_t)row * stride]; }
   RBD_HD void st(int row, T v) const { p[(int64_t)row * stride] = v; }
   RBD_HD void add(int row, T v) const { p[(int64_t)row * stride] += v; }
+  template <int N> RBD_HD void ldv(int row, T* out) const {
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = p[(int64_t)(row + k) * stride];
+  }
+  RBD_HD void fence_st() const {}
   RBD_HD const Stash& slots() const { return *this; }
 };
 // Body rows in shared memory ([row][lane]); the pending slots -- touched only a handful of times per sample -- in a
@@ -120,11 +130,21 @@ template <class T, int STRIDE> struct StashGS {
   RBD_HD T ld(int row) const { return p[row * STRIDE]; }
   RBD_HD void st(int row, T v) const { p[row * STRIDE] = v; }
   RBD_HD void add(int row, T v) const { p[row * STRIDE] += v; }
+  template <int N> RBD_HD void ldv(int row, T* out) const {
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = p[(row + k) * STRIDE];
+  }
+  RBD_HD void fence_st() const {}
   struct Slots {
     T* g; int64_t gstride; int base;
     RBD_HD T ld(int row) const { return g[(int64_t)(row - base) * gstride]; }
     RBD_HD void st(int row, T v) const { g[(int64_t)(row - base) * gstride] = v; }
     RBD_HD void add(int row, T v) const { g[(int64_t)(row - base) * gstride] += v; }
+    template <int N> RBD_HD void ldv(int row, T* out) const {
+#pragma unroll
+      for (int k = 0; k < N; ++k) out[k] = g[(int64_t)(row + k - base) * gstride];
+    }
+    RBD_HD void fence_st() const {}
   };
   RBD_HD Slots slots() const { return Slots{g, gstride, slot_base}; }
 };
@@ -398,8 +418,8 @@ template <class T, class S> RBD_HD void art_accum(const S& st, int row, const Ar
   // all loads first, then all stores: a store to the stash may alias a later load as far as the compiler can tell, and
   // interleaving them would serialise 27 memory round trips
   T t[27];
-#pragma unroll
-  for (int k = 0; k < 27; ++k) t[k] = st.ld(row + k);
+  st.fence_st();
+  st.template ldv<27>(row, t);
 #pragma unroll
   for (int k = 0; k < 6; ++k) { t[k] += a.A[k]; t[15 + k] += a.C[k]; }
 #pragma unroll
@@ -410,12 +430,15 @@ template <class T, class S> RBD_HD void art_accum(const S& st, int row, const Ar
   for (int k = 0; k < 27; ++k) st.st(row + k, t[k]);
 }
 template <class T, class S> RBD_HD void art_add_from(const S& st, int row, Art<T>& a) {
+  T t[27];
+  st.fence_st();
+  st.template ldv<27>(row, t);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { a.A[k] += st.ld(row + k); a.C[k] += st.ld(row + 15 + k); }
+  for (int k = 0; k < 6; ++k) { a.A[k] += t[k]; a.C[k] += t[15 + k]; }
 #pragma unroll
-  for (int k = 0; k < 9; ++k) a.B[k] += st.ld(row + 6 + k);
+  for (int k = 0; k < 9; ++k) a.B[k] += t[6 + k];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { a.n[k] += st.ld(row + 21 + k); a.f[k] += st.ld(row + 24 + k); }
+  for (int k = 0; k < 3; ++k) { a.n[k] += t[21 + k]; a.f[k] += t[24 + k]; }
 }
 
 // X^T I X and X^T p for the child -> parent hand-over: rotate the 3x3 blocks by R, then shift the origin by r.
@@ -647,8 +670,11 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const ST& 
     vp = vcur;
   } else {
     const int pr = M.body[bd.parent].row0;
+    T t[6];
+    st.fence_st();
+    st.template ldv<6>(pr, t);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { vp.w[k] = st.ld(pr + k); vp.l[k] = st.ld(pr + 3 + k); }
+    for (int k = 0; k < 3; ++k) { vp.w[k] = t[k]; vp.l[k] = t[3 + k]; }
   }
   const int kind = bd.kind;
   T R[9], r[3];
@@ -721,8 +747,12 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
   Mot<T> v;
+  {
+    T t[6];
+    st.template ldv<6>(bd.row0, t);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { v.w[k] = st.ld(bd.row0 + k); v.l[k] = st.ld(bd.row0 + 3 + k); }
+    for (int k = 0; k < 3; ++k) { v.w[k] = t[k]; v.l[k] = t[3 + k]; }
+  }
   Art<T> a;
   art_set_body(bd, a);
   bias_force(bd, v, a.n, a.f);
@@ -927,11 +957,11 @@ RBD_HD void load_parent_va(const ModelDev<T>& M, const BodyDev<T>& bd, const ST&
   } else {
     const int row = M.slot_base + bd.pslot * kSlotRowsAba;
     const auto sl = st.slots();
+    T t[12];
+    sl.fence_st();
+    sl.template ldv<12>(row, t);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      vp.w[k] = sl.ld(row + k); vp.l[k] = sl.ld(row + 3 + k);
-      ap.w[k] = sl.ld(row + 6 + k); ap.l[k] = sl.ld(row + 9 + k);
-    }
+    for (int k = 0; k < 3; ++k) { vp.w[k] = t[k]; vp.l[k] = t[3 + k]; ap.w[k] = t[6 + k]; ap.l[k] = t[9 + k]; }
   }
 }
 template <class T, class ST>
@@ -966,8 +996,9 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
   T sn, c, dd;
   joint_scd(kind, pre, sn, c, dd);
   const T qd = pre.qd;
-  const T t0 = st.ld(bd.row0 + 0), t1 = st.ld(bd.row0 + 1), t2 = st.ld(bd.row0 + 2), t3 = st.ld(bd.row0 + 3),
-          t4 = st.ld(bd.row0 + 4), tu = st.ld(bd.row0 + 5);
+  T tt[6];
+  st.template ldv<6>(bd.row0, tt);
+  const T t0 = tt[0], t1 = tt[1], t2 = tt[2], t3 = tt[3], t4 = tt[4], tu = tt[5];
   Mot<T> a;
   if (!(IO::kKinds & kHasPris) || kind != K_PRIS) {
     frame_1dof(bd, sn, c, T(0), R, r);
@@ -1044,12 +1075,14 @@ RBD_HD void aba_pass1_pair(const ModelDev<T>& M, int i0, int i1, const IO& io, c
   if (b0.flags & F_FIRST_CHILD) vp0 = v0;
   else {
     const int pr = M.body[b0.parent].row0;
+    st.fence_st();
 #pragma unroll
     for (int k = 0; k < 3; ++k) { vp0.w[k] = st.ld(pr + k); vp0.l[k] = st.ld(pr + 3 + k); }
   }
   if (b1.flags & F_FIRST_CHILD) vp1 = v1;
   else {
     const int pr = M.body[b1.parent].row0;
+    st.fence_st();
 #pragma unroll
     for (int k = 0; k < 3; ++k) { vp1.w[k] = st.ld(pr + k); vp1.l[k] = st.ld(pr + 3 + k); }
   }
@@ -1176,6 +1209,7 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
     i = in;
   }
   // ---- pass 2 ----
+  st.fence_st();
   Art<T> carry, carryB;
 #pragma unroll
   for (int k = 0; k < 6; ++k) { carry.A[k] = T(0); carry.C[k] = T(0); carryB.A[k] = T(0); carryB.C[k] = T(0); }
@@ -1216,6 +1250,7 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
     if (PAIRS) prefetch_body<T, 3>(M, first < nb ? M.body[first].pair : -1, io, nxtB);
     if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass2_1dof(M, 0, io, st, carry, cur);
+      st.fence_st();
       aba_pass3_1dof(M, 0, io, st, vcur, acur, cur);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
       aba_pass2_multi<T, ST, 6, K_QFLOAT, true>(M, 0, io, st, carry, vcur, acur);
@@ -1229,6 +1264,7 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
     }
   }
   // ---- pass 3 ----
+  st.fence_st();
   cur = nxt; curB = nxtB;
   for (int i = first; i < nb;) {
     const int kind = M.body[i].kind;

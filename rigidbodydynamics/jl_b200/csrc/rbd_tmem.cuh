@@ -15,17 +15,27 @@ namespace rbd {
 struct StashTM {
   uint32_t base;     // TMEM address of row 0 for this warp: (lane quadrant << 16) | first column
 
-  __device__ __forceinline__ float ld(int row) const {
-    uint32_t r;
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(base + (uint32_t)row) : "memory");
+  // tcgen05.st is asynchronous: a later tcgen05.ld of the same word needs tcgen05.wait::st in between.  The algorithms
+  // call fence_st() exactly where a thread re-reads what it wrote (pass boundaries, pending slots, parent rows).
+  __device__ __forceinline__ void fence_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+  template <int N> __device__ __forceinline__ void ldv(int row, float* out) const {
+    uint32_t r[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[k]) : "r"(base + (uint32_t)(row + k)) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    return __uint_as_float(r);
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = __uint_as_float(r[k]);
+  }
+  __device__ __forceinline__ float ld(int row) const {
+    float v;
+    ldv<1>(row, &v);
+    return v;
   }
   __device__ __forceinline__ void st(int row, float v) const {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(base + (uint32_t)row), "r"(__float_as_uint(v)) : "memory");
   }
-  __device__ __forceinline__ void add(int row, float v) const { st(row, ld(row) + v); }
+  __device__ __forceinline__ void add(int row, float v) const { fence_st(); st(row, ld(row) + v); }
   __device__ __forceinline__ const StashTM& slots() const { return *this; }
 };
 

@@ -85,7 +85,8 @@ def test_host_pointer_entry_point(built):
     rbd._cabi.check(lib.rbd_dynamics_host(state.handle.ptr, 0, B, B, hq.data_ptr(), hv.data_ptr(), ht.data_ptr(), None,
                                           out.data_ptr(), None))
     assert np.array_equal(out.numpy().astype(np.float64), got_dev)
-    assert rbd.launch_info().kernels_launched == 2
+    # two chunks; the full one runs as the shared-memory + Tensor-Memory kernel pair, the 777-sample tail as one kernel
+    assert rbd.launch_info().kernels_launched in (2, 3)
 
 
 def test_errors_match_reference_behaviour(built):
