@@ -655,9 +655,9 @@ int32_t rbd_get_launch_info(rbd_launch_info* info) {
 int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                      const void* tau, const void* wext, void* vd_out, void* qd_out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (!q || !v || !vd_out) return fail(RBD_EINVAL, "rbd_dynamics: q, v and vd_out must not be NULL");
   g_launch = {0, 0, 0, 0, 0, 0.f};
-  if (B == 0) return RBD_OK;
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q || !v || !vd_out) return fail(RBD_EINVAL, "rbd_dynamics: q, v and vd_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == RBD_DUAL64X6) {
     if (wext || qd_out) return fail(RBD_EUNSUPPORTED, "RBD_DUAL64X6: external wrenches / q̇ output are not implemented");
@@ -670,9 +670,9 @@ int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t l
 int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                              const void* v, const void* vd, const void* wext, void* tau_out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (!q || !v || !vd || !tau_out) return fail(RBD_EINVAL, "rbd_inverse_dynamics: q, v, vd and tau_out must not be NULL");
   g_launch = {0, 0, 0, 0, 0, 0.f};
-  if (B == 0) return RBD_OK;
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q || !v || !vd || !tau_out) return fail(RBD_EINVAL, "rbd_inverse_dynamics: q, v, vd and tau_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
   return dtype == RBD_F32 ? inverse_dynamics_t<float>(model, B, ld, q, v, vd, wext, tau_out, s)
                           : inverse_dynamics_t<double>(model, B, ld, q, v, vd, wext, tau_out, s);
@@ -681,9 +681,9 @@ int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, i
 int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                           const void* v, const void* wext, void* c_out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (!q || !v || !c_out) return fail(RBD_EINVAL, "rbd_dynamics_bias: q, v and c_out must not be NULL");
   g_launch = {0, 0, 0, 0, 0, 0.f};
-  if (B == 0) return RBD_OK;
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q || !v || !c_out) return fail(RBD_EINVAL, "rbd_dynamics_bias: q, v and c_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
   return dtype == RBD_F32 ? inverse_dynamics_t<float>(model, B, ld, q, v, nullptr, wext, c_out, s)
                           : inverse_dynamics_t<double>(model, B, ld, q, v, nullptr, wext, c_out, s);
@@ -692,9 +692,9 @@ int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int6
 int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
                         void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix: q and M_out must not be NULL");
   g_launch = {0, 0, 0, 0, 0, 0.f};
-  if (B == 0) return RBD_OK;
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix: q and M_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
   return dtype == RBD_F32 ? mass_matrix_t<float>(model, B, ld, q, M_out, s) : mass_matrix_t<double>(model, B, ld, q, M_out, s);
 }
@@ -705,9 +705,9 @@ int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_
 int32_t rbd_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                           const void* tau, const void* wext, void* vd_out, void* qd_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (!q || !v || !vd_out) return fail(RBD_EINVAL, "rbd_dynamics_host: q, v and vd_out must not be NULL");
   g_launch = {0, 0, 0, 0, 0, 0.f};
-  if (B == 0) return RBD_OK;
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q || !v || !vd_out) return fail(RBD_EINVAL, "rbd_dynamics_host: q, v and vd_out must not be NULL");
   const HostModel& hm = model->hm;
   const HostArr ins[4] = {{q, nullptr, hm.nq}, {v, nullptr, hm.nv}, {tau, nullptr, hm.nv}, {wext, nullptr, 6 * hm.nb}};
   const HostArr outs[2] = {{nullptr, vd_out, hm.nv}, {nullptr, qd_out, hm.nq}};
@@ -722,9 +722,9 @@ int32_t rbd_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld
 int32_t rbd_inverse_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                                   const void* v, const void* vd, const void* wext, void* tau_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (!q || !v || !vd || !tau_out) return fail(RBD_EINVAL, "rbd_inverse_dynamics_host: q, v, vd and tau_out must not be NULL");
   g_launch = {0, 0, 0, 0, 0, 0.f};
-  if (B == 0) return RBD_OK;
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q || !v || !vd || !tau_out) return fail(RBD_EINVAL, "rbd_inverse_dynamics_host: q, v, vd and tau_out must not be NULL");
   const HostModel& hm = model->hm;
   const HostArr ins[4] = {{q, nullptr, hm.nq}, {v, nullptr, hm.nv}, {vd, nullptr, hm.nv}, {wext, nullptr, 6 * hm.nb}};
   const HostArr outs[1] = {{nullptr, tau_out, hm.nv}};
@@ -739,9 +739,9 @@ int32_t rbd_inverse_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, in
 int32_t rbd_dynamics_bias_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                                const void* v, const void* wext, void* c_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (!q || !v || !c_out) return fail(RBD_EINVAL, "rbd_dynamics_bias_host: q, v and c_out must not be NULL");
   g_launch = {0, 0, 0, 0, 0, 0.f};
-  if (B == 0) return RBD_OK;
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q || !v || !c_out) return fail(RBD_EINVAL, "rbd_dynamics_bias_host: q, v and c_out must not be NULL");
   const HostModel& hm = model->hm;
   const HostArr ins[3] = {{q, nullptr, hm.nq}, {v, nullptr, hm.nv}, {wext, nullptr, 6 * hm.nb}};
   const HostArr outs[1] = {{nullptr, c_out, hm.nv}};
@@ -755,9 +755,9 @@ int32_t rbd_dynamics_bias_host(rbd_model* model, int32_t dtype, int64_t B, int64
 
 int32_t rbd_mass_matrix_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix_host: q and M_out must not be NULL");
   g_launch = {0, 0, 0, 0, 0, 0.f};
-  if (B == 0) return RBD_OK;
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix_host: q and M_out must not be NULL");
   const HostModel& hm = model->hm;
   const HostArr ins[1] = {{q, nullptr, hm.nq}};
   const HostArr outs[1] = {{nullptr, M_out, hm.nv * hm.nv}};

@@ -246,3 +246,92 @@ def test_dual_number_dynamics_gpu(built, name, floating, B):
     res = rbd.DynamicsResult(mech, B, torch.float64)
     rbd.dynamics_(res, st2, _cu(tau, torch.float64), want_qd=False)
     assert torch.equal(res.vd, out[..., 0])
+
+
+def test_edge_cases_empty_padded_and_defaults(built):
+    """Edge cases of the C ABI: empty batch (no launch), leading dimension larger than the batch, default (NULL) torques,
+    optional q̇ output, single-body model, and the largest supported model (64-body chain)."""
+    lib = rbd.load_library()
+    mech = rbd.load_model("iiwa14")
+    o = Oracle(mech.flatten())
+    st = rbd.MechanismState(mech, 1, torch.float64)
+    # B = 0: RBD_OK, nothing launched
+    z = torch.empty((7, 0), dtype=torch.float64, device="cuda")
+    assert lib.rbd_dynamics(st.handle.ptr, 1, 0, 0, z.data_ptr(), z.data_ptr(), None, None, z.data_ptr(), None, None) == 0
+    assert rbd.launch_info().kernels_launched == 0
+    # ld > B: rows are 50 apart, only the first 37 columns are a batch
+    B, ld = 37, 50
+    q, v, tau, _, _ = rand_inputs(mech, B, 8)
+    pad = lambda a: torch.from_numpy(np.pad(a, ((0, 0), (0, ld - B)), constant_values=np.nan)).cuda()
+    Q, V, T = pad(q), pad(v), pad(tau)
+    out = torch.full((7, ld), float("nan"), dtype=torch.float64, device="cuda")
+    rbd._cabi.check(lib.rbd_dynamics(st.handle.ptr, 1, B, ld, Q.data_ptr(), V.data_ptr(), T.data_ptr(), None,
+                                     out.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    assert rel_err(out[:, :B].cpu().numpy(), o.dynamics(q, v, tau)) < 1e-9
+    assert bool(torch.isnan(out[:, B:]).all())                       # the padding is never written
+    # default torques (NULL) == zero torques
+    got, _ = gpu_dynamics(mech, q, v, None, torch.float64)
+    assert rel_err(got, o.dynamics(q, v, np.zeros_like(tau))) < 1e-9
+    # one revolute body
+    rng = np.random.default_rng(3)
+    one = rbd.rand_chain_mechanism(rng, [rbd.Revolute])
+    q1, v1, t1, _, _ = rand_inputs(one, 5, 1)
+    got, _ = gpu_dynamics(one, q1, v1, t1, torch.float64)
+    assert rel_err(got, Oracle(one.flatten()).dynamics(q1, v1, t1)) < 1e-10
+    # RBD_MAX_BODIES-long chain (fp64 and fp32 kernels; the stash no longer fits Tensor Memory's 256 columns -> single kernel)
+    big = rbd.rand_chain_mechanism(rng, [rbd.Revolute] * 64)
+    qb, vb, tb, _, _ = rand_inputs(big, 40, 2)
+    ref = Oracle(big.flatten()).dynamics(qb, vb, tb)
+    got, _ = gpu_dynamics(big, qb, vb, tb, torch.float64)
+    assert rel_err(got, ref) < 1e-8
+    got32, _ = gpu_dynamics(big, qb, vb, tb, torch.float32)
+    assert rel_err(got32, ref) < 5e-3
+
+
+def test_concurrent_streams_and_cuda_graph(built):
+    """The plain entry points are asynchronous on the caller's stream: two streams evaluate different batches concurrently,
+    and a call can be captured into a CUDA graph (fork/join to the side stream included) and replayed."""
+    mech = rbd.load_model("atlas", floating=True)
+    o = Oracle(mech.flatten())
+    B = 1 << 16
+    rng = np.random.default_rng(5)
+    states, taus, results, streams = [], [], [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for k in range(2):
+        st = rbd.MechanismState(mech, B, torch.float32)
+        rbd.rand_(st, rng)
+        states.append(st)
+        taus.append(torch.rand((36, B), dtype=torch.float32, device="cuda"))
+        results.append(rbd.DynamicsResult(mech, B, torch.float32))
+    torch.cuda.synchronize()
+    for _ in range(3):
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                rbd.dynamics_(results[k], states[k], taus[k], want_qd=False)
+    torch.cuda.synchronize()
+    for k in range(2):
+        n = 64
+        ref = o.dynamics(states[k].q[:, :n].double().cpu().numpy(), states[k].v[:, :n].double().cpu().numpy(),
+                         taus[k][:, :n].double().cpu().numpy())
+        assert rel_err(results[k].vd[:, :n].double().cpu().numpy(), ref) < 2e-5
+    # CUDA graph: capture one evaluation, change the inputs in place, replay
+    g = torch.cuda.CUDAGraph()
+    expected = results[0].vd.clone()
+    results[0].vd.zero_()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        rbd.dynamics_(results[0], states[0], taus[0], want_qd=False)      # warm-up outside capture
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            rbd.dynamics_(results[0], states[0], taus[0], want_qd=False)
+    results[0].vd.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(results[0].vd, expected)
+    taus[0].mul_(0.5)
+    g.replay()
+    torch.cuda.synchronize()
+    n = 32
+    ref = o.dynamics(states[0].q[:, :n].double().cpu().numpy(), states[0].v[:, :n].double().cpu().numpy(),
+                     taus[0][:, :n].double().cpu().numpy())
+    assert rel_err(results[0].vd[:, :n].double().cpu().numpy(), ref) < 2e-5
