@@ -147,8 +147,8 @@ __device__ __forceinline__ int64_t claim_group(unsigned long long* counter) {
   if ((threadIdx.x & 31) == 0) g = atomicAdd(counter, 1ull);
   return (int64_t)__shfl_sync(0xffffffffu, g, 0);
 }
-template <class ST, int KINDS>
-__device__ __forceinline__ void aba_queue_loop(const ModelDev<float>& M, const AbaArgs<float>& a, const ST& st) {
+template <class T, class ST, int KINDS>
+__device__ __forceinline__ void aba_queue_loop(const ModelDev<T>& M, const AbaArgs<T>& a, const ST& st) {
   constexpr int NT = 32;
   const int lane = threadIdx.x & 31;
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(a.scratch);
@@ -165,7 +165,7 @@ __device__ __forceinline__ void aba_queue_loop(const ModelDev<float>& M, const A
     const int64_t b = g * NT + lane;
     const bool active = b < a.B;
     const int64_t bl = active ? b : a.B - 1;
-    AbaIO<float, false, KINDS> io;
+    AbaIO<T, false, KINDS> io;
     io.q = {a.q + bl, a.ld};
     io.v = {a.v + bl, a.ld};
     io.tau = {a.tau ? a.tau + bl : nullptr, a.ld};
@@ -173,22 +173,22 @@ __device__ __forceinline__ void aba_queue_loop(const ModelDev<float>& M, const A
     io.vd = {a.vd + bl, a.ld, active};
     io.qd = {a.qd ? a.qd + bl : nullptr, a.ld, active};
     io.ext = {nullptr, 0};
-    aba_sample<float, ST, false>(M, io, st);
+    aba_sample<T, ST, false>(M, io, st);
     g = gn;
   }
 }
-template <int KINDS>
-__global__ void __launch_bounds__(32) aba_kernel_smem_q(const __grid_constant__ ModelDev<float> M, const AbaArgs<float> a) {
+template <class T, int KINDS>
+__global__ void __launch_bounds__(32) aba_kernel_smem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  aba_queue_loop<Stash<float, 32>, KINDS>(M, a, Stash<float, 32>{reinterpret_cast<float*>(smem_raw) + threadIdx.x});
+  aba_queue_loop<T, Stash<T, 32>, KINDS>(M, a, Stash<T, 32>{reinterpret_cast<T*>(smem_raw) + threadIdx.x});
 }
-// CTA of 4 * WG warps: warp w owns TMEM lane quadrant w % 4 and the column range [(w / 4) * COLS / WG, ...).
-template <int COLS, int WG, int KINDS>
-__global__ void __launch_bounds__(128 * WG) aba_kernel_tmem_q(const __grid_constant__ ModelDev<float> M, const AbaArgs<float> a) {
+// CTA of 4 warps: warp w owns TMEM lane quadrant w; COLS columns per thread (fp32: one per row, fp64: two per row).
+template <class T, int COLS, int KINDS>
+__global__ void __launch_bounds__(128) aba_kernel_tmem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   __shared__ uint32_t tm_slot;
   const uint32_t tm_base = tmem_alloc_cta<COLS>(&tm_slot);
-  const uint32_t warp = threadIdx.x >> 5;
-  aba_queue_loop<StashTM, KINDS>(M, a, StashTM{tm_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (COLS / WG)});
+  using ST = typename StashTMFor<T>::type;
+  aba_queue_loop<T, ST, KINDS>(M, a, ST{tm_base + ((uint32_t)((threadIdx.x >> 5) * 32) << 16)});
   tmem_free_cta<COLS>(tm_base);
 }
 
@@ -369,17 +369,18 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   const int sr = wext ? 6 * hm.nb : 0;
   bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
   for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
-  if constexpr (std::is_same<T, float>::value) {
-    // Default fp32 path for all-revolute trees whose stash fits 256 TMEM columns: the shared-memory kernel (8 warps/SM on
-    // Atlas) on `stream` plus the Tensor-Memory kernel (one 4-warp CTA per SM, stash in TMEM, no shared memory) on the
-    // handle's side stream, both claiming groups from one atomic counter.  12 resident warps/SM instead of 8.
+  {
+    // Default path for all-revolute trees whose stash fits Tensor Memory (fp32: <= 256 rows in 256 columns, fp64: <= 256 rows
+    // in 512 columns): the shared-memory kernel on `stream` plus the Tensor-Memory kernel (one 4-warp CTA per SM, stash in
+    // TMEM, no shared memory) on the handle's side stream, both claiming groups from one atomic counter.  On Atlas that is
+    // 8 + 4 resident warps/SM in fp32 and 4 + 4 in fp64.
     const int64_t ngroups = (B + kNT - 1) / kNT;
     if (!wext && !hm.general && !other_kinds && rows <= 256 && !getenv("RBD_NO_TMEM")) {
       DeviceProps p;
       if (int rc = get_props(p)) return rc;
-      auto ks = aba_kernel_smem_q<0>;
-      auto kt = aba_kernel_tmem_q<256, 1, 0>;
-      const size_t smem = (size_t)rows * kNT * sizeof(float);
+      auto ks = aba_kernel_smem_q<T, 0>;
+      auto kt = aba_kernel_tmem_q<T, 256 * StashTMFor<T>::kColsPerRow, 0>;
+      const size_t smem = (size_t)rows * kNT * sizeof(T);
       int bps = 0;
       if (int rc = configure(ks, kNT, smem, p, bps)) return rc;
       if (ngroups >= (int64_t)(bps + 4) * p.sms) {        // enough work for every resident warp of both kernels
@@ -389,11 +390,7 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
           std::lock_guard<std::mutex> lk(mm->side_mu);
           if (!mm->side_stream) CUDA_TRY(cudaStreamCreateWithFlags(&mm->side_stream, cudaStreamNonBlocking));
           side = mm->side_stream;
-          static bool carveout_set = false;
-          if (!carveout_set) {
-            CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            carveout_set = true;
-          }
+          CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
         cudaEvent_t fork = nullptr, join = nullptr;
         CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
@@ -401,15 +398,16 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
         void* counter = nullptr;
         CUDA_TRY(cudaMallocAsync(&counter, 8, stream));
         CUDA_TRY(cudaMemsetAsync(counter, 0, 8, stream));
-        AbaArgs<float> ah = a;
-        ah.scratch = (float*)counter;
+        AbaArgs<T> ah = a;
+        ah.scratch = (T*)counter;
         CUDA_TRY(cudaEventRecord(fork, stream));
         CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
         // (profiling aid: under ncu kernels are serialised and the first one drains the queue; RBD_ONLY=smem|tmem launches
         //  just one of the two so each can be captured doing the whole batch)
         const char* only = getenv("RBD_ONLY");
+        if (getenv("RBD_SMEM_BLOCKS")) bps = std::min(bps, atoi(getenv("RBD_SMEM_BLOCKS")));
         if (!only || only[0] == 's') ks<<<bps * p.sms, kNT, smem, stream>>>(M, ah);
-        if (!only || only[0] == 't') kt<<<(only ? 2 : 1) * p.sms, 128, 0, side>>>(M, ah);
+        if (!only || only[0] == 't') kt<<<((only && sizeof(T) == 4) ? 2 : 1) * p.sms, 128, 0, side>>>(M, ah);
         cudaError_t e = cudaGetLastError();
         cudaEventRecord(join, side);
         cudaStreamWaitEvent(stream, join, 0);

@@ -39,6 +39,34 @@ struct StashTM {
   __device__ __forceinline__ const StashTM& slots() const { return *this; }
 };
 
+// fp64 stash in Tensor Memory: one row = two adjacent 32-bit columns (tcgen05.ld/st .x2).
+struct StashTM64 {
+  uint32_t base;
+  __device__ __forceinline__ void fence_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+  template <int N> __device__ __forceinline__ void ldv(int row, double* out) const {
+    uint32_t lo[N], hi[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo[k]), "=r"(hi[k]) : "r"(base + 2u * (uint32_t)(row + k)) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = __hiloint2double((int)hi[k], (int)lo[k]);
+  }
+  __device__ __forceinline__ double ld(int row) const {
+    double v;
+    ldv<1>(row, &v);
+    return v;
+  }
+  __device__ __forceinline__ void st(int row, double v) const {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(base + 2u * (uint32_t)row), "r"((uint32_t)__double2loint(v)), "r"((uint32_t)__double2hiint(v)) : "memory");
+  }
+  __device__ __forceinline__ void add(int row, double v) const { fence_st(); st(row, ld(row) + v); }
+  __device__ __forceinline__ const StashTM64& slots() const { return *this; }
+};
+template <class T> struct StashTMFor;
+template <> struct StashTMFor<float> { using type = StashTM; static constexpr int kColsPerRow = 1; };
+template <> struct StashTMFor<double> { using type = StashTM64; static constexpr int kColsPerRow = 2; };
+
 // Allocate `cols` (power of two >= 32) TMEM columns for the CTA; every thread returns the base address.
 template <uint32_t COLS> __device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t* smem_slot) {
   if (threadIdx.x < 32) {

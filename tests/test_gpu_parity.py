@@ -335,3 +335,28 @@ def test_concurrent_streams_and_cuda_graph(built):
     ref = o.dynamics(states[0].q[:, :n].double().cpu().numpy(), states[0].v[:, :n].double().cpu().numpy(),
                      taus[0][:, :n].double().cpu().numpy())
     assert rel_err(results[0].vd[:, :n].double().cpu().numpy(), ref) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_large_batch_uses_tensor_memory_path(built, dtype):
+    """At batch 2^16 (config 2's size) the default path is the shared-memory kernel PLUS the Tensor-Memory kernel fed from one
+    work queue (2 launches); whichever kernel evaluates a sample, the result must match the oracle and be bit-identical to the
+    single-kernel path (small batches) on the same sample."""
+    mech = rbd.load_model("atlas", floating=True)
+    B = 1 << 16
+    st = rbd.MechanismState(mech, B, dtype)
+    rbd.rand_(st, np.random.default_rng(21))
+    tau = torch.rand((36, B), dtype=dtype, device="cuda")
+    res = rbd.DynamicsResult(mech, B, dtype)
+    rbd.dynamics_(res, st, tau, want_qd=False)
+    assert rbd.launch_info().kernels_launched == 2
+    idx = torch.arange(0, B, 509, device="cuda")
+    sub = rbd.MechanismState(mech, idx.numel(), dtype)
+    sub.q.copy_(st.q[:, idx]); sub.v.copy_(st.v[:, idx])
+    res2 = rbd.DynamicsResult(mech, idx.numel(), dtype)
+    rbd.dynamics_(res2, sub, tau[:, idx].contiguous(), want_qd=False)
+    assert rbd.launch_info().kernels_launched == 1
+    assert torch.equal(res2.vd, res.vd[:, idx])
+    ref = Oracle(mech.flatten()).dynamics(sub.q.double().cpu().numpy(), sub.v.double().cpu().numpy(),
+                                          tau[:, idx].double().cpu().numpy())
+    assert rel_err(res2.vd.double().cpu().numpy(), ref) < TOL[dtype]
