@@ -164,6 +164,8 @@ def other_configs(steps):
     tout = torch.empty_like(vd)
     ms = time_fn(lambda: rbd.inverse_dynamics_(tout, st, vd), steps)
     out["atlas_f32_inverse_dynamics_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * 580 / (ms * 1e-3) / 1e9}
+    ms = time_fn(lambda: rbd.simulate_(st, 1e-4, tau, dt=1e-4), max(3, steps // 4))      # one Munthe-Kaas RK4 step (4 dynamics)
+    out["atlas_f32_rk4_step_b1048576"] = {"sample_steps_per_s": B / (ms * 1e-3), "ms": ms, "kernel_launches_per_step": rbd.launch_info().kernels_launched}
     del res, wext, tau, vd, tout, st
     iiwa = rbd.load_model("iiwa14")
     st = rbd.MechanismState(iiwa, B, torch.float32)

@@ -160,6 +160,16 @@ int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int6
 int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
                         void* stream);
 
+/* Next row of the scope table, the main caller of dynamics!:
+ * simulate(state0, final_time, control!; dt) with the default passive / constant-torque control
+ *                                                             src/simulate.jl:36-55
+ * = `nsteps` steps of MuntheKaasIntegrator with the runge_kutta_4 tableau   src/ode_integrators.jl:48-55, 233-300
+ *   (stages in local coordinates around the configuration at the start of the step; local_coordinates! /
+ *   global_coordinates! per joint type, src/mechanism_state.jl:1057-1085).
+ *   q [nq x B], v [nv x B] are updated IN PLACE; tau [nv x B] or NULL is held constant over the call. */
+int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,
+                      double dt, int32_t nsteps, void* stream);
+
 /* Host-pointer variants: same semantics, host buffers in, host buffers out, copies inside the call. */
 int32_t rbd_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                           const void* tau, const void* wext, void* vd_out, void* qd_out);

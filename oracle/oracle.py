@@ -31,6 +31,7 @@ def _load():
     lib.rbdo_nv.argtypes = [vp]
     lib.rbdo_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32, i32]
     lib.rbdo_dynamics_dual6.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32]
+    lib.rbdo_integrate.argtypes = [vp, i64, vp, vp, vp, ctypes.c_double, i32, i32]
     lib.rbdo_inverse_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32]
     lib.rbdo_mass_matrix.argtypes = [vp, i32, i64, vp, vp, i32]
     return lib
@@ -105,6 +106,15 @@ class Oracle:
         if rc != 0:
             raise np.linalg.LinAlgError("mass matrix not positive definite")
         return vd
+
+    def integrate(self, q, v, tau=None, *, dt=1e-4, nsteps=1, nthreads=1):
+        """simulate(): ``nsteps`` Munthe-Kaas RK4 steps with constant torques (fp64); returns (q, v)."""
+        q = np.array(self._prep(q, self.nq, np.float64)); v = np.array(self._prep(v, self.nv, np.float64))
+        tau = self._prep(tau, self.nv, np.float64)
+        rc = _lib.rbdo_integrate(self._h, q.shape[1], _ptr(q), _ptr(v), _ptr(tau), float(dt), int(nsteps), nthreads)
+        if rc != 0:
+            raise np.linalg.LinAlgError("mass matrix not positive definite")
+        return q, v
 
     def inverse_dynamics(self, q, v, vd, wext=None, *, nthreads=1, dtype=None):
         dt = np.dtype(dtype or np.asarray(q).dtype)

@@ -196,6 +196,25 @@ int rbdo_dynamics_dual6(void* mp, int64_t B, const double* q, const double* v, c
                         int nthreads) {
   return dynamics_dual6(*static_cast<Model*>(mp), B, q, v, tau, vd, algo, nthreads);
 }
+// simulate(): nsteps RK4 Munthe-Kaas steps, constant torques, fp64; q [nq][B], v [nv][B] updated in place
+int rbdo_integrate(void* mp, int64_t B, double* q, double* v, const double* tau, double dt, int nsteps, int nthreads) {
+  const Model& m = *static_cast<Model*>(mp);
+  std::vector<int> status(std::max(1, nthreads), 0);
+  parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int tid) {
+    Workspace<double> w(m);
+    std::vector<double> ql(m.nq), vl(m.nv), tl(m.nv);
+    for (int64_t b = lo; b < hi; ++b) {
+      for (int k = 0; k < m.nq; ++k) ql[k] = q[(int64_t)k * B + b];
+      for (int k = 0; k < m.nv; ++k) { vl[k] = v[(int64_t)k * B + b]; if (tau) tl[k] = tau[(int64_t)k * B + b]; }
+      for (int s = 0; s < nsteps; ++s)
+        if (!integrate_step(w, ql.data(), vl.data(), tau ? tl.data() : nullptr, dt)) status[tid] = 1;
+      for (int k = 0; k < m.nq; ++k) q[(int64_t)k * B + b] = ql[k];
+      for (int k = 0; k < m.nv; ++k) v[(int64_t)k * B + b] = vl[k];
+    }
+  });
+  for (int s : status) if (s) return 1;
+  return 0;
+}
 // vd == NULL  =>  dynamics_bias
 int rbdo_inverse_dynamics(void* mp, int dtype, int64_t B, const void* q, const void* v, const void* vd, const void* wext,
                           void* tau, int nthreads) {

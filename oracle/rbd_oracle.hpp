@@ -616,4 +616,149 @@ template <class T> bool aba(Workspace<T>& w, const T* q, const T* v, const T* ta
   return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// MuntheKaasIntegrator step with the RK4 tableau (ode_integrators.jl:48-55, 233-300) around dynamics(),
+// local / global coordinates per joint type with the reference's own closed forms (no series expansions).
+// ------------------------------------------------------------------------------------------------
+inline void o_quat_mul(const double* a, const double* b, double* o) {
+  o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  o[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  o[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+}
+inline void o_rotvec_to_quat(const V3<double>& r, double* q) {
+  double th = std::sqrt(dot(r, r));
+  if (th < 1e-300) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  double s = std::sin(th / 2) / th;
+  q[0] = std::cos(th / 2); q[1] = s * r.x; q[2] = s * r.y; q[3] = s * r.z;
+}
+inline V3<double> o_quat_to_rotvec(const double* qin, double& th) {      // angle in [0, pi]
+  double q[4] = {qin[0], qin[1], qin[2], qin[3]};
+  if (q[0] < 0) for (double& c : q) c = -c;
+  double sn = std::sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  th = 2 * std::atan2(sn, q[0]);
+  if (sn < 1e-300) return V3<double>();
+  double k = th / sn;
+  return V3<double>(k * q[1], k * q[2], k * q[3]);
+}
+// exp(::Twist) spatialmotion.jl:306-326 -> (relative quaternion, translation)
+inline void o_se3_exp(const V3<double>& pr, const V3<double>& pt, double* dq, V3<double>& tr) {
+  double th = std::sqrt(dot(pr, pr));
+  o_rotvec_to_quat(pr, dq);
+  if (std::fabs(std::remainder(th, 2 * M_PI)) < 2.220446049250313e-16) { tr = pt; return; }
+  V3<double> w = pr * (1 / th), v = pt * (1 / th);
+  M3<double> R = rot_quat(dq[0], dq[1], dq[2], dq[3]);
+  V3<double> t = cross(w, v);
+  t = t - R * t;
+  tr = t + w * (dot(w, v) * th);
+}
+// log_with_time_derivative spatialmotion.jl:262-300 (+ _log :226-252): rate of the exponential coordinates
+inline void o_se3_log_rate(const double* dq, const V3<double>& p, const V3<double>& w, const V3<double>& v, double* rate) {
+  double th;
+  V3<double> psi = o_quat_to_rotvec(dq, th);
+  double th2 = th * th, h = th / 2, sh = std::sin(h), ch = std::cos(h);
+  V3<double> qq = p;
+  bool small = std::fabs(std::remainder(th, 2 * M_PI)) < 2.220446049250313e-16;
+  double alpha = 1;
+  if (!small) {
+    alpha = h * ch / sh;
+    qq = p - cross(psi, p) * 0.5 + cross(psi, cross(psi, p)) * ((1 - alpha) / th2);
+  }
+  S6<double> X{psi, qq}, V{w, v}, Xd = V;
+  if (!small) {
+    double beta = h * h / (sh * sh);
+    double A = (2 * (1 - alpha) + (alpha - beta) / 2) / th2;
+    double B = ((1 - alpha) + (alpha - beta) / 2) / (th2 * th2);
+    S6<double> a1 = se3_commutator(X, V), a2 = se3_commutator(X, a1), a3 = se3_commutator(X, a2), a4 = se3_commutator(X, a3);
+    Xd.ang = V.ang + a1.ang * 0.5 + a2.ang * A + a4.ang * B;
+    Xd.lin = V.lin + a1.lin * 0.5 + a2.lin * A + a4.lin * B;
+  }
+  rate[0] = Xd.ang.x; rate[1] = Xd.ang.y; rate[2] = Xd.ang.z; rate[3] = Xd.lin.x; rate[4] = Xd.lin.y; rate[5] = Xd.lin.z;
+}
+
+inline void o_global_coordinates(const Model& m, const double* q0, const double* phi, double* q) {
+  for (int i = 0; i < m.nb; ++i) {
+    const double* a = q0 + m.qstart[i];
+    const double* f = phi + m.vstart[i];
+    double* o = q + m.qstart[i];
+    switch (m.jtype[i]) {
+      case JT_QUAT_FLOATING: {                       // quaternion_floating.jl:233-249
+        double dq[4]; V3<double> tr;
+        o_se3_exp(V3<double>(f[0], f[1], f[2]), V3<double>(f[3], f[4], f[5]), dq, tr);
+        o_quat_mul(a, dq, o);
+        V3<double> t = rot_quat(a[0], a[1], a[2], a[3]) * tr;
+        o[4] = a[4] + t.x; o[5] = a[5] + t.y; o[6] = a[6] + t.z;
+        break;
+      }
+      case JT_QUAT_SPHERICAL: {                      // quaternion_spherical.jl:149-154
+        double dq[4];
+        o_rotvec_to_quat(V3<double>(f[0], f[1], f[2]), dq);
+        o_quat_mul(a, dq, o);
+        break;
+      }
+      case JT_SINCOS_REVOLUTE: {                     // sin_cos_revolute.jl:186-196
+        double s = std::sin(f[0]), c = std::cos(f[0]);
+        o[0] = a[0] * c + a[1] * s; o[1] = a[1] * c - a[0] * s;
+        break;
+      }
+      default:                                       // joint_types.jl:16-18
+        for (int k = 0; k < joint_nq(m.jtype[i]); ++k) o[k] = a[k] + f[k];
+    }
+  }
+}
+inline void o_local_rate(const Model& m, const double* q0, const double* q, const double* v, double* phid) {
+  for (int i = 0; i < m.nb; ++i) {
+    const double* a = q0 + m.qstart[i];
+    const double* b = q + m.qstart[i];
+    const double* w = v + m.vstart[i];
+    double* o = phid + m.vstart[i];
+    switch (m.jtype[i]) {
+      case JT_QUAT_FLOATING: {                       // quaternion_floating.jl:205-231
+        double ac[4] = {a[0], -a[1], -a[2], -a[3]}, dq[4];
+        o_quat_mul(ac, b, dq);
+        V3<double> dp = transpose(rot_quat(a[0], a[1], a[2], a[3])) * V3<double>(b[4] - a[4], b[5] - a[5], b[6] - a[6]);
+        o_se3_log_rate(dq, dp, V3<double>(w[0], w[1], w[2]), V3<double>(w[3], w[4], w[5]), o);
+        break;
+      }
+      case JT_QUAT_SPHERICAL: {                      // quaternion_spherical.jl:139-147, util.jl:83-101
+        double ac[4] = {a[0], -a[1], -a[2], -a[3]}, dq[4], th;
+        o_quat_mul(ac, b, dq);
+        V3<double> phi = o_quat_to_rotvec(dq, th), om(w[0], w[1], w[2]);
+        V3<double> r = om + cross(phi, om) * 0.5;
+        if (th > 2.220446049250313e-16) {
+          double s = std::sin(th), c = std::cos(th);
+          r = r + cross(phi, cross(phi, om)) * (1 / (th * th) * (1 - (th * s) / (2 * (1 - c))));
+        }
+        o[0] = r.x; o[1] = r.y; o[2] = r.z;
+        break;
+      }
+      case JT_SINCOS_REVOLUTE: o[0] = w[0]; break;   // sin_cos_revolute.jl:173-184
+      default: qdot_joint(m.jtype[i], b, w, o);      // joint_types.jl:9-14: phi_dot = q̇ (nq == nv for these types)
+    }
+  }
+}
+// one RK4 Munthe-Kaas step with constant torques (zero-order hold); q, v updated in place
+inline bool integrate_step(Workspace<double>& w, double* q, double* v, const double* tau, double dt) {
+  const Model& m = *w.mdl;
+  const double a[4] = {0, 0.5, 0.5, 1.0}, b[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+  std::vector<double> q0(q, q + m.nq), v0(v, v + m.nv), qs(m.nq), vs(m.nv), phi(m.nv);
+  std::vector<std::vector<double>> phid(4, std::vector<double>(m.nv)), vd(4, std::vector<double>(m.nv));
+  for (int i = 0; i < 4; ++i) {
+    for (int k = 0; k < m.nv; ++k) {
+      phi[k] = i ? dt * a[i] * phid[i - 1][k] : 0.0;
+      vs[k] = v0[k] + (i ? dt * a[i] * vd[i - 1][k] : 0.0);
+    }
+    o_global_coordinates(m, q0.data(), phi.data(), qs.data());
+    if (!dynamics(w, qs.data(), vs.data(), tau, (const double*)nullptr, vd[i].data(), (double*)nullptr)) return false;
+    o_local_rate(m, q0.data(), qs.data(), vs.data(), phid[i].data());
+  }
+  for (int k = 0; k < m.nv; ++k) {
+    phi[k] = 0; v[k] = v0[k];
+    for (int i = 0; i < 4; ++i) { phi[k] += dt * b[i] * phid[i][k]; v[k] += dt * b[i] * vd[i][k]; }
+  }
+  o_global_coordinates(m, q0.data(), phi.data(), q);
+  return true;
+}
+
 }  // namespace rbdo

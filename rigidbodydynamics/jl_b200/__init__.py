@@ -18,5 +18,5 @@ from .urdf import (default_urdf_joint_types, load_description, load_model, mecha
 from .state import (DynamicsResult, MechanismState, rand_, rand_configuration_, rand_velocity_, zero_,  # noqa: F401
                     zero_configuration_, zero_velocity_)
 from .algorithms import (DimensionMismatch, dynamics_, dynamics_dual_, dynamics_bias, dynamics_bias_, dynamics_ode_,  # noqa: F401
-                         inverse_dynamics, inverse_dynamics_, mass_matrix, mass_matrix_)
+                         inverse_dynamics, inverse_dynamics_, mass_matrix, mass_matrix_, simulate_)
 from ._cabi import RbdError, launch_info, load_library  # noqa: F401

@@ -18,7 +18,7 @@ import torch
 from . import _cabi
 from .state import DynamicsResult, MechanismState, _DT
 
-__all__ = ["dynamics_", "dynamics_dual_", "dynamics_ode_", "inverse_dynamics_", "inverse_dynamics", "mass_matrix_", "mass_matrix",
+__all__ = ["dynamics_", "dynamics_dual_", "dynamics_ode_", "simulate_", "inverse_dynamics_", "inverse_dynamics", "mass_matrix_", "mass_matrix",
            "dynamics_bias_", "dynamics_bias", "DimensionMismatch"]
 
 
@@ -95,6 +95,23 @@ def dynamics_ode_(xdot: torch.Tensor, result: DynamicsResult, state: MechanismSt
     xdot[: state.nq].copy_(result.qd)
     xdot[state.nq:].copy_(result.vd)
     return xdot
+
+
+def simulate_(state: MechanismState, final_time: float, torques: Optional[torch.Tensor] = None, dt: float = 1e-4) -> int:
+    """``simulate(state0, final_time, control!; Δt)`` (src/simulate.jl:36-55) for the whole batch, on the GPU: Munthe-Kaas RK4
+    steps (src/ode_integrators.jl:233-300) until ``t >= final_time``; ``state.q`` / ``state.v`` are advanced in place.  The
+    control is the default passive one (``torques=None``) or a constant torque array [nv, B] (zero-order hold over the call);
+    a time-varying controller calls this once per control interval.  Returns the number of steps taken."""
+    state.check_modcount()
+    lib = _cabi.load_library()
+    _check(torques, state.nv, state, "torques")
+    nsteps, t = 0, 0.0
+    while t < final_time:            # the reference's `while t < final_time` loop (ode_integrators.jl:311)
+        t += dt
+        nsteps += 1
+    _call(lib.rbd_integrate(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(state.v),
+                            _ptr(torques), float(dt), nsteps, _stream()))
+    return nsteps
 
 
 def inverse_dynamics_(torquesout: torch.Tensor, state: MechanismState, vd: torch.Tensor,

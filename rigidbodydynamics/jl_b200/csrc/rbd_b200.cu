@@ -25,6 +25,7 @@
 #include "../../../include/rbd_b200.h"
 #include "rbd_rnea_crba.cuh"
 #include "rbd_dual.cuh"
+#include "rbd_integrate.cuh"
 #include "rbd_tmem.cuh"
 #include "rbd_model.h"
 
@@ -489,6 +490,104 @@ int dynamics_dual(const rbd_model* model, int64_t B, int64_t ld, const void* q, 
   return RBD_OK;
 }
 
+// ---- Munthe-Kaas RK4 (rbd_integrate): elementwise stage kernels around the dynamics kernels -----------------------------
+template <class T> struct StageArgs {
+  const T* q0; const T* v0;     // state at the start of the step
+  T* phi; T* phid; T* vd;       // local coordinates of the stage, their rate (in: previous stage, out: this stage), v̇ of the previous stage
+  T* qs; T* vs;                 // stage state handed to the dynamics kernel
+  T* accphi; T* accv;           // sum_i b_i phid_i, sum_i b_i vd_i
+  T wa, wb_prev, wb;            // dt * a_i ; b_{i-1} ; b_i
+  int first;                    // stage 0: no previous stage
+  int64_t B;
+};
+// One thread per sample.  phi = wa * phid_prev, v_stage = v0 + wa * vd_prev, q_stage = global(q0, phi), phid = rate of the local
+// coordinates at (q_stage, v_stage); accumulators updated with the previous stage's v̇ and this stage's phid.
+template <class T>
+__global__ void __launch_bounds__(128) integrate_stage_kernel(const __grid_constant__ ModelDev<T> M, const StageArgs<T> a) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
+    for (int k = 0; k < M.nv; ++k) {
+      const int64_t e = (int64_t)k * a.B + b;
+      const T vdp = a.first ? T(0) : a.vd[e];
+      const T pdp = a.first ? T(0) : a.phid[e];
+      a.phi[e] = a.wa * pdp;
+      a.vs[e] = a.v0[e] + a.wa * vdp;
+      a.accv[e] = a.first ? T(0) : a.accv[e] + a.wb_prev * vdp;
+    }
+    const Col<T> q0{a.q0 + b, a.B}, phi{a.phi + b, a.B}, vs{a.vs + b, a.B};
+    const ColOut<T> qs{a.qs + b, a.B, true}, phid{a.phid + b, a.B, true};
+    for (int i = 0; i < M.nb; ++i) joint_stage(M.body[i], q0, phi, vs, qs, phid);
+    for (int k = 0; k < M.nv; ++k) {
+      const int64_t e = (int64_t)k * a.B + b;
+      a.accphi[e] = (a.first ? T(0) : a.accphi[e]) + a.wb * a.phid[e];
+    }
+  }
+}
+template <class T> struct FinishArgs {
+  const T* q0; const T* v0; const T* vd; const T* accphi; const T* accv;
+  T* phi; T* scratch; T* q; T* v;    // q, v: user arrays (leading dimension ld)
+  T dt, wb_last;
+  int64_t B, ld;
+};
+// v = v0 + dt (accv + b_4 vd_4), q = global(q0, dt accphi)
+template <class T>
+__global__ void __launch_bounds__(128) integrate_finish_kernel(const __grid_constant__ ModelDev<T> M, const FinishArgs<T> a) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
+    for (int k = 0; k < M.nv; ++k) {
+      const int64_t e = (int64_t)k * a.B + b;
+      const T vn = a.v0[e] + a.dt * (a.accv[e] + a.wb_last * a.vd[e]);
+      a.v[(int64_t)k * a.ld + b] = vn;
+      a.scratch[e] = vn;
+      a.phi[e] = a.dt * a.accphi[e];
+    }
+    const Col<T> q0{a.q0 + b, a.B}, phi{a.phi + b, a.B}, vs{a.scratch + b, a.B};
+    const ColOut<T> q{a.q + b, a.ld, true}, dump{a.scratch + b, a.B, false};
+    for (int i = 0; i < M.nb; ++i) joint_stage(M.body[i], q0, phi, vs, q, dump);
+  }
+}
+
+template <class T>
+int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v, const void* tau, double dt, int nsteps,
+                cudaStream_t stream) {
+  const HostModel& hm = model->hm;
+  const ModelDev<T>& M = dev_model<T>(hm);
+  DeviceProps p;
+  if (int rc = get_props(p)) return rc;
+  const size_t nq = hm.nq, nv = hm.nv;
+  const size_t rows = 2 * nq + 7 * nv + (tau && ld != B ? nv : 0);
+  T* ws = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&ws, rows * (size_t)B * sizeof(T), stream));
+  T* q0 = ws; T* qs = q0 + nq * B; T* v0 = qs + nq * B; T* vs = v0 + nv * B; T* phi = vs + nv * B; T* phid = phi + nv * B;
+  T* vd = phid + nv * B; T* accphi = vd + nv * B; T* accv = accphi + nv * B; T* taud = accv + nv * B;
+  const T* tau_dense = (const T*)tau;
+  if (tau && ld != B) {
+    CUDA_TRY(cudaMemcpy2DAsync(taud, B * sizeof(T), tau, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
+    tau_dense = taud;
+  }
+  const int grid = (int)std::min<int64_t>((B + 127) / 128, (int64_t)p.sms * 8);
+  const double a[4] = {0.0, 0.5, 0.5, 1.0}, bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};   // runge_kutta_4, ode_integrators.jl:48-55
+  int rc = RBD_OK, launches = 0;
+  for (int s = 0; s < nsteps && rc == RBD_OK; ++s) {
+    CUDA_TRY(cudaMemcpy2DAsync(q0, B * sizeof(T), q, ld * sizeof(T), B * sizeof(T), nq, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaMemcpy2DAsync(v0, B * sizeof(T), v, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
+    for (int i = 0; i < 4 && rc == RBD_OK; ++i) {
+      StageArgs<T> sa{q0, v0, phi, phid, vd, qs, vs, accphi, accv, (T)(dt * a[i]), (T)(i ? bw[i - 1] : 0.0), (T)bw[i], i == 0, B};
+      integrate_stage_kernel<T><<<grid, 128, 0, stream>>>(M, sa);
+      CUDA_TRY(cudaGetLastError());
+      const int before = g_launch.kernels_launched;
+      rc = dynamics_t<T>(model, B, B, qs, vs, tau_dense, nullptr, vd, nullptr, stream);
+      launches += 1 + (g_launch.kernels_launched - before);
+    }
+    if (rc != RBD_OK) break;
+    FinishArgs<T> fa{q0, v0, vd, accphi, accv, phi, vs, (T*)q, (T*)v, (T)dt, (T)bw[3], B, ld};
+    integrate_finish_kernel<T><<<grid, 128, 0, stream>>>(M, fa);
+    CUDA_TRY(cudaGetLastError());
+    launches += 1;
+  }
+  cudaFreeAsync(ws, stream);
+  g_launch.kernels_launched = launches;
+  return rc;
+}
+
 int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld) {
   if (!model) return fail(RBD_EINVAL, "model handle is NULL");
   if (dtype != RBD_F32 && dtype != RBD_F64 && dtype != RBD_DUAL64X6)
@@ -663,6 +762,19 @@ int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t l
   }
   return dtype == RBD_F32 ? dynamics_t<float>(model, B, ld, q, v, tau, wext, vd_out, qd_out, s)
                           : dynamics_t<double>(model, B, ld, q, v, tau, wext, vd_out, qd_out, s);
+}
+
+int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,
+                      double dt, int32_t nsteps, void* stream) {
+  if (int rc = check_common(model, dtype, B, ld)) return rc;
+  if (dtype == RBD_DUAL64X6) return fail(RBD_EUNSUPPORTED, "rbd_integrate: RBD_DUAL64X6 is not supported");
+  if (nsteps < 0 || !(dt > 0)) return fail(RBD_EINVAL, "rbd_integrate: need dt > 0 and nsteps >= 0");
+  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (B == 0 || nsteps == 0) return RBD_OK;
+  if (!q || !v) return fail(RBD_EINVAL, "rbd_integrate: q and v must not be NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == RBD_F32 ? integrate_t<float>(model, B, ld, q, v, tau, dt, nsteps, s)
+                          : integrate_t<double>(model, B, ld, q, v, tau, dt, nsteps, s);
 }
 
 int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,

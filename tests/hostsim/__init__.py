@@ -96,3 +96,16 @@ def dynamics_dual(desc, q, v, tau=None):
     rc = fn(ctypes.byref(d), B, _p(q), _p(v), _p(tau), _p(vd))
     assert rc == 0, rc
     return vd
+
+
+def integrate(desc, q, v, tau=None, dt=1e-4, nsteps=1):
+    dt_ = q.dtype
+    d, keep = make_desc(desc)
+    q = np.array(q, dt_, order="C"); v = np.array(v, dt_, order="C")
+    tau = None if tau is None else np.ascontiguousarray(tau, dt_)
+    fn = lib().hostsim_integrate
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc), ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                   ctypes.c_double, ctypes.c_int]
+    rc = fn(ctypes.byref(d), 0 if dt_ == np.float32 else 1, q.shape[1], _p(q), _p(v), _p(tau), float(dt), int(nsteps))
+    assert rc == 0, rc
+    return q, v

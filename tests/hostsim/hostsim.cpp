@@ -7,6 +7,7 @@
 
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_rnea_crba.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_dual.cuh"
+#include "../../rigidbodydynamics/jl_b200/csrc/rbd_integrate.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_model.h"
 
 using namespace rbd;
@@ -67,7 +68,57 @@ template <class T> void run_crba(const HostModel& hm, int64_t B, const T* q, T* 
 }
 }  // namespace
 
+// Munthe-Kaas RK4 steps with the device coordinate maps (joint_stage) and the device ABA, one sample at a time
+template <class T>
+void run_integrate(const HostModel& hm, int64_t B, T* q, T* v, const T* tau, double dt, int nsteps) {
+  const ModelDev<T>& M = dev<T>(hm);
+  const int nq = M.nq, nv = M.nv;
+  std::vector<T> stash(M.nrows + 64), q0(nq), v0(nv), qs(nq), vs(nv), phi(nv), phid(nv), vd(nv), accphi(nv), accv(nv), dump(nv);
+  const double a[4] = {0.0, 0.5, 0.5, 1.0}, bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+  for (int64_t b = 0; b < B; ++b) {
+    for (int s = 0; s < nsteps; ++s) {
+      for (int k = 0; k < nq; ++k) q0[k] = q[(int64_t)k * B + b];
+      for (int k = 0; k < nv; ++k) v0[k] = v[(int64_t)k * B + b];
+      for (int i = 0; i < 4; ++i) {
+        const T wa = (T)(dt * a[i]);
+        for (int k = 0; k < nv; ++k) {
+          const T vdp = i ? vd[k] : T(0), pdp = i ? phid[k] : T(0);
+          phi[k] = wa * pdp; vs[k] = v0[k] + wa * vdp;
+          accv[k] = i ? accv[k] + (T)bw[i - 1] * vdp : T(0);
+        }
+        const Col<T> cq0{q0.data(), 1}, cphi{phi.data(), 1}, cvs{vs.data(), 1};
+        const ColOut<T> oqs{qs.data(), 1, true}, ophid{phid.data(), 1, true};
+        for (int j = 0; j < M.nb; ++j) joint_stage(M.body[j], cq0, cphi, cvs, oqs, ophid);
+        for (int k = 0; k < nv; ++k) accphi[k] = (i ? accphi[k] : T(0)) + (T)bw[i] * phid[k];
+        AbaIO<T, false> io;
+        io.q = {qs.data(), 1}; io.v = {vs.data(), 1};
+        io.tau = {tau ? tau + b : nullptr, B}; io.wext = {nullptr, 1};
+        io.vd = {vd.data(), 1, true}; io.qd = {nullptr, 1, true}; io.ext = {nullptr, 1};
+        Stash<T, 1> st{stash.data()};
+        if (hm.general) aba_sample<T, Stash<T, 1>, true>(M, io, st);
+        else aba_sample<T, Stash<T, 1>, false>(M, io, st);
+      }
+      for (int k = 0; k < nv; ++k) {
+        vs[k] = v0[k] + (T)dt * (accv[k] + (T)bw[3] * vd[k]);
+        phi[k] = (T)dt * accphi[k];
+        v[(int64_t)k * B + b] = vs[k];
+      }
+      const Col<T> cq0{q0.data(), 1}, cphi{phi.data(), 1}, cvs{vs.data(), 1};
+      const ColOut<T> oq{q + b, B, true}, odump{dump.data(), 1, false};
+      for (int j = 0; j < M.nb; ++j) joint_stage(M.body[j], cq0, cphi, cvs, oq, odump);
+    }
+  }
+}
+
 extern "C" {
+int hostsim_integrate(const rbd_model_desc* d, int dtype, int64_t B, void* q, void* v, const void* tau, double dt, int nsteps) {
+  HostModel hm; std::string err;
+  int rc = build_host_model(d, hm, err);
+  if (rc) return rc;
+  if (dtype == 0) run_integrate<float>(hm, B, (float*)q, (float*)v, (const float*)tau, dt, nsteps);
+  else run_integrate<double>(hm, B, (double*)q, (double*)v, (const double*)tau, dt, nsteps);
+  return 0;
+}
 int hostsim_info(const rbd_model_desc* d, int* nrows, int* general, int* nslots, int* order) {
   HostModel hm; std::string err;
   int rc = build_host_model(d, hm, err);

@@ -11,7 +11,7 @@ import torch
 
 import rigidbodydynamics.jl_b200 as rbd
 from oracle import Oracle
-from tests.util import make_duals, rand_inputs, randmech, rel_err
+from tests.util import config_distance, make_duals, rand_inputs, randmech, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = {torch.float64: 1e-9, torch.float32: 2e-5}
@@ -360,3 +360,50 @@ def test_large_batch_uses_tensor_memory_path(built, dtype):
     ref = Oracle(mech.flatten()).dynamics(sub.q.double().cpu().numpy(), sub.v.double().cpu().numpy(),
                                           tau[:, idx].double().cpu().numpy())
     assert rel_err(res2.vd.double().cpu().numpy(), ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("name,floating", [("atlas", True), ("iiwa14", False)])
+def test_simulate_rk4_matches_oracle(built, name, floating):
+    """rbd_integrate = simulate() / MuntheKaasIntegrator with the RK4 tableau: q, v after several steps
+    vs the oracle's restatement; fp64 1e-9, fp32 1e-4 (quaternion sign-insensitive configuration distance)."""
+    mech = rbd.load_model(name, floating=floating)
+    o = Oracle(mech.flatten())
+    q, v, tau, _, _ = rand_inputs(mech, 150, 14)
+    qr, vr = o.integrate(q, v, tau, dt=1e-3, nsteps=5)
+    for dtype, tq, tv in ((torch.float64, 1e-9, 1e-9), (torch.float32, 5e-5, 5e-4)):
+        st = _state(mech, q, v, dtype)
+        n = rbd.simulate_(st, 5e-3 - 1e-9, _cu(tau, dtype), dt=1e-3)
+        assert n == 5
+        assert config_distance(mech, st.q.double().cpu().numpy(), qr) < tq
+        assert rel_err(st.v.double().cpu().numpy(), vr) < tv
+    # passive (no torques) run keeps unit quaternions on the manifold
+    st = _state(mech, q, v, torch.float64)
+    rbd.simulate_(st, 0.01, None, dt=1e-3)
+    if floating:
+        assert float((st.q[:4].norm(dim=0) - 1).abs().max()) < 1e-12
+
+
+def test_simulate_all_joint_types_and_energy(built):
+    mech = randmech(2)
+    o = Oracle(mech.flatten())
+    q, v, tau, _, _ = rand_inputs(mech, 33, 3)
+    qr, vr = o.integrate(q, v, tau, dt=5e-4, nsteps=3)
+    st = _state(mech, q, v, torch.float64)
+    rbd.simulate_(st, 1.5e-3 - 1e-9, _cu(tau, torch.float64), dt=5e-4)
+    assert config_distance(mech, st.q.cpu().numpy(), qr) < 1e-9
+    assert rel_err(st.v.cpu().numpy(), vr) < 1e-8
+    # energy conservation of the passive double pendulum (test/test_simulate.jl:5-13, atol 1e-3), batch of 1000 on the GPU
+    from tests.util import double_pendulum
+    pend = double_pendulum()
+    B = 1000
+    stp = rbd.MechanismState(pend, B, torch.float64)
+    rbd.rand_(stp, np.random.default_rng(60))
+
+    def energy(s):
+        M = rbd.mass_matrix(s).reshape(2, 2, B)
+        ke = 0.5 * torch.einsum("ib,ijb,jb->b", s.v, M, s.v)
+        z1 = -0.5 * torch.cos(s.q[0]); z2 = -torch.cos(s.q[0]) - 0.5 * torch.cos(s.q[0] + s.q[1])
+        return ke + 9.81 * (z1 + z2)
+    e0 = energy(stp)
+    rbd.simulate_(stp, 0.1, None, dt=1e-2)
+    assert float((energy(stp) - e0).abs().max()) < 1e-3

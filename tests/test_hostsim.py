@@ -6,7 +6,7 @@ import pytest
 import rigidbodydynamics.jl_b200 as rbd
 from oracle import Oracle
 from tests import hostsim
-from tests.util import make_duals, rand_inputs, randmech, rel_err
+from tests.util import config_distance, make_duals, rand_inputs, randmech, rel_err
 
 MODELS = [("atlas", True), ("atlas", False), ("valkyrie", True), ("iiwa14", False), ("double_pendulum", False)]
 
@@ -118,3 +118,55 @@ def test_dual_number_dynamics(name, floating):
     fd = (o.dynamics(q + h * Q[..., 3], v + h * V[..., 3], tau + h * T[..., 3])
           - o.dynamics(q - h * Q[..., 3], v - h * V[..., 3], tau - h * T[..., 3])) / (2 * h)
     assert np.abs(fd - got[..., 3]).max() / np.abs(fd).max() < 1e-6
+
+
+@pytest.mark.parametrize("name,floating", [("atlas", True), ("iiwa14", False), ("double_pendulum", False)])
+def test_rk4_step_matches_oracle(name, floating):
+    """simulate / MuntheKaasIntegrator (src/ode_integrators.jl:233-300): device coordinate maps + device ABA vs the oracle's
+    restatement with the reference's closed forms, fp64, several steps."""
+    mech = rbd.load_model(name, floating=floating)
+    d = mech.flatten()
+    q, v, tau, _, _ = rand_inputs(mech, 3, 12)
+    for tq in (None, tau):
+        qr, vr = Oracle(d).integrate(q, v, tq, dt=1e-3, nsteps=5)
+        qg, vg = hostsim.integrate(d, q, v, tq, dt=1e-3, nsteps=5)
+        assert config_distance(mech, qg, qr) < 1e-11
+        assert rel_err(vg, vr) < 1e-10
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_rk4_step_all_joint_types(seed):
+    mech = randmech(seed, shuffle=seed % 2 == 1)
+    d = mech.flatten()
+    q, v, tau, _, _ = rand_inputs(mech, 2, seed)
+    qr, vr = Oracle(d).integrate(q, v, tau, dt=5e-4, nsteps=3)
+    qg, vg = hostsim.integrate(d, q, v, tau, dt=5e-4, nsteps=3)
+    assert config_distance(mech, qg, qr) < 1e-10
+    assert rel_err(vg, vr) < 1e-9
+
+
+def test_rk4_fp32_small_angle_series():
+    """fp32: the Taylor branch of the dexp^-1 coefficients keeps the floating-base step accurate (1e-5 of the fp64 oracle)."""
+    mech = rbd.load_model("atlas", floating=True)
+    d = mech.flatten()
+    q, v, tau, _, _ = rand_inputs(mech, 4, 2)
+    qr, vr = Oracle(d).integrate(q, v, tau, dt=1e-3, nsteps=4)
+    qg, vg = hostsim.integrate(d, q.astype(np.float32), v.astype(np.float32), tau.astype(np.float32), dt=1e-3, nsteps=4)
+    assert config_distance(mech, qg, qr) < 2e-5
+    assert rel_err(vg, vr) < 2e-4
+
+
+def test_energy_conservation_passive_pendulum():
+    """test/test_simulate.jl:5-13: total energy of the passive double pendulum changes by < 1e-3 over 0.1 s at dt = 1e-2."""
+    from tests.util import double_pendulum
+    mech = double_pendulum()
+    d = mech.flatten()
+    o = Oracle(d)
+
+    def energy(q, v):
+        M = o.mass_matrix(q).reshape(2, 2)
+        z1 = -0.5 * np.cos(q[0, 0]); z2 = -np.cos(q[0, 0]) - 0.5 * np.cos(q[0, 0] + q[1, 0])
+        return 0.5 * v[:, 0] @ M @ v[:, 0] + 9.81 * (z1 + z2)
+    q, v = np.array([[0.3], [0.4]]), np.array([[1.0], [2.0]])
+    q1, v1 = hostsim.integrate(d, q, v, None, dt=1e-2, nsteps=10)
+    assert abs(energy(q1, v1) - energy(q, v)) < 1e-3

@@ -78,3 +78,19 @@ def make_duals(mech, q, v, tau, seed):
                 dq -= qq * (qq * dq).sum(0)
         qs += j.nq
     return Q, V, T
+
+
+def config_distance(mech, qa, qb):
+    """max over joints / samples of the distance between two configurations, insensitive to the sign of unit quaternions
+    (q and -q are the same rotation; the reference's matrix -> quaternion conversion fixes a sign this code does not need)."""
+    qa, qb = np.asarray(qa, float), np.asarray(qb, float)
+    d, qs = 0.0, 0
+    for j in mech.joints:
+        a, b = qa[qs:qs + j.nq], qb[qs:qs + j.nq]
+        if isinstance(j.joint_type, (rbd.QuaternionFloating, rbd.QuaternionSpherical)):
+            sgn = np.sign((a[:4] * b[:4]).sum(0))
+            d = max(d, np.abs(a[:4] - sgn * b[:4]).max(initial=0.0), np.abs(a[4:] - b[4:]).max(initial=0.0))
+        elif j.nq:
+            d = max(d, np.abs(a - b).max())
+        qs += j.nq
+    return d
