@@ -99,13 +99,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def effective_cores():
+    """CPU cores this process may actually use: the cgroup CPU quota when there is one (the GPU boxes expose 128 logical CPUs
+    but cap the container at 16 -- running 128 threads there is 2x SLOWER than 16), else the affinity mask."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                quota, period = int(f.read()), int(g.read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
 def cpu_baseline(mech, q, v, tau, dtype, seconds_target=12.0):
     """Oracle (CPU port of the reference's dynamics!: RNEA bias + CRBA + Cholesky) on a bounded sample, all host cores."""
     from oracle import Oracle
     o = Oracle(mech.flatten())
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     dt = np.float32 if dtype == "f32" else np.float64
-    n = min(q.shape[1], 4096 * cores)
+    n = min(q.shape[1], 8192 * cores)
     qs, vs, ts = (np.ascontiguousarray(a[:, :n], dt) for a in (q, v, tau))
     o.dynamics(qs[:, :256], vs[:, :256], ts[:, :256], nthreads=cores)     # warm
     t0 = time.perf_counter()
@@ -191,8 +211,8 @@ def run_reference(args):
         return
     import rigidbodydynamics.jl_b200 as rbd
     mech = rbd.load_model("atlas", floating=True)
-    cores = os.cpu_count() or 1
-    n = 2048 * cores
+    cores = effective_cores()
+    n = 8192 * cores
     q, v, tau = make_inputs(mech, n, 1)
     from oracle import Oracle
     o = Oracle(mech.flatten())
@@ -371,8 +391,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": B * bpe, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                          "note": "algorithmic bytes/eval x evals/s per GPU; traffic = ncu dram bytes per launch "
-                                 "(profiles/r1_traffic.json). The fused kernel is instruction-issue bound (~970 instr/sample, "
-                                 "56 % issue-active), not HBM-bound: DESIGN.md section 4.1"},
+                                 "(profiles/r1_traffic.json). The fused kernel is instruction-issue bound (~31k thread-instr/sample, "
+                                 "~68 % of the chip's issue rate), not HBM-bound: DESIGN.md section 4.1"},
         }
         if gather:
             out["with_nccl_gather"] = gather
