@@ -186,7 +186,19 @@ def other_configs(steps):
     out["atlas_f32_inverse_dynamics_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * 580 / (ms * 1e-3) / 1e9}
     ms = time_fn(lambda: rbd.simulate_(st, 1e-4, tau, dt=1e-4), max(3, steps // 4))      # one Munthe-Kaas RK4 step (4 dynamics)
     out["atlas_f32_rk4_step_b1048576"] = {"sample_steps_per_s": B / (ms * 1e-3), "ms": ms, "kernel_launches_per_step": rbd.launch_info().kernels_launched}
-    del res, wext, tau, vd, tout, st
+    # kinematics by-products (perf/runbenchmarks.jl:69-110): algorithmic bytes = q (+ v) in, the requested outputs out
+    A = torch.empty((6 * 36, B), dtype=torch.float32, device="cuda")
+    ms = time_fn(lambda: rbd.momentum_matrix_(A, st), steps)
+    out["atlas_f32_momentum_matrix_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * (37 + 216) * 4 / (ms * 1e-3) / 1e9}
+    pth = rbd.path(atlas, atlas.findbody("r_foot"), atlas.findbody("l_hand"))    # perf/runbenchmarks.jl:29-31
+    ms = time_fn(lambda: rbd.geometric_jacobian_(A, st, pth), steps)
+    out["atlas_f32_geometric_jacobian_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * (37 + 216) * 4 / (ms * 1e-3) / 1e9}
+    small = {k: torch.empty((r, B), dtype=torch.float32, device="cuda") for k, r in
+             (("center_of_mass", 3), ("kinetic_energy", 1), ("gravitational_potential_energy", 1), ("momentum", 6),
+              ("momentum_rate_bias", 6))}
+    ms = time_fn(lambda: rbd.kinematics_(st, None, **small), steps)
+    out["atlas_f32_com_energies_momentum_fused_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * (37 + 36 + 17) * 4 / (ms * 1e-3) / 1e9}
+    del res, wext, tau, vd, tout, st, A, small
     iiwa = rbd.load_model("iiwa14")
     st = rbd.MechanismState(iiwa, B, torch.float32)
     rbd.rand_(st, rng)

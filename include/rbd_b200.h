@@ -170,6 +170,38 @@ int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_
 int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,
                       double dt, int32_t nsteps, void* stream);
 
+/* Next row of the scope table: kinematics by-products of the same outward sweep, all expressed in the
+ * mechanism's root frame, 6-vectors as [angular; linear].  Every output pointer may be NULL (not computed).
+ *   transforms_to_root  [12*nb x B]  rows 12 i .. 12 i + 11 = transform_to_root(state, successor of tree joint i):
+ *                                    rotation row-major (9) then translation (3)      src/mechanism_state.jl:687-714
+ *   center_of_mass      [3 x B]      center_of_mass(state)                            src/mechanism_algorithms.jl:30-49
+ *   kinetic_energy      [1 x B]      kinetic_energy(state)                            src/mechanism_state.jl:886-888, 989-994
+ *   gravitational_potential_energy [1 x B]                                            src/mechanism_state.jl:897-903, 996-1000
+ *   momentum            [6 x B]      momentum(state)                                  src/mechanism_state.jl:878-880, 975-980
+ *   momentum_rate_bias  [6 x B]      momentum_rate_bias(state)                        src/mechanism_state.jl:882-884, 982-987
+ *   momentum_matrix     [6*nv x B]   momentum_matrix!(A, state): column k at rows 6 k .. 6 k + 5
+ *                                                                                     src/mechanism_algorithms.jl:313-327
+ *   geometric_jacobian  [6*nv x B]   geometric_jacobian!(J, state, path), same column layout; requires `path_sign`
+ *                                                                                     src/mechanism_algorithms.jl:80-100 */
+typedef struct rbd_kinematics_out {
+  void* transforms_to_root;
+  void* center_of_mass;
+  void* kinetic_energy;
+  void* gravitational_potential_energy;
+  void* momentum;
+  void* momentum_rate_bias;
+  void* momentum_matrix;
+  void* geometric_jacobian;
+} rbd_kinematics_out;
+
+/* q [nq x B]; v [nv x B], may be NULL when none of kinetic_energy / momentum / momentum_rate_bias is requested (RBD_EINVAL
+ * otherwise).  `path_sign` is a HOST array of nb entries (tree-joint order) describing a TreePath (src/graphs/tree_path.jl):
+ * +1 for joints traversed from predecessor to successor (PathDirections.down), -1 for the opposite direction (up: the
+ * reference negates those columns, mechanism_algorithms.jl:95), 0 for joints not on the path; NULL iff geometric_jacobian is
+ * NULL.  fp32 / fp64 only. */
+int32_t rbd_kinematics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                       const int8_t* path_sign, const rbd_kinematics_out* out, void* stream);
+
 /* Host-pointer variants: same semantics, host buffers in, host buffers out, copies inside the call. */
 int32_t rbd_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                           const void* tau, const void* wext, void* vd_out, void* qd_out);

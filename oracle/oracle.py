@@ -34,6 +34,7 @@ def _load():
     lib.rbdo_integrate.argtypes = [vp, i64, vp, vp, vp, ctypes.c_double, i32, i32]
     lib.rbdo_inverse_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32]
     lib.rbdo_mass_matrix.argtypes = [vp, i32, i64, vp, vp, i32]
+    lib.rbdo_kinematics.argtypes = [vp, i32, i64] + [vp] * 11 + [i32]
     return lib
 
 
@@ -136,3 +137,22 @@ class Oracle:
         M = np.empty((self.nv * self.nv, B), dt)
         _lib.rbdo_mass_matrix(self._h, self._code(dt), B, _ptr(q), _ptr(M), nthreads)
         return M
+
+    def kinematics(self, q, v=None, sign=None, *, want=("transforms", "com", "ke", "pe", "momentum", "mrb", "A", "J"),
+                   nthreads=1, dtype=None):
+        """Kinematics by-products in the root frame.  Returns a dict of [rows, B] arrays:
+        transforms [12*nb] (R row-major, p per body), com [3], ke [1], pe [1], momentum [6], mrb (momentum_rate_bias) [6],
+        A (momentum matrix) [6*nv], J (geometric jacobian of the path given by ``sign`` [nb] in {-1, 0, +1}) [6*nv]."""
+        dt = np.dtype(dtype or np.asarray(q).dtype)
+        q = self._prep(q, self.nq, dt); v = self._prep(v, self.nv, dt)
+        B = q.shape[1]
+        rows = {"transforms": 12 * self.nb, "com": 3, "ke": 1, "pe": 1, "momentum": 6, "mrb": 6, "A": 6 * self.nv, "J": 6 * self.nv}
+        out = {k: (np.empty((rows[k], B), dt) if k in want else None) for k in rows}
+        if v is None:
+            for k in ("ke", "momentum", "mrb"):
+                out[k] = None
+        sg = None if sign is None else np.ascontiguousarray(sign, np.int8)
+        if sg is None:
+            out["J"] = None
+        _lib.rbdo_kinematics(self._h, self._code(dt), B, _ptr(q), _ptr(v), _ptr(sg), *[_ptr(out[k]) for k in rows], nthreads)
+        return {k: a for k, a in out.items() if a is not None}

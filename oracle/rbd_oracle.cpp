@@ -123,6 +123,29 @@ template <class T> int mass_matrix_t(const Model& m, int64_t B, const T* q, T* M
   return 0;
 }
 
+template <class T>
+int kinematics_t(const Model& m, int64_t B, const T* q, const T* v, const signed char* sign, T* tr, T* com, T* ke, T* pe,
+                 T* mom, T* mrb, T* A, T* J, int nthreads) {
+  parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
+    Workspace<T> w(m);
+    const int nt12 = 12 * m.nb, n6v = 6 * m.nv;
+    std::vector<T> ql(m.nq), vl(m.nv), trl(nt12), Al(n6v), Jl(n6v);
+    T c3[3], k1[1], p1[1], h6[6], b6[6];
+    for (int64_t b = lo; b < hi; ++b) {
+      for (int k = 0; k < m.nq; ++k) ql[k] = q[(int64_t)k * B + b];
+      if (v) for (int k = 0; k < m.nv; ++k) vl[k] = v[(int64_t)k * B + b];
+      KinOut<T> o;
+      o.transforms = tr ? trl.data() : nullptr; o.com = com ? c3 : nullptr; o.ke = ke ? k1 : nullptr; o.pe = pe ? p1 : nullptr;
+      o.momentum = mom ? h6 : nullptr; o.mrb = mrb ? b6 : nullptr; o.A = A ? Al.data() : nullptr; o.J = J ? Jl.data() : nullptr;
+      kinematics(w, ql.data(), v ? vl.data() : nullptr, sign, o);
+      auto put = [&](T* dst, const T* src, int n) { if (dst) for (int k = 0; k < n; ++k) dst[(int64_t)k * B + b] = src[k]; };
+      put(tr, trl.data(), nt12); put(com, c3, 3); put(ke, k1, 1); put(pe, p1, 1); put(mom, h6, 6); put(mrb, b6, 6);
+      put(A, Al.data(), n6v); put(J, Jl.data(), n6v);
+    }
+  });
+  return 0;
+}
+
 // Dual{Float64,6} arrays: [rows][B][7] doubles (value, 6 partials) -- Julia's memory layout of Matrix{Dual}(B, n)
 int dynamics_dual6(const Model& m, int64_t B, const double* q, const double* v, const double* tau, double* vd, int algo,
                    int nthreads) {
@@ -226,6 +249,14 @@ int rbdo_mass_matrix(void* mp, int dtype, int64_t B, const void* q, void* M, int
   const Model& m = *static_cast<Model*>(mp);
   if (dtype == 0) return mass_matrix_t<float>(m, B, (const float*)q, (float*)M, nthreads);
   return mass_matrix_t<double>(m, B, (const double*)q, (double*)M, nthreads);
+}
+
+// kinematics by-products; every output pointer may be NULL; v may be NULL when no velocity-dependent output is requested
+int rbdo_kinematics(void* mp, int dtype, int64_t B, const void* q, const void* v, const signed char* sign, void* tr, void* com,
+                    void* ke, void* pe, void* mom, void* mrb, void* A, void* J, int nthreads) {
+  const Model& m = *static_cast<Model*>(mp);
+  if (dtype == 0) return kinematics_t<float>(m, B, (const float*)q, (const float*)v, sign, (float*)tr, (float*)com, (float*)ke, (float*)pe, (float*)mom, (float*)mrb, (float*)A, (float*)J, nthreads);
+  return kinematics_t<double>(m, B, (const double*)q, (const double*)v, sign, (double*)tr, (double*)com, (double*)ke, (double*)pe, (double*)mom, (double*)mrb, (double*)A, (double*)J, nthreads);
 }
 
 }  // extern "C"

@@ -437,6 +437,81 @@ template <class T> void update_kinematics(Workspace<T>& w, const T* q, const T* 
   update_spatial_inertias(w);
 }
 
+// ------------------------------------------------------------------------------------------------
+// kinematics by-products: all world (root) frame, straight from the caches above
+// ------------------------------------------------------------------------------------------------
+//   transform_to_root             mechanism_state.jl:687-714 (the cache itself)
+//   center_of_mass                mechanism_algorithms.jl:30-49
+//   kinetic_energy                mechanism_state.jl:886-888, :989-994; motion_force_interaction.jl:337-346
+//   gravitational_potential_energy mechanism_state.jl:897-903, :996-1000
+//   momentum / momentum_rate_bias mechanism_state.jl:878-884, :975-987
+//   momentum_matrix!              mechanism_algorithms.jl:313-327
+//   geometric_jacobian!           mechanism_algorithms.jl:80-100 (sign[i] = +1 joint i traversed down, -1 up, 0 not on the path)
+template <class T> struct KinOut {
+  T* transforms = nullptr;   // [nb][12]: R row-major, p
+  T* com = nullptr;          // [3]
+  T* ke = nullptr;           // [1]
+  T* pe = nullptr;           // [1]
+  T* momentum = nullptr;     // [6]
+  T* mrb = nullptr;          // [6]
+  T* A = nullptr;            // [nv][6]
+  T* J = nullptr;            // [nv][6]
+};
+template <class T> void kinematics(Workspace<T>& w, const T* q, const T* v, const signed char* sign, const KinOut<T>& o) {
+  const Model& m = *w.mdl;
+  update_transforms(w, q);
+  update_motion_subspaces(w);
+  update_spatial_inertias(w);
+  if (v) { update_twists(w, v); update_bias_accelerations(w); }
+  if (o.transforms)
+    for (int i = 0; i < m.nb; ++i) {
+      for (int k = 0; k < 9; ++k) o.transforms[12 * i + k] = w.T_root[i].R.m[k];
+      o.transforms[12 * i + 9] = w.T_root[i].p.x; o.transforms[12 * i + 10] = w.T_root[i].p.y; o.transforms[12 * i + 11] = w.T_root[i].p.z;
+    }
+  if (o.com || o.pe) {
+    V3<T> mc(T(0), T(0), T(0));
+    T mass = T(0), pe = T(0);
+    for (int i = 0; i < m.nb; ++i) {
+      const Inertia<T>& I = w.jc[i].I;
+      if (!(I.m > T(0))) continue;
+      V3<T> c_body = (T(1) / I.m) * I.c;                                  // center_of_mass(inertia) = cross_part / mass
+      V3<T> c_world = w.T_root[i].R * c_body + w.T_root[i].p;
+      mc = mc + I.m * c_world;
+      mass = mass + I.m;
+      pe = pe - I.m * dot(w.g, c_world);
+    }
+    if (o.com) { V3<T> c = (T(1) / mass) * mc; o.com[0] = c.x; o.com[1] = c.y; o.com[2] = c.z; }
+    if (o.pe) o.pe[0] = pe;
+  }
+  if (v && (o.ke || o.momentum || o.mrb)) {
+    T ke = T(0);
+    S6<T> h{V3<T>(T(0), T(0), T(0)), V3<T>(T(0), T(0), T(0))}, hb = h;
+    for (int i = 0; i < m.nb; ++i) {
+      const Inertia<T>& I = w.Iw[i];
+      const S6<T>& tw = w.twist[i];
+      ke = ke + (dot(tw.ang, I.J * tw.ang) + dot(tw.lin, I.m * tw.lin + T(2) * cross(tw.ang, I.c))) / T(2);
+      h = h + mul_inertia(I, tw);
+      hb = hb + newton_euler(I, w.bias[i], tw);
+    }
+    if (o.ke) o.ke[0] = ke;
+    if (o.momentum) { for (int k = 0; k < 3; ++k) { o.momentum[k] = h.ang[k]; o.momentum[3 + k] = h.lin[k]; } }
+    if (o.mrb) { for (int k = 0; k < 3; ++k) { o.mrb[k] = hb.ang[k]; o.mrb[3 + k] = hb.lin[k]; } }
+  }
+  if (o.A) {
+    update_crb_inertias(w);
+    for (int i = 0; i < m.nv; ++i) {
+      S6<T> F = mul_inertia(w.Ic[m.vjoint[i]], w.S[i]);
+      for (int k = 0; k < 3; ++k) { o.A[6 * i + k] = F.ang[k]; o.A[6 * i + 3 + k] = F.lin[k]; }
+    }
+  }
+  if (o.J) {
+    for (int i = 0; i < m.nv; ++i) {
+      T sg = sign ? T((int)sign[m.vjoint[i]]) : T(0);
+      for (int k = 0; k < 3; ++k) { o.J[6 * i + k] = sg * w.S[i].ang[k]; o.J[6 * i + 3 + k] = sg * w.S[i].lin[k]; }
+    }
+  }
+}
+
 // dynamics_bias! :484-498 (bias_accelerations! :377-385: a_i = -g + b_i)
 template <class T> void dynamics_bias(Workspace<T>& w, const T* q, const T* v, const T* wext, T* c) {
   update_kinematics(w, q, v);

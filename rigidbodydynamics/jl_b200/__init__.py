@@ -19,4 +19,7 @@ from .state import (DynamicsResult, MechanismState, rand_, rand_configuration_, 
                     zero_configuration_, zero_velocity_)
 from .algorithms import (DimensionMismatch, dynamics_, dynamics_dual_, dynamics_bias, dynamics_bias_, dynamics_ode_,  # noqa: F401
                          inverse_dynamics, inverse_dynamics_, mass_matrix, mass_matrix_, simulate_)
+from .kinematics import (TreePath, center_of_mass, geometric_jacobian, geometric_jacobian_,  # noqa: F401
+                         gravitational_potential_energy, kinematics_, kinetic_energy, momentum, momentum_matrix,
+                         momentum_matrix_, momentum_rate_bias, path, transforms_to_root, transforms_to_root_)
 from ._cabi import RbdError, launch_info, load_library  # noqa: F401

@@ -52,6 +52,12 @@ class RbdLaunchInfo(Structure):
     ]
 
 
+class RbdKinematicsOut(Structure):
+    _fields_ = [(n, c_void_p) for n in ("transforms_to_root", "center_of_mass", "kinetic_energy",
+                                        "gravitational_potential_energy", "momentum", "momentum_rate_bias",
+                                        "momentum_matrix", "geometric_jacobian")]
+
+
 class RbdError(RuntimeError):
     """Raised for any non-zero rbd_status.  ``status`` carries the code so callers can map it to the reference's
     exception types (DimensionMismatch, ModificationCountMismatch, ...)."""
@@ -100,6 +106,7 @@ SYMBOLS = {
     "rbd_dynamics_bias": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rbd_mass_matrix": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "rbd_integrate": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, c_double, _i32, _vp]),
+    "rbd_kinematics": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, POINTER(RbdKinematicsOut), _vp]),
     "rbd_dynamics_host": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rbd_inverse_dynamics_host": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rbd_dynamics_bias_host": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -24,6 +24,7 @@
 
 #include "../../../include/rbd_b200.h"
 #include "rbd_rnea_crba.cuh"
+#include "rbd_kin.cuh"
 #include "rbd_dual.cuh"
 #include "rbd_integrate.cuh"
 #include "rbd_tmem.cuh"
@@ -316,6 +317,41 @@ __global__ void __launch_bounds__(NT) crba_kernel(const __grid_constant__ ModelD
   }
 }
 
+template <class T> struct KinArgs {
+  const T* q; const T* v;
+  T* tr; T* com; T* ke; T* pe; T* mom; T* mrb; T* A; T* J;
+  T* scratch;
+  int64_t ld, B;
+};
+
+template <class T, int NT>
+__global__ void __launch_bounds__(NT) kin_kernel(const __grid_constant__ ModelDev<T> M, const KinArgs<T> a,
+                                                  const __grid_constant__ KinDev<T> K) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sh = reinterpret_cast<T*>(smem_raw);
+  const Stash<T, NT> st{sh + threadIdx.x};
+  const int64_t ngroups = (a.B + NT - 1) / NT;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t gn = g + gridDim.x;
+    if (gn < ngroups) {
+      const int64_t bn = gn * NT + (threadIdx.x & ~31);
+      prefetch_rows(a.q, M.nq, a.ld, bn);
+      if (a.v) prefetch_rows(a.v, M.nv, a.ld, bn);
+    }
+    const int64_t b = g * NT + threadIdx.x;
+    const bool active = b < a.B;
+    const int64_t bl = active ? b : a.B - 1;
+    KinIO<T> io;
+    io.q = {a.q + bl, a.ld};
+    io.v = {a.v ? a.v + bl : nullptr, a.ld};
+    auto out = [&](T* p) { return ColOut<T>{p ? p + bl : nullptr, a.ld, active}; };
+    io.tr = out(a.tr); io.com = out(a.com); io.ke = out(a.ke); io.pe = out(a.pe);
+    io.mom = out(a.mom); io.mrb = out(a.mrb); io.A = out(a.A); io.J = out(a.J);
+    io.poses = {a.scratch ? a.scratch + (int64_t)blockIdx.x * NT + threadIdx.x : nullptr, (int64_t)gridDim.x * NT};
+    kin_sample<T>(M, K, io, st);
+  }
+}
+
 template <class K> int configure(K kernel, int nt, size_t smem, const DeviceProps& p, int& blocks_per_sm) {
   if ((int)smem > p.max_smem_optin) return fail(RBD_EUNSUPPORTED, "model working set exceeds shared memory per block");
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -450,6 +486,45 @@ int mass_matrix_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, 
   for (int i = 0; i < hm.nb; ++i) multi |= kind_nv(M.body[i].kind) > 1;
   return multi ? launch<T>(crba_kernel<T, kNT, 6>, M, a, kNT, rows, 0, stream)
                : launch<T>(crba_kernel<T, kNT, 1>, M, a, kNT, rows, 0, stream);
+}
+
+// Kinematics by-products.  One launch; the momentum matrix additionally parks the 12 nb pose rows of
+// every resident thread in a stream-ordered scratch between its outward and inward sweeps.
+template <class T>
+int kinematics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, const void* v, const int8_t* path_sign,
+                 const rbd_kinematics_out& o, cudaStream_t stream) {
+  const HostModel& hm = model->hm;
+  const ModelDev<T>& M = dev_model<T>(hm);
+  KinDev<T> K;
+  std::memset(&K, 0, sizeof(K));
+  for (int p = 0; p < hm.nb; ++p) {
+    for (int k = 0; k < 9; ++k) K.At[p][k] = (T)hm.alignT[9 * p + k];
+    K.sign[p] = path_sign ? path_sign[hm.order[p]] : 0;
+  }
+  K.inv_mass = (T)(1.0 / hm.total_mass);
+  KinArgs<T> a{(const T*)q, (const T*)v, (T*)o.transforms_to_root, (T*)o.center_of_mass, (T*)o.kinetic_energy,
+               (T*)o.gravitational_potential_energy, (T*)o.momentum, (T*)o.momentum_rate_bias, (T*)o.momentum_matrix,
+               (T*)o.geometric_jacobian, nullptr, ld, B};
+  DeviceProps p;
+  if (int rc = get_props(p)) return rc;
+  auto kernel = kin_kernel<T, kNT>;
+  const size_t smem = (size_t)std::max(1, kin_rows(hm)) * kNT * sizeof(T);
+  int bps = 0;
+  if (int rc = configure(kernel, kNT, smem, p, bps)) return rc;
+  const int64_t ngroups = (B + kNT - 1) / kNT;
+  const int grid = (int)std::min<int64_t>(ngroups, (int64_t)bps * p.sms);
+  void* scratch = nullptr;
+  if (o.momentum_matrix) {
+    CUDA_TRY(cudaMallocAsync(&scratch, (size_t)12 * hm.nb * grid * kNT * sizeof(T), stream));
+    a.scratch = (T*)scratch;
+  }
+  kernel<<<grid, kNT, smem, stream>>>(M, a, K);
+  cudaError_t e = cudaGetLastError();
+  if (scratch) cudaFreeAsync(scratch, stream);
+  if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+  g_launch.kernels_launched += 1;
+  g_launch.grid = grid; g_launch.block = kNT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
+  return RBD_OK;
 }
 
 // dynamics! on Dual{Float64,6} arrays (config 4).  The Dual model (constants with zero partials, 25 KB) is built per call
@@ -601,6 +676,27 @@ int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld) {
 // ------------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------------
+int32_t rbd_kinematics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                       const int8_t* path_sign, const rbd_kinematics_out* out, void* stream) {
+  if (int rc = check_common(model, dtype, B, ld)) return rc;
+  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (dtype != RBD_F32 && dtype != RBD_F64) return fail(RBD_EUNSUPPORTED, "rbd_kinematics: fp32 and fp64 only");
+  if (!out) return fail(RBD_EINVAL, "rbd_kinematics: out must not be NULL");
+  if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
+  if (!q) return fail(RBD_EINVAL, "rbd_kinematics: q must not be NULL");
+  if (!v && (out->kinetic_energy || out->momentum || out->momentum_rate_bias))
+    return fail(RBD_EINVAL, "rbd_kinematics: kinetic_energy / momentum / momentum_rate_bias need v");
+  if ((out->geometric_jacobian != nullptr) != (path_sign != nullptr))
+    return fail(RBD_EINVAL, "rbd_kinematics: path_sign must be given iff geometric_jacobian is requested");
+  if (path_sign)
+    for (int i = 0; i < model->hm.nb; ++i)
+      if (path_sign[i] < -1 || path_sign[i] > 1) return fail(RBD_EINVAL, "rbd_kinematics: path_sign entries must be -1, 0 or +1");
+  if (model->hm.total_mass <= 0 && out->center_of_mass) return fail(RBD_EINVAL, "rbd_kinematics: mechanism has no mass");
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == RBD_F32 ? kinematics_t<float>(model, B, ld, q, v, path_sign, *out, s)
+                          : kinematics_t<double>(model, B, ld, q, v, path_sign, *out, s);
+}
+
 // ---- host-pointer variants: chunked H2D -> kernel -> D2H pipeline over three internal streams ----
 namespace {
 constexpr int64_t kChunk = 1 << 16;

@@ -1,0 +1,268 @@
+// Per-sample kinematics by-products in the ROOT frame, one thread per sample, same depth-first order,
+// register hand-over and pending slots as the dynamics passes.  Reference (relative to /root/reference/src):
+//   transform_to_root               mechanism_state.jl:687-714      T_i = T_parent * joint_to_predecessor_i * J_i(q_i)
+//   center_of_mass                  mechanism_algorithms.jl:30-49
+//   kinetic_energy                  mechanism_state.jl:886-888, :989-994 ; spatial/motion_force_interaction.jl:337-346
+//   gravitational_potential_energy  mechanism_state.jl:897-903, :996-1000
+//   momentum, momentum_rate_bias    mechanism_state.jl:878-884, :975-987
+//   momentum_matrix!                mechanism_algorithms.jl:313-327   A[:, k] = Ic_{body(k)} S_k
+//   geometric_jacobian!             mechanism_algorithms.jl:80-100    J[:, k] = +-S_k for the joints on a tree path
+// The kernels keep body frames canonicalised (rbd_model.cpp); every quantity written here is expressed in the root frame,
+// which does not depend on that choice, except transform_to_root itself, which is mapped back to the caller's body frames
+// with the per-body alignment rotation kept in KinDev.
+#pragma once
+#include "rbd_rnea_crba.cuh"
+
+namespace rbd {
+
+constexpr int kSlotRowsKin = 24;   // pose (12) + twist (6) + bias acceleration (6) of a branch node; 10 for the inward sweep
+
+template <class T> struct KinDev {
+  T At[kMaxBodies][9];         // preorder position -> A_i^T (canonical body frame <- caller's body frame), row-major
+  T inv_mass;                  // 1 / total mass
+  int8_t sign[kMaxBodies];     // preorder position -> +1 / -1 / 0: joint's direction on the jacobian path
+};
+
+template <class T> struct KinIO {
+  Col<T> q, v;                 // v may be invalid when no velocity-dependent output is requested
+  ColOut<T> tr, com, ke, pe, mom, mrb, A, J;
+  Scr<T> poses;                // [12 nb] rows per resident thread, only for the momentum matrix
+};
+
+// column c (0..2) of a row-major 3x3 with a warp-uniform runtime c
+template <class T> RBD_HD void mat_col(const T* R, int c, T* o) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) o[j] = c == 0 ? R[3 * j] : (c == 1 ? R[3 * j + 1] : R[3 * j + 2]);
+}
+
+// world-frame motion subspace column driven by one-hot body-frame component `comp` of [w; l]   (:749-763)
+template <class T> RBD_HD void world_subspace(const Pose<T>& w, int comp, Mot<T>& S) {
+  T ax[3];
+  mat_col(w.R, comp < 3 ? comp : comp - 3, ax);
+  if (comp < 3) {
+    S.w[0] = ax[0]; S.w[1] = ax[1]; S.w[2] = ax[2];
+    cross3(w.p, ax, S.l);
+  } else {
+    S.w[0] = S.w[1] = S.w[2] = T(0);
+    S.l[0] = ax[0]; S.l[1] = ax[1]; S.l[2] = ax[2];
+  }
+}
+
+template <class T> RBD_HD void body_rbi(const BodyDev<T>& bd, Rbi<T>& I) {
+  I.m = bd.m;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) I.h[k] = bd.h[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) I.J[k] = bd.J[k];
+}
+
+template <class T, class ST>
+RBD_HD void kin_sample(const ModelDev<T>& M, const KinDev<T>& K, const KinIO<T>& io, const ST& st) {
+  const int nb = M.nb;
+  const bool vel = io.v.valid();
+  const bool want_mom = vel && (io.ke.valid() || io.mom.valid() || io.mrb.valid());
+  Pose<T> cur;
+  pose_identity(cur);
+  Mot<T> twc, bc;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) twc.w[k] = twc.l[k] = bc.w[k] = bc.l[k] = T(0);
+  T mc[3] = {T(0), T(0), T(0)}, ke = T(0);
+  T hn[3] = {T(0), T(0), T(0)}, hf[3] = {T(0), T(0), T(0)}, bn[3] = {T(0), T(0), T(0)}, bf[3] = {T(0), T(0), T(0)};
+
+  // ---- outward sweep: poses, twists, bias accelerations, sums ----
+  for (int i = 0; i < nb; ++i) {
+    const BodyDev<T>& bd = M.body[i];
+    Pose<T> pp;
+    Mot<T> twp, bp;
+    if (bd.flags & F_ROOT_CHILD) {
+      pose_identity(pp);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) twp.w[k] = twp.l[k] = bp.w[k] = bp.l[k] = T(0);
+    } else if (bd.flags & F_FIRST_CHILD) {
+      pp = cur; twp = twc; bp = bc;
+    } else {
+      const int row = bd.pslot * kSlotRowsKin;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) pp.R[k] = st.ld(row + k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        pp.p[k] = st.ld(row + 9 + k);
+        twp.w[k] = st.ld(row + 12 + k); twp.l[k] = st.ld(row + 15 + k);
+        bp.w[k] = st.ld(row + 18 + k); bp.l[k] = st.ld(row + 21 + k);
+      }
+    }
+    T R[9], r[3], t[3];
+    frame_any(bd, io.q, R, r);
+    Pose<T> w;
+    mat_mul3(pp.R, R, w.R);
+    mat_vec(pp.R, r, t);
+    w.p[0] = pp.p[0] + t[0]; w.p[1] = pp.p[1] + t[1]; w.p[2] = pp.p[2] + t[2];
+    if (io.tr.valid()) {
+      T Ro[9];
+      mat_mul3(w.R, K.At[i], Ro);
+      const int row = 12 * bd.refidx;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) io.tr.st(row + k, Ro[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) io.tr.st(row + 9 + k, w.p[k]);
+    }
+    if (io.poses.valid()) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) io.poses.st(12 * i + k, w.R[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) io.poses.st(12 * i + 9 + k, w.p[k]);
+    }
+    // joint twist in the root frame, jacobian columns
+    Mot<T> jt;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) jt.w[k] = jt.l[k] = T(0);
+    const int nvj = kind_nv_dev(bd.kind);
+    if (vel || io.J.valid()) {
+      const T sg = T((int)K.sign[i]);
+      for (int k = 0; k < nvj; ++k) {
+        Mot<T> S;
+        world_subspace(w, sub_comp(bd.kind, k), S);
+        if (io.J.valid()) {
+          const int row = 6 * (bd.vrow + k);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { io.J.st(row + c, sg * S.w[c]); io.J.st(row + 3 + c, sg * S.l[c]); }
+        }
+        if (vel) {
+          const T x = io.v(bd.vrow + k);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { jt.w[c] += x * S.w[c]; jt.l[c] += x * S.l[c]; }
+        }
+      }
+    }
+    Mot<T> tw, bias;
+    {
+      Mot<T> cm;
+      motion_cross(twp, jt, cm);          // v_parent x (S v) == v_i x (S v): the world-frame velocity-product acceleration
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        tw.w[k] = twp.w[k] + jt.w[k]; tw.l[k] = twp.l[k] + jt.l[k];
+        bias.w[k] = bp.w[k] + cm.w[k]; bias.l[k] = bp.l[k] + cm.l[k];
+      }
+    }
+    // mass moment (for the centre of mass and the potential energy)
+    {
+      T Rh[3];
+      mat_vec(w.R, bd.h, Rh);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mc[k] += Rh[k] + bd.m * w.p[k];
+    }
+    if (want_mom) {
+      Rbi<T> Ib, Iw;
+      body_rbi(bd, Ib);
+      rbi_to_parent(w.R, w.p, Ib, Iw);     // body -> root frame (:836-846)
+      T n[3], f[3];
+      rbi_mul(Iw, tw, n, f);               // momentum of this body
+      ke += T(0.5) * (tw.w[0] * n[0] + tw.w[1] * n[1] + tw.w[2] * n[2] + tw.l[0] * f[0] + tw.l[1] * f[1] + tw.l[2] * f[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { hn[k] += n[k]; hf[k] += f[k]; }
+      if (io.mrb.valid()) {                // newton_euler(I, bias, twist) = I b + v x* (I v)
+        T an[3], af[3], c1[3], c2[3], c3[3];
+        rbi_mul(Iw, bias, an, af);
+        cross3(tw.w, n, c1);
+        cross3(tw.l, f, c2);
+        cross3(tw.w, f, c3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { bn[k] += an[k] + c1[k] + c2[k]; bf[k] += af[k] + c3[k]; }
+      }
+    }
+    if (bd.flags & F_HAS_PENDING) {
+      const int row = bd.oslot * kSlotRowsKin;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) st.st(row + k, w.R[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        st.st(row + 9 + k, w.p[k]);
+        st.st(row + 12 + k, tw.w[k]); st.st(row + 15 + k, tw.l[k]);
+        st.st(row + 18 + k, bias.w[k]); st.st(row + 21 + k, bias.l[k]);
+      }
+    }
+    cur = w; twc = tw; bc = bias;
+  }
+  if (io.com.valid()) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) io.com.st(k, mc[k] * K.inv_mass);
+  }
+  if (io.pe.valid()) io.pe.st(0, -(M.g[0] * mc[0] + M.g[1] * mc[1] + M.g[2] * mc[2]));
+  if (vel) {
+    if (io.ke.valid()) io.ke.st(0, ke);
+    if (io.mom.valid()) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { io.mom.st(k, hn[k]); io.mom.st(3 + k, hf[k]); }
+    }
+    if (io.mrb.valid()) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { io.mrb.st(k, bn[k]); io.mrb.st(3 + k, bf[k]); }
+    }
+  }
+  if (!io.A.valid()) return;
+
+  // ---- inward sweep: composite inertias in the root frame (plain sums, :852-868) and A[:, k] = Ic S_k ----
+  Rbi<T> carry;
+  carry.m = T(0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) carry.h[k] = T(0);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) carry.J[k] = T(0);
+  for (int i = nb - 1; i >= 0; --i) {
+    const BodyDev<T>& bd = M.body[i];
+    Pose<T> w;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w.R[k] = io.poses.get(12 * i + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w.p[k] = io.poses.get(12 * i + 9 + k);
+    Rbi<T> Ib, Ic;
+    body_rbi(bd, Ib);
+    rbi_to_parent(w.R, w.p, Ib, Ic);
+    if (!(bd.flags & F_LEAF)) {
+      Ic.m += carry.m;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Ic.h[k] += carry.h[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Ic.J[k] += carry.J[k];
+    }
+    if (bd.flags & F_HAS_PENDING) {
+      const int row = bd.oslot * kSlotRowsKin;
+      Ic.m += st.ld(row);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Ic.h[k] += st.ld(row + 1 + k);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Ic.J[k] += st.ld(row + 4 + k);
+    }
+    const int nvj = kind_nv_dev(bd.kind);
+    for (int k = 0; k < nvj; ++k) {
+      Mot<T> S;
+      world_subspace(w, sub_comp(bd.kind, k), S);
+      T n[3], f[3];
+      rbi_mul(Ic, S, n, f);
+      const int row = 6 * (bd.vrow + k);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { io.A.st(row + c, n[c]); io.A.st(row + 3 + c, f[c]); }
+    }
+    if (bd.flags & F_ROOT_CHILD) continue;
+    if (bd.flags & F_FIRST_CHILD) {
+      carry = Ic;
+    } else {
+      const int row = bd.pslot * kSlotRowsKin;
+      if (bd.flags & F_SLOT_INIT) {
+        st.st(row, Ic.m);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st.st(row + 1 + k, Ic.h[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st.st(row + 4 + k, Ic.J[k]);
+      } else {
+        st.add(row, Ic.m);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st.add(row + 1 + k, Ic.h[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st.add(row + 4 + k, Ic.J[k]);
+      }
+    }
+  }
+}
+
+}  // namespace rbd

@@ -246,6 +246,11 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
     b.J[3] = Jc.m[4]; b.J[4] = 0.5 * (Jc.m[5] + Jc.m[7]); b.J[5] = Jc.m[8];
     mulv(transp(A[j]), in + 9, b.h);
     b.m = in[12];
+    {
+      Mat3 At = transp(A[j]);
+      out.alignT.insert(out.alignT.end(), At.m, At.m + 9);
+      out.total_mass += in[12];
+    }
     // flags
     const int nchild = (int)children[j].size();
     int flags = 0;

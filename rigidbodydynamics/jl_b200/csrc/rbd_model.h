@@ -18,6 +18,8 @@ struct HostModel {
   std::vector<int> order;    // preorder position -> reference joint index
   std::vector<int> pos;      // reference joint index -> preorder position
   std::vector<int> qstart, vstart;   // reference order
+  std::vector<double> alignT;        // preorder position -> A^T (9), canonical body frame <- caller's body frame
+  double total_mass = 0;
   ModelDev<double> dev64;    // ABA row layout (row0 / nrows); RNEA and CRBA derive theirs from slot indices
   ModelDev<float> dev32;
 };
@@ -29,5 +31,6 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
 inline int aba_rows(const HostModel& m) { return m.dev64.nrows; }
 inline int rnea_rows(const HostModel& m) { return m.nb * 6 + m.nslots * kSlotRowsRnea; }
 inline int crba_rows(const HostModel& m) { return m.nb * 2 + m.nslots * kSlotRowsCrba; }
+inline int kin_rows(const HostModel& m) { return m.nslots * 24; }
 
 }  // namespace rbd

@@ -9,8 +9,8 @@ _LIB = os.path.join(_HERE, "libhostsim.so")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in
-            ("rbd_model.cpp", "rbd_model.h", "rbd_types.h", "rbd_device.cuh")]
+    srcs = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)
+                                                   if f.endswith((".cuh", ".h", ".cpp"))]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB,
                                os.path.join(_HERE, "hostsim.cpp"), os.path.join(_CSRC, "rbd_model.cpp")])
@@ -109,3 +109,28 @@ def integrate(desc, q, v, tau=None, dt=1e-4, nsteps=1):
     rc = fn(ctypes.byref(d), 0 if dt_ == np.float32 else 1, q.shape[1], _p(q), _p(v), _p(tau), float(dt), int(nsteps))
     assert rc == 0, rc
     return q, v
+
+
+KIN_ROWS = ("transforms", "com", "ke", "pe", "momentum", "mrb", "A", "J")
+
+
+def kinematics(desc, q, v=None, sign=None, want=KIN_ROWS):
+    """kin_sample on the CPU; returns the same dict as Oracle.kinematics."""
+    dt = q.dtype
+    d, keep = make_desc(desc)
+    q = np.ascontiguousarray(q); v = None if v is None else np.ascontiguousarray(v, dt)
+    B = q.shape[1]
+    rows = {"transforms": 12 * desc.nb, "com": 3, "ke": 1, "pe": 1, "momentum": 6, "mrb": 6, "A": 6 * desc.nv, "J": 6 * desc.nv}
+    out = {k: (np.full((rows[k], B), np.nan, dt) if k in want else None) for k in KIN_ROWS}
+    if v is None:
+        out["ke"] = out["momentum"] = out["mrb"] = None
+    sg = None if sign is None else np.ascontiguousarray(sign, np.int8)
+    if sg is None:
+        out["J"] = None
+    ptrs = (ctypes.c_void_p * 8)(*[None if out[k] is None else out[k].ctypes.data for k in KIN_ROWS])
+    fn = lib().hostsim_kinematics
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc), ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                   ctypes.c_void_p]
+    rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(v), _p(sg), ptrs)
+    assert rc == 0, rc
+    return {k: a for k, a in out.items() if a is not None}

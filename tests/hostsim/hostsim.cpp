@@ -2,10 +2,12 @@
 // Runs the per-sample device algorithms of csrc/rbd_device.cuh ON THE CPU (they are __host__ __device__ templates)
 // so that the math of the kernels can be checked against the oracle in the CPU-only test tier, before any GPU time
 // is spent.  The shipped librbd_b200.so does not contain this file and has no CPU path.
+#include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_rnea_crba.cuh"
+#include "../../rigidbodydynamics/jl_b200/csrc/rbd_kin.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_dual.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_integrate.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_model.h"
@@ -50,6 +52,28 @@ void run_rnea(const HostModel& hm, int64_t B, const T* q, const T* v, const T* v
     io.tau = {tau + b, B, true};
     io.ext = {wext ? scratch.data() : nullptr, 1};
     rnea_sample<T, 1>(M, io, Stash<T, 1>{stash.data()});
+  }
+}
+
+template <class T>
+void run_kin(const HostModel& hm, int64_t B, const T* q, const T* v, const int8_t* sign, T* const* o /* 8 outputs */) {
+  const ModelDev<T>& M = dev<T>(hm);
+  KinDev<T> K;
+  std::memset(&K, 0, sizeof(K));
+  for (int p = 0; p < hm.nb; ++p) {
+    for (int k = 0; k < 9; ++k) K.At[p][k] = (T)hm.alignT[9 * p + k];
+    K.sign[p] = sign ? sign[hm.order[p]] : 0;
+  }
+  K.inv_mass = (T)(1.0 / hm.total_mass);
+  std::vector<T> stash(kin_rows(hm) + 64), scratch(12 * M.nb);
+  for (int64_t b = 0; b < B; ++b) {
+    KinIO<T> io;
+    io.q = {q + b, B}; io.v = {v ? v + b : nullptr, B};
+    auto out = [&](T* p) { return ColOut<T>{p ? p + b : nullptr, B, true}; };
+    io.tr = out(o[0]); io.com = out(o[1]); io.ke = out(o[2]); io.pe = out(o[3]);
+    io.mom = out(o[4]); io.mrb = out(o[5]); io.A = out(o[6]); io.J = out(o[7]);
+    io.poses = {o[6] ? scratch.data() : nullptr, 1};
+    kin_sample<T>(M, K, io, Stash<T, 1>{stash.data()});
   }
 }
 
@@ -190,6 +214,15 @@ int hostsim_mass_matrix(const rbd_model_desc* d, int dtype, int64_t B, const voi
   if (rc) return rc;
   if (dtype == 0) run_crba<float>(hm, B, (const float*)q, (float*)M);
   else run_crba<double>(hm, B, (const double*)q, (double*)M);
+  return 0;
+}
+int hostsim_kinematics(const rbd_model_desc* d, int dtype, int64_t B, const void* q, const void* v, const int8_t* sign,
+                       void* const* outs) {
+  HostModel hm; std::string err;
+  int rc = build_host_model(d, hm, err);
+  if (rc) return rc;
+  if (dtype == 0) run_kin<float>(hm, B, (const float*)q, (const float*)v, sign, (float* const*)outs);
+  else run_kin<double>(hm, B, (const double*)q, (const double*)v, sign, (double* const*)outs);
   return 0;
 }
 }

@@ -407,3 +407,94 @@ def test_simulate_all_joint_types_and_energy(built):
     e0 = energy(stp)
     rbd.simulate_(stp, 0.1, None, dt=1e-2)
     assert float((energy(stp) - e0).abs().max()) < 1e-3
+
+
+# ---- kinematics by-products ---------------------------------------------------------------------
+KIN_NAMES = {"transforms": "transforms_to_root", "com": "center_of_mass", "ke": "kinetic_energy",
+             "pe": "gravitational_potential_energy", "momentum": "momentum", "mrb": "momentum_rate_bias",
+             "A": "momentum_matrix", "J": "geometric_jacobian"}
+
+
+def _gpu_state(mech, q, v, dtype):
+    state = rbd.MechanismState(mech, q.shape[1], dtype)
+    state.q.copy_(torch.from_numpy(q).to(dtype))
+    state.v.copy_(torch.from_numpy(v).to(dtype))
+    return state
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name,floating", [("atlas", True), ("valkyrie", False), ("iiwa14", False), ("double_pendulum", False)])
+def test_kinematics_matches_oracle(built, name, floating, dtype):
+    mech = rbd.load_model(name, floating=floating)
+    desc = mech.flatten()
+    q, v, _, _, _ = rand_inputs(mech, 257, 23)
+    p = rbd.path(mech, mech.joints[-1].successor, mech.joints[min(2, desc.nb - 1)].successor)
+    ref = Oracle(desc).kinematics(q, v, p.sign)
+    state = _gpu_state(mech, q, v, dtype)
+    outs = {KIN_NAMES[k]: torch.full((a.shape[0], q.shape[1]), float("nan"), dtype=dtype, device="cuda") for k, a in ref.items()}
+    rbd.kinematics_(state, p, **outs)                     # fused: all eight outputs from one launch
+    assert rbd.launch_info().kernels_launched == 1
+    torch.cuda.synchronize()
+    tol = 1e-11 if dtype == torch.float64 else 2e-5
+    for k, a in ref.items():
+        got = outs[KIN_NAMES[k]].double().cpu().numpy()
+        assert np.abs(got - a).max() / max(1.0, np.abs(a).max()) < tol, k
+    # the reference-named single-output calls
+    assert np.allclose(rbd.center_of_mass(state).double().cpu().numpy(), ref["com"], atol=tol * 10)
+    assert np.allclose(rbd.kinetic_energy(state).double().cpu().numpy(), ref["ke"][0], rtol=tol * 10, atol=tol * 10)
+    assert np.allclose(rbd.gravitational_potential_energy(state).double().cpu().numpy(), ref["pe"][0], rtol=tol * 10, atol=tol * 10)
+    assert np.allclose(rbd.momentum(state).double().cpu().numpy(), ref["momentum"], rtol=tol * 10, atol=tol * 10)
+    assert np.allclose(rbd.momentum_rate_bias(state).double().cpu().numpy(), ref["mrb"], rtol=tol * 100, atol=tol * 100)
+    assert np.allclose(rbd.momentum_matrix(state).double().cpu().numpy(), ref["A"], rtol=tol * 10, atol=tol * 10)
+    assert np.allclose(rbd.geometric_jacobian(state, p).double().cpu().numpy(), ref["J"], atol=tol * 10)
+    assert np.allclose(rbd.transforms_to_root(state).double().cpu().numpy(), ref["transforms"], atol=tol * 10)
+
+
+@pytest.mark.parametrize("seed", [17, 18, 19])
+def test_kinematics_all_joint_types(built, seed):
+    mech = randmech(seed, shuffle=seed % 2 == 1)
+    desc = mech.flatten()
+    q, v, _, _, _ = rand_inputs(mech, 97, seed)
+    rng = np.random.default_rng(seed)
+    a, b = rng.choice(desc.nb, 2, replace=False)
+    p = rbd.path(mech, mech.joints[a].successor, mech.joints[b].successor)
+    ref = Oracle(desc).kinematics(q, v, p.sign)
+    state = _gpu_state(mech, q, v, torch.float64)
+    outs = {KIN_NAMES[k]: torch.empty((r.shape[0], q.shape[1]), dtype=torch.float64, device="cuda") for k, r in ref.items()}
+    rbd.kinematics_(state, p, **outs)
+    torch.cuda.synchronize()
+    for k, r in ref.items():
+        assert np.abs(outs[KIN_NAMES[k]].cpu().numpy() - r).max() / max(1.0, np.abs(r).max()) < 1e-11, k
+
+
+def test_kinematics_identities_at_scale_and_errors(built):
+    """Atlas, fp32, 2^18 samples: 1/2 v'Mv = KE and A v = momentum (size-independent properties); error behaviour."""
+    mech = rbd.load_model("atlas", floating=True)
+    B = 1 << 18
+    state = rbd.MechanismState(mech, B, torch.float32)
+    rng = np.random.default_rng(3)
+    rbd.rand_(state, rng)
+    nv = state.nv
+    ke = rbd.kinetic_energy(state)
+    A = rbd.momentum_matrix(state).view(nv, 6, B)
+    h = rbd.momentum(state)
+    M = rbd.mass_matrix(state).view(nv, nv, B)
+    torch.cuda.synchronize()
+    ke2 = 0.5 * torch.einsum("ib,ijb,jb->b", state.v.double(), M.double(), state.v.double())
+    assert float(((ke.double() - ke2).abs() / ke2.abs().clamp(min=1)).max()) < 1e-4
+    Av = torch.einsum("kcb,kb->cb", A.double(), state.v.double())
+    assert float(((Av - h.double()).abs().max(0).values / h.double().abs().max(0).values.clamp(min=1)).max()) < 1e-4
+    # errors: wrong size -> DimensionMismatch; jacobian without a path; path of another mechanism
+    with pytest.raises(rbd.DimensionMismatch):
+        rbd.kinematics_(state, None, center_of_mass=torch.empty((4, B), dtype=torch.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        rbd.kinematics_(state, None, geometric_jacobian=torch.empty((6 * nv, B), dtype=torch.float32, device="cuda"))
+    lib = rbd.load_library()
+    from rigidbodydynamics.jl_b200 import _cabi
+    ko = _cabi.RbdKinematicsOut()
+    ko.kinetic_energy = ke.data_ptr()
+    import ctypes
+    rc = lib.rbd_kinematics(state.handle.ptr, 0, B, B, state.q.data_ptr(), None, None, ctypes.byref(ko), None)
+    assert rc == _cabi.RBD_EINVAL                                    # kinetic energy without v
+    assert lib.rbd_kinematics(state.handle.ptr, 2, B, B, state.q.data_ptr(), None, None, ctypes.byref(ko), None) == _cabi.RBD_EUNSUPPORTED
+    assert lib.rbd_kinematics(state.handle.ptr, 0, 0, 0, None, None, None, ctypes.byref(ko), None) == _cabi.RBD_OK
