@@ -180,17 +180,22 @@ __device__ __forceinline__ void aba_queue_loop(const ModelDev<T>& M, const AbaAr
   }
 }
 template <class T, int KINDS>
-__global__ void __launch_bounds__(32) aba_kernel_smem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
+__global__ void __launch_bounds__(32, sizeof(T) == 4 ? 16 : 1) aba_kernel_smem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   aba_queue_loop<T, Stash<T, 32>, KINDS>(M, a, Stash<T, 32>{reinterpret_cast<T*>(smem_raw) + threadIdx.x});
 }
-// CTA of 4 warps: warp w owns TMEM lane quadrant w; COLS columns per thread (fp32: one per row, fp64: two per row).
-template <class T, int COLS, int KINDS>
-__global__ void __launch_bounds__(128) aba_kernel_tmem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
+// CTA of NW = 4 or 8 warps over COLS TMEM columns.  Warp w may only touch TMEM lane quadrant w % 4, so warps 0-3 keep their
+// stash in the first COLS / (NW / 4) columns and warps 4-7 (same lanes) in the second half: in fp32 (one column per row,
+// <= 256 rows) one CTA fills all 512 columns with the working sets of 8 warps; fp64 needs two columns per row, 4 warps.
+// Register budget: the CTA shares the SM with the 8 single-warp blocks of aba_kernel_smem_q, 16 warps x 32 x 128 = 64 K.
+template <class T, int COLS, int KINDS, int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1)
+aba_kernel_tmem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   __shared__ uint32_t tm_slot;
   const uint32_t tm_base = tmem_alloc_cta<COLS>(&tm_slot);
   using ST = typename StashTMFor<T>::type;
-  aba_queue_loop<T, ST, KINDS>(M, a, ST{tm_base + ((uint32_t)((threadIdx.x >> 5) * 32) << 16)});
+  const uint32_t w = threadIdx.x >> 5;
+  aba_queue_loop<T, ST, KINDS>(M, a, ST{tm_base + (((w & 3u) * 32u) << 16) + (w >> 2) * (uint32_t)(COLS / (NW / 4))});
   tmem_free_cta<COLS>(tm_base);
 }
 
@@ -407,20 +412,22 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
   for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
   {
-    // Default path for all-revolute trees whose stash fits Tensor Memory (fp32: <= 256 rows in 256 columns, fp64: <= 256 rows
-    // in 512 columns): the shared-memory kernel on `stream` plus the Tensor-Memory kernel (one 4-warp CTA per SM, stash in
-    // TMEM, no shared memory) on the handle's side stream, both claiming groups from one atomic counter.  On Atlas that is
-    // 8 + 4 resident warps/SM in fp32 and 4 + 4 in fp64.
+    // Default path for all-revolute trees whose stash fits Tensor Memory (<= 256 rows): the shared-memory kernel on `stream`
+    // plus the Tensor-Memory kernel (one CTA per SM, stash in TMEM, no shared memory) on the handle's side stream, both
+    // claiming groups from one atomic counter.  fp32: one row = one TMEM column, so the 512 columns hold the stash of 8 warps
+    // (two column halves x four lane quadrants); fp64: two columns per row, 4 warps.  On Atlas that is 8 + 8 resident
+    // warps/SM in fp32 (16 x 32 x 128 registers = the whole register file) and 4 + 4 in fp64.
     const int64_t ngroups = (B + kNT - 1) / kNT;
     if (!wext && !hm.general && !other_kinds && rows <= 256 && !getenv("RBD_NO_TMEM")) {
       DeviceProps p;
       if (int rc = get_props(p)) return rc;
       auto ks = aba_kernel_smem_q<T, 0>;
-      auto kt = aba_kernel_tmem_q<T, 256 * StashTMFor<T>::kColsPerRow, 0>;
+      constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;      // fp32: 2 x 256 columns, fp64: 1 x 512 columns
+      auto kt = aba_kernel_tmem_q<T, 512, 0, kTmWarps>;
       const size_t smem = (size_t)rows * kNT * sizeof(T);
       int bps = 0;
       if (int rc = configure(ks, kNT, smem, p, bps)) return rc;
-      if (ngroups >= (int64_t)(bps + 4) * p.sms) {        // enough work for every resident warp of both kernels
+      if (ngroups >= (int64_t)(bps + kTmWarps / 2) * p.sms) {   // enough work to keep both kernels' warps busy
         rbd_model* mm = const_cast<rbd_model*>(model);
         cudaStream_t side = nullptr;
         {
@@ -444,7 +451,7 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
         const char* only = getenv("RBD_ONLY");
         if (getenv("RBD_SMEM_BLOCKS")) bps = std::min(bps, atoi(getenv("RBD_SMEM_BLOCKS")));
         if (!only || only[0] == 's') ks<<<bps * p.sms, kNT, smem, stream>>>(M, ah);
-        if (!only || only[0] == 't') kt<<<((only && sizeof(T) == 4) ? 2 : 1) * p.sms, 128, 0, side>>>(M, ah);
+        if (!only || only[0] == 't') kt<<<p.sms, 32 * kTmWarps, 0, side>>>(M, ah);
         cudaError_t e = cudaGetLastError();
         cudaEventRecord(join, side);
         cudaStreamWaitEvent(stream, join, 0);
@@ -543,6 +550,7 @@ int dynamics_dual(const rbd_model* model, int64_t B, int64_t ld, const void* q, 
     for (int k = 0; k < 3; ++k) { d.pt[k] = Dual64(s.pt[k]); d.h[k] = Dual64(s.h[k]); }
     for (int k = 0; k < 6; ++k) d.J[k] = Dual64(s.J[k]);
     d.m = Dual64(s.m);
+    d.qoff = Dual64(s.qoff);
     d.kind = s.kind; d.parent = s.parent; d.qrow = s.qrow; d.vrow = s.vrow; d.row0 = s.row0;
     d.oslot = s.oslot; d.pslot = s.pslot; d.flags = s.flags; d.refidx = s.refidx;
     d.pair = s.pair; d.next_fwd = s.next_fwd; d.next_rev = s.next_rev;

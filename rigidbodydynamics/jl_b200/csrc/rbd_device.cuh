@@ -331,8 +331,18 @@ template <class T, int K> RBD_HD void joint_motion_multi(int kind, const T* x, M
 }
 
 // q̇ = N(q) v per joint type (velocity_to_configuration_derivative!)
-template <class T> RBD_HD void qdot_joint(const BodyDev<T>& bd, const Col<T>& q, const Col<T>& v, const ColOut<T>& qd) {
+template <class T, bool ONLY1 = false>
+RBD_HD void qdot_joint(const BodyDev<T>& bd, const Col<T>& q, const Col<T>& v, const ColOut<T>& qd) {
   const int q0 = bd.qrow, v0 = bd.vrow;
+  if (ONLY1) {                                    // caller guarantees a 1-DoF / fixed joint: keep the multi-DoF code out of its loop
+    if (bd.kind == K_REV || bd.kind == K_PRIS) qd.st(q0, v(v0));
+    else if (bd.kind == K_SINCOS) {
+      T w = v(v0);
+      qd.st(q0, q(q0 + 1) * w);
+      qd.st(q0 + 1, -q(q0) * w);
+    }
+    return;
+  }
   switch (bd.kind) {
     case K_REV: case K_PRIS: qd.st(q0, v(v0)); break;                           // joint_types.jl:29-32
     case K_FIXED: break;
@@ -527,6 +537,114 @@ template <class T, bool ZAZ> RBD_HD void art_to_parent(const T* R, const T* r, c
   force_to_parent(R, r, c.n, c.f, o.n, o.f);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast classes (F_ZPAR / F_ZPERP): joint transform E = [P] Rz(s, c), origin r = pt.  PERM = 1 applies the cyclic
+// permutation P after the z-rotation (P v = (v_z, v_x, v_y)); PERM = 0 is a plain z-rotation.
+// ------------------------------------------------------------------------------------------------------------------
+template <class T, int PERM> RBD_HD void zrot_fwd(T s, T c, const T* v, T* o) {          // o = E v
+  const T t0 = c * v[0] - s * v[1], t1 = s * v[0] + c * v[1];
+  if (PERM) { o[0] = v[2]; o[1] = t0; o[2] = t1; } else { o[0] = t0; o[1] = t1; o[2] = v[2]; }
+}
+template <class T, int PERM> RBD_HD void zrot_inv(T s, T c, const T* w, T* o) {          // o = E^T w
+  const T u0 = PERM ? w[1] : w[0], u1 = PERM ? w[2] : w[1], u2 = PERM ? w[0] : w[2];
+  o[0] = c * u0 + s * u1; o[1] = c * u1 - s * u0; o[2] = u2;
+}
+template <class T, int PERM> RBD_HD void motion_to_child_z(T s, T c, const T* r, const Mot<T>& p, Mot<T>& ch) {
+  zrot_inv<T, PERM>(s, c, p.w, ch.w);
+  T t[3];
+  cross3(p.w, r, t);
+  t[0] += p.l[0]; t[1] += p.l[1]; t[2] += p.l[2];
+  zrot_inv<T, PERM>(s, c, t, ch.l);
+}
+// Shared tail of the child -> parent hand-over: blocks already rotated into the parent's axes, now shift the origin by r.
+//   C' = Cr ;  B' = Br + r^ Cr ;  A' = Ar + P + P^T + W  with  P = r^ Br^T,  W = r^ (r^ Cr)^T ;  f' = fr ;  n' = nr + r x fr
+template <class T>
+RBD_HD void art_shift(const T* r, const T* Ar, const T* Br, const T* Cr, const T* nr, const T* fr, Art<T>& o) {
+  T Q[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const T m0 = Cr[sidx(0, j)], m1 = Cr[sidx(1, j)], m2 = Cr[sidx(2, j)];
+    Q[0 + j] = r[1] * m2 - r[2] * m1;
+    Q[3 + j] = r[2] * m0 - r[0] * m2;
+    Q[6 + j] = r[0] * m1 - r[1] * m0;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) o.B[k] = Br[k] + Q[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) o.C[k] = Cr[k];
+  T P[9], W[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    P[0 + j] = r[1] * Br[3 * j + 2] - r[2] * Br[3 * j + 1];
+    P[3 + j] = r[2] * Br[3 * j + 0] - r[0] * Br[3 * j + 2];
+    P[6 + j] = r[0] * Br[3 * j + 1] - r[1] * Br[3 * j + 0];
+    W[0 + j] = r[1] * Q[3 * j + 2] - r[2] * Q[3 * j + 1];
+    W[3 + j] = r[2] * Q[3 * j + 0] - r[0] * Q[3 * j + 2];
+    W[6 + j] = r[0] * Q[3 * j + 1] - r[1] * Q[3 * j + 0];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) o.A[sidx(i, j)] = Ar[sidx(i, j)] + P[3 * i + j] + P[3 * j + i] + W[3 * i + j];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) o.f[k] = fr[k];
+  o.n[0] = nr[0] + r[1] * fr[2] - r[2] * fr[1];
+  o.n[1] = nr[1] + r[2] * fr[0] - r[0] * fr[2];
+  o.n[2] = nr[2] + r[0] * fr[1] - r[1] * fr[0];
+}
+// Child -> parent hand-over for the fast classes.  The child's inertia `b` has a vanishing angular-z row / column (a
+// revolute-z DoF was just eliminated).  Congruence by Rz acts on the xy-plane only: a symmetric 2x2 block turns by the
+// double angle ( (xx-yy)/2, xy ), the (xz, yz) pairs turn by the single angle, zz stays; P is an index relabelling.
+template <class T, int PERM> RBD_HD void art_to_parent_z(T s, T c, const T* r, const Art<T>& b, Art<T>& o) {
+  const T c2 = c * c - s * s, s2 = (s + s) * c;
+  T Ya[6], Yb[9], Yc[6], yn[3], yf[3];
+  {  // A: only xx, xy, yy are non-zero
+    const T m = T(0.5) * (b.A[0] + b.A[3]), d = T(0.5) * (b.A[0] - b.A[3]);
+    const T dn = c2 * d - s2 * b.A[1];
+    Ya[0] = m + dn; Ya[1] = s2 * d + c2 * b.A[1]; Ya[3] = m - dn;
+    Ya[2] = T(0); Ya[4] = T(0); Ya[5] = T(0);
+  }
+  {  // C: full symmetric
+    const T m = T(0.5) * (b.C[0] + b.C[3]), d = T(0.5) * (b.C[0] - b.C[3]);
+    const T dn = c2 * d - s2 * b.C[1];
+    Yc[0] = m + dn; Yc[1] = s2 * d + c2 * b.C[1]; Yc[3] = m - dn;
+    Yc[2] = c * b.C[2] - s * b.C[4]; Yc[4] = s * b.C[2] + c * b.C[4]; Yc[5] = b.C[5];
+  }
+  {  // B: rows x, y (row z vanishes):  Rz2 B Rz3^T
+    T t[6];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {        // columns
+      t[3 * i + 0] = c * b.B[3 * i + 0] - s * b.B[3 * i + 1];
+      t[3 * i + 1] = s * b.B[3 * i + 0] + c * b.B[3 * i + 1];
+      t[3 * i + 2] = b.B[3 * i + 2];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {        // rows
+      Yb[0 + j] = c * t[0 + j] - s * t[3 + j];
+      Yb[3 + j] = s * t[0 + j] + c * t[3 + j];
+      Yb[6 + j] = T(0);
+    }
+  }
+  yn[0] = c * b.n[0] - s * b.n[1]; yn[1] = s * b.n[0] + c * b.n[1]; yn[2] = b.n[2];
+  yf[0] = c * b.f[0] - s * b.f[1]; yf[1] = s * b.f[0] + c * b.f[1]; yf[2] = b.f[2];
+  if (PERM) {
+    // X'[i][j] = Y[sg(i)][sg(j)], sg = (2, 0, 1)
+    constexpr int sg[3] = {2, 0, 1};
+    T Ar[6], Br[9], Cr[6], nr[3], fr[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = i; j < 3; ++j) { Ar[sidx(i, j)] = Ya[sidx(sg[i], sg[j])]; Cr[sidx(i, j)] = Yc[sidx(sg[i], sg[j])]; }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Br[3 * i + j] = Yb[3 * sg[i] + sg[j]];
+      nr[i] = yn[sg[i]]; fr[i] = yf[sg[i]];
+    }
+    art_shift(r, Ar, Br, Cr, nr, fr, o);
+  } else {
+    art_shift(r, Ya, Yb, Yc, yn, yf, o);
+  }
+}
+
 // Hand a finished child contribution (already in `carry`, written there by art_to_parent) to its parent: a first child's
 // stays in registers; any other child's goes to the parent's pending slot.  Writing every contribution into `carry` is safe
 // because a non-first child is followed (in reverse preorder) by the last body of a sibling subtree, a leaf, which does not
@@ -628,15 +746,18 @@ template <class T, bool EXT = false, int KINDS = kAllKinds> struct AbaIO {
 
 // Scalars of one 1-DoF body that come from global memory.  They are requested one body AHEAD of their use (software
 // pipelining in aba_sample) so the load latency overlaps the previous body's arithmetic instead of stalling the warp.
-template <class T> struct Pre { T q0, q1, qd, tau; T w[6]; };
+template <class T> struct Pre { T q0, q1, qd, tau; T w[6]; T qoff; int32_t zflags; };
 template <class T, int PASS, class IO>
 RBD_HD void prefetch_body(const ModelDev<T>& M, int i, const IO& io, Pre<T>& p) {
   p.q0 = T(0); p.q1 = T(0); p.qd = T(0); p.tau = T(0);
 #pragma unroll
   for (int k = 0; k < 6; ++k) p.w[k] = T(0);
+  p.zflags = 0; p.qoff = T(0);
   if (i < 0 || i >= M.nb) return;
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
+  p.zflags = bd.flags & (F_ZPAR | F_ZPERP);      // fast-class bits and angle offset, fetched a body ahead like the joint scalars
+  p.qoff = bd.qoff;
   if (PASS == 2 && IO::kExt) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) p.w[k] = io.ext.get(6 * i + k);
@@ -650,15 +771,18 @@ RBD_HD void prefetch_body(const ModelDev<T>& M, int i, const IO& io, Pre<T>& p) 
 }
 
 // sin / cos / displacement of a 1-DoF joint from its prefetched configuration scalars
-template <class T> RBD_HD void joint_scd(int kind, const Pre<T>& pre, T& s, T& c, T& d) {
+// (`qoff`: the constant z-rotation of the fast classes, added HERE and not where q is loaded, so that the load issued one body
+//  ahead is not consumed before it has arrived)
+template <class T> RBD_HD void joint_scd(int kind, const Pre<T>& pre, T& s, T& c, T& d, T qoff = T(0)) {
   s = T(0); c = T(1); d = T(0);
-  if (kind == K_REV) sincos_t(pre.q0, s, c);
+  if (kind == K_REV) sincos_t(pre.q0 + qoff, s, c);
   else if (kind == K_SINCOS) { s = pre.q0; c = pre.q1; }
   else if (kind == K_PRIS) d = pre.q0;
 }
 
 // ---- pass 1 (outward): velocities ---------------------------------------------------------------------------------
-template <class T, class ST, bool GENERAL, class IO>
+// ANY: the body may carry a multi-DoF joint (always possible for body 0; elsewhere only in GENERAL models)
+template <class T, class ST, bool ANY, class IO>
 RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const ST& st, Mot<T>& vcur,
                            const Pre<T>& pre) {
   const BodyDev<T>& bd = M.body[i];
@@ -679,7 +803,13 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const ST& 
   const int kind = bd.kind;
   T R[9], r[3];
   Mot<T> v;
-  if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
+  if (pre.zflags) {                                  // revolute, E = [P] Rz(q + qoff)
+    T s, c;
+    sincos_t(pre.q0 + pre.qoff, s, c);
+    if (pre.zflags & F_ZPERP) motion_to_child_z<T, 1>(s, c, bd.pt, vp, v);
+    else motion_to_child_z<T, 0>(s, c, bd.pt, vp, v);
+    v.w[2] += pre.qd;
+  } else if (!ANY || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
     T s, c, d, qd = T(0);
     joint_scd(kind, pre, s, c, d);
     if (!(IO::kKinds & kHasFixed) || kind != K_FIXED) qd = pre.qd;
@@ -703,7 +833,7 @@ RBD_HD void aba_pass1_body(const ModelDev<T>& M, int i, const IO& io, const ST& 
 #pragma unroll
   for (int k = 0; k < 3; ++k) { st.st(bd.row0 + k, v.w[k]); st.st(bd.row0 + 3 + k, v.l[k]); }
   vcur = v;
-  if (io.qd.valid()) qdot_joint(bd, io.q, io.v, io.qd);
+  if (io.qd.valid()) qdot_joint<T, !ANY>(bd, io.q, io.v, io.qd);
 }
 
 // Eliminate a revolute-z DoF from the assembled articulated quantities `a` of a body moving with `v`:
@@ -774,7 +904,7 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
     return;
   }
   T sn, c, dd;
-  joint_scd(kind, pre, sn, c, dd);
+  joint_scd(kind, pre, sn, c, dd, pre.qoff);
   const T qd = pre.qd;
   const T tau = pre.tau;
   if (!(IO::kKinds & kHasPris) || kind != K_PRIS) {
@@ -786,9 +916,13 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
     for (int k = 0; k < 5; ++k) st.st(bd.row0 + k, tU[k]);
     st.st(bd.row0 + 5, tu);
     if (bd.flags & F_ROOT_CHILD) return;
-    T R[9], r[3];
-    frame_1dof(bd, sn, c, T(0), R, r);
-    art_to_parent<T, true>(R, r, b, carry);
+    if (pre.zflags & F_ZPERP) art_to_parent_z<T, 1>(sn, c, bd.pt, b, carry);
+    else if (pre.zflags & F_ZPAR) art_to_parent_z<T, 0>(sn, c, bd.pt, b, carry);
+    else {
+      T R[9], r[3];
+      frame_1dof(bd, sn, c, T(0), R, r);
+      art_to_parent<T, true>(R, r, b, carry);
+    }
     hand_over(M, bd, st, carry);
   } else {
     // ---- prismatic along e_z: S = e_{lin z} ----
@@ -994,16 +1128,24 @@ RBD_HD void aba_pass3_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
     return;
   }
   T sn, c, dd;
-  joint_scd(kind, pre, sn, c, dd);
+  joint_scd(kind, pre, sn, c, dd, pre.qoff);
   const T qd = pre.qd;
   T tt[6];
   st.template ldv<6>(bd.row0, tt);
   const T t0 = tt[0], t1 = tt[1], t2 = tt[2], t3 = tt[3], t4 = tt[4], tu = tt[5];
   Mot<T> a;
   if (!(IO::kKinds & kHasPris) || kind != K_PRIS) {
-    frame_1dof(bd, sn, c, T(0), R, r);
-    motion_to_child(R, r, vp, v);
-    motion_to_child(R, r, ap, xa);
+    if (pre.zflags & F_ZPERP) {
+      motion_to_child_z<T, 1>(sn, c, bd.pt, vp, v);
+      motion_to_child_z<T, 1>(sn, c, bd.pt, ap, xa);
+    } else if (pre.zflags & F_ZPAR) {
+      motion_to_child_z<T, 0>(sn, c, bd.pt, vp, v);
+      motion_to_child_z<T, 0>(sn, c, bd.pt, ap, xa);
+    } else {
+      frame_1dof(bd, sn, c, T(0), R, r);
+      motion_to_child(R, r, vp, v);
+      motion_to_child(R, r, ap, xa);
+    }
     v.w[2] += qd;
     // v̇ = u~ - U~ . (X a_parent), U~ = (t0, t1, 1 | t2, t3, t4)
     const T vd = tu - (t0 * xa.w[0] + t1 * xa.w[1] + xa.w[2] + t2 * xa.l[0] + t3 * xa.l[1] + t4 * xa.l[2]);
@@ -1198,13 +1340,20 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
   Pre<T> cur, nxt, curB, nxtB;
   prefetch_body<T, 1>(M, 0, io, cur);
   prefetch_body<T, 1>(M, PAIRS ? M.body[0].pair : -1, io, curB);
-  for (int i = 0; i < nb;) {
+  int i1 = 0;
+  if (!PAIRS) {     // body 0 may be multi-DoF in any model; peeled so the loop of a non-GENERAL model carries 1-DoF code only
+    prefetch_body<T, 1>(M, 1, io, nxt);
+    aba_pass1_body<T, ST, true>(M, 0, io, st, vcur, cur);
+    cur = nxt;
+    i1 = 1;
+  }
+  for (int i = i1; i < nb;) {
     const int j = PAIRS ? M.body[i].pair : -1;
     const int in = PAIRS ? M.body[i].next_fwd : i + 1;
     prefetch_body<T, 1>(M, in, io, nxt);
     if (PAIRS) prefetch_body<T, 1>(M, in < nb ? M.body[in].pair : -1, io, nxtB);
     if (PAIRS && j >= 0) aba_pass1_pair(M, i, j, io, st, vcur, vB, cur, curB);
-    else aba_pass1_body<T, ST, GENERAL>(M, i, io, st, vcur, cur);
+    else aba_pass1_body<T, ST, GENERAL || PAIRS>(M, i, io, st, vcur, cur);
     cur = nxt; curB = nxtB;
     i = in;
   }

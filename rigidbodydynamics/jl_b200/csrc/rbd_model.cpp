@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace rbd {
@@ -82,6 +83,7 @@ template <class T> void fill_dev(const HostModel& hm, const ModelDev<double>& sr
     for (int k = 0; k < 3; ++k) { d.pt[k] = (T)s.pt[k]; d.h[k] = (T)s.h[k]; }
     for (int k = 0; k < 6; ++k) d.J[k] = (T)s.J[k];
     d.m = (T)s.m;
+    d.qoff = (T)s.qoff;
     d.kind = s.kind; d.parent = s.parent; d.qrow = s.qrow; d.vrow = s.vrow; d.row0 = s.row0;
     d.oslot = s.oslot; d.pslot = s.pslot; d.flags = s.flags; d.refidx = s.refidx;
     d.pair = s.pair; d.next_fwd = s.next_fwd; d.next_rev = s.next_rev;
@@ -199,6 +201,35 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
       }
     }
   }
+  // A 1-DoF body's canonical frame is only fixed up to a rotation about its own axis.  Spend that freedom on the body's
+  // FIRST child (the one that follows it in preorder, i.e. the continuation of the chain): when the child is revolute and
+  // its axis is perpendicular to this body's axis, turn this frame so that the child's axis is its +x.  The child's tree
+  // rotation then is  P Rz(gamma)  (see F_ZPERP), which the ABA passes exploit.  RBD_ZFAST=0 disables, 1 = perpendicular only.
+  const int zfast = getenv("RBD_ZFAST") ? atoi(getenv("RBD_ZFAST")) : 2;
+  if (zfast > 0) {
+    for (int p = 0; p < nb; ++p) {
+      const int kp = desc->jtype[p];
+      if (!(kp == K_REV || kp == K_PRIS || kp == K_SINCOS) || children[p].empty()) continue;
+      const int c = children[p].front();
+      if (desc->jtype[c] != K_REV) continue;
+      Mat3 Rt{}; std::memcpy(Rt.m, desc->X_tree + 12 * c, sizeof(Rt.m));
+      double ax[3] = {desc->jparam[9 * c], desc->jparam[9 * c + 1], desc->jparam[9 * c + 2]};
+      const double na = norm3(ax);
+      if (na < 1e-12) continue;
+      for (double& v : ax) v /= na;
+      double ac[3];
+      mulv(Rt, ax, ac);                                   // child's axis in this body's original frame
+      const double z[3] = {A[p].m[2], A[p].m[5], A[p].m[8]};
+      const double d = ac[0] * z[0] + ac[1] * z[1] + ac[2] * z[2];
+      if (std::fabs(d) > 1e-12) continue;                 // not perpendicular
+      double x[3] = {ac[0] - d * z[0], ac[1] - d * z[1], ac[2] - d * z[2]};
+      const double nx = norm3(x);
+      for (double& v : x) v /= nx;
+      double y[3];
+      cross(z, x, y);
+      for (int i = 0; i < 3; ++i) { A[p].m[3 * i + 0] = x[i]; A[p].m[3 * i + 1] = y[i]; }
+    }
+  }
   out.order.clear();
   out.pos.assign(nb, -1);
   {
@@ -260,6 +291,19 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
     else {
       if (par == p - 1) flags |= F_FIRST_CHILD;
       else if (children[par_ref].back() == j) flags |= F_SLOT_INIT;
+    }
+    // fast classes of revolute joints (F_ZPAR / F_ZPERP): the canonical tree rotation Rc's third column is the child's axis
+    b.qoff = 0.0;
+    if (b.kind == K_REV && zfast > 0) {
+      const double cx = Rc.m[2], cy = Rc.m[5], cz = Rc.m[8];
+      const double tol = 1e-12;
+      if (std::fabs(cx - 1) < tol && std::fabs(cy) < tol && std::fabs(cz) < tol) {
+        flags |= F_ZPERP;                                 // Rc = P Rz(gamma):  P^T Rc = Rz(gamma), (P^T w) = (w_y, w_z, w_x)
+        b.qoff = std::atan2(Rc.m[6], Rc.m[3]);
+      } else if (zfast > 1 && std::fabs(cz - 1) < tol && std::fabs(cx) < tol && std::fabs(cy) < tol) {
+        flags |= F_ZPAR;                                  // Rc = Rz(gamma)
+        b.qoff = std::atan2(Rc.m[3], Rc.m[0]);
+      }
     }
     b.flags = flags;
     // Pending slot of a branch node: live over the preorder interval [p, position of its last child] in BOTH directions

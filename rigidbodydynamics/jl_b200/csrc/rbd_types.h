@@ -26,6 +26,11 @@ enum BodyFlags : int32_t {
   F_HAS_PENDING = 4,   // has >= 2 children: owns a pending slot (inward accumulation / outward (v, a) save)
   F_LEAF = 8,          // no children
   F_ROOT_CHILD = 16,   // parent is the world: nothing is propagated inward
+  // Revolute bodies whose constant tree rotation is a pure z-rotation (joint axis parallel to the parent's) or the cyclic
+  // permutation P (P v = (v_z, v_x, v_y): joint axis along the parent frame's +x) times a z-rotation: the whole joint
+  // transform is then  E(q) = [P] Rz(q + qoff)  and the spatial transforms of the ABA passes use sparse z-rotations.
+  F_ZPAR = 32,
+  F_ZPERP = 64,
 };
 
 // Shared-memory "stash" rows per sample.  One row = one scalar per sample (lane); rows are private to a thread.
@@ -40,6 +45,7 @@ template <class T> struct BodyDev {
   T m;                // body inertia in the (canonicalised) body frame: mass,
   T h[3];             //   cross_part = m * com,
   T J[6];             //   moment about the frame origin: xx xy xz yy yz zz
+  T qoff;             // F_ZPAR / F_ZPERP bodies: constant z-rotation folded into the joint angle; 0 otherwise
   int32_t kind;       // Kind
   int32_t parent;     // preorder index of the parent body, -1 = world
   int32_t qrow, vrow; // first row of this joint in q / v (reference order!)

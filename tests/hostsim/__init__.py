@@ -134,3 +134,12 @@ def kinematics(desc, q, v=None, sign=None, want=KIN_ROWS):
     rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(v), _p(sg), ptrs)
     assert rc == 0, rc
     return {k: a for k, a in out.items() if a is not None}
+
+
+def flags(desc):
+    """Per-body flag words (csrc/rbd_types.h BodyFlags) in preorder."""
+    d, keep = make_desc(desc)
+    out = (ctypes.c_int * desc.nb)()
+    rc = lib().hostsim_flags(ctypes.byref(d), out)
+    assert rc == 0, rc
+    return list(out)

@@ -177,6 +177,7 @@ int hostsim_dynamics_dual(const rbd_model_desc* d, int64_t B, const double* q, c
     for (int k = 0; k < 3; ++k) { b.pt[k] = Dual64(s.pt[k]); b.h[k] = Dual64(s.h[k]); }
     for (int k = 0; k < 6; ++k) b.J[k] = Dual64(s.J[k]);
     b.m = Dual64(s.m);
+    b.qoff = Dual64(s.qoff);
     b.kind = s.kind; b.parent = s.parent; b.qrow = s.qrow; b.vrow = s.vrow; b.row0 = s.row0;
     b.oslot = s.oslot; b.pslot = s.pslot; b.flags = s.flags; b.refidx = s.refidx;
     b.pair = s.pair; b.next_fwd = s.next_fwd; b.next_rev = s.next_rev;
@@ -223,6 +224,13 @@ int hostsim_kinematics(const rbd_model_desc* d, int dtype, int64_t B, const void
   if (rc) return rc;
   if (dtype == 0) run_kin<float>(hm, B, (const float*)q, (const float*)v, sign, (float* const*)outs);
   else run_kin<double>(hm, B, (const double*)q, (const double*)v, sign, (double* const*)outs);
+  return 0;
+}
+int hostsim_flags(const rbd_model_desc* d, int* flags /* [nb], preorder */) {
+  HostModel hm; std::string err;
+  int rc = build_host_model(d, hm, err);
+  if (rc) return rc;
+  for (int p = 0; p < hm.nb; ++p) flags[p] = hm.dev64.body[p].flags;
   return 0;
 }
 }

@@ -245,7 +245,9 @@ def test_dual_number_dynamics_gpu(built, name, floating, B):
     st2 = _state(mech, q, v, torch.float64)
     res = rbd.DynamicsResult(mech, B, torch.float64)
     rbd.dynamics_(res, st2, _cu(tau, torch.float64), want_qd=False)
-    assert torch.equal(res.vd, out[..., 0])
+    # the value part is the plain fp64 kernel's result up to the different FMA contraction of Dual arithmetic
+    scale = float(res.vd.abs().max())
+    assert float((res.vd - out[..., 0]).abs().max()) < 1e-11 * scale
 
 
 def test_edge_cases_empty_padded_and_defaults(built):
