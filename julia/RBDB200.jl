@@ -179,4 +179,72 @@ function RigidBodyDynamics.mass_matrix!(M::AbstractMatrix{T}, state::BatchedStat
     M
 end
 
+
+# ---- SURVEY 8(f) rank 1 / rank 2: the callers and by-products either side of the path -----------------------------------
+
+"`simulate(state, final_time; Δt)` with passive / constant-torque control (src/simulate.jl:36-55), whole batch on the GPU."
+function RigidBodyDynamics.simulate(state::BatchedState{T}, final_time, torques = nothing; Δt = 1e-4) where {T <: Union{Float32, Float64}}
+    checkstate(state)
+    B = size(state.q, 1)
+    nsteps = 0; t = 0.0
+    while t < final_time; t += Δt; nsteps += 1; end            # the reference's `while t < final_time` (ode_integrators.jl:311)
+    GC.@preserve state torques begin
+        check(ccall((:rbd_integrate, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Int32, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v),
+                    torques === nothing ? C_NULL : devptr(torques), Float64(Δt), Int32(nsteps), stream_ptr()))
+    end
+    nsteps
+end
+
+"Mirror of `rbd_kinematics_out` (include/rbd_b200.h): eight device pointers, C_NULL = not requested."
+struct rbd_kinematics_out
+    transforms_to_root::Ptr{Cvoid}
+    center_of_mass::Ptr{Cvoid}
+    kinetic_energy::Ptr{Cvoid}
+    gravitational_potential_energy::Ptr{Cvoid}
+    momentum::Ptr{Cvoid}
+    momentum_rate_bias::Ptr{Cvoid}
+    momentum_matrix::Ptr{Cvoid}
+    geometric_jacobian::Ptr{Cvoid}
+end
+
+"+1 / -1 / 0 per tree joint for a `TreePath` (src/graphs/tree_path.jl): down / up (column negated, mechanism_algorithms.jl:95) / absent."
+function path_signs(model::Model, p::RigidBodyDynamics.TreePath)
+    sign = zeros(Int8, model.nb)
+    index = Dict(j => i for (i, j) in enumerate(tree_joints(model.mechanism)))
+    for (joint, dir) in zip(p.edges, RigidBodyDynamics.Graphs.directions(p))
+        sign[index[joint]] = dir == RigidBodyDynamics.Graphs.PathDirections.up ? Int8(-1) : Int8(1)
+    end
+    sign
+end
+
+"""
+One launch of `rbd_kinematics`; every keyword is an optional B x rows output matrix (root frame, [angular; linear]):
+`transforms_to_root` (12 nb), `center_of_mass` (3), `kinetic_energy` (1), `gravitational_potential_energy` (1), `momentum` (6),
+`momentum_rate_bias` (6), `momentum_matrix` (6 nv), `geometric_jacobian` (6 nv, needs `path`).  The reference's single-output
+names (`center_of_mass(state)`, `momentum_matrix!(A, state)`, `geometric_jacobian!(J, state, path)` ...) are one-line methods
+over this.  src/mechanism_algorithms.jl:30-49, 80-100, 313-327; src/mechanism_state.jl:878-903, 975-1000.
+"""
+function kinematics!(state::BatchedState{T}; path = nothing, outs...) where {T <: Union{Float32, Float64}}
+    checkstate(state)
+    B = size(state.q, 1)
+    ptr(name) = haskey(outs, name) ? devptr(outs[name]) : C_NULL
+    ko = rbd_kinematics_out(ptr(:transforms_to_root), ptr(:center_of_mass), ptr(:kinetic_energy),
+                            ptr(:gravitational_potential_energy), ptr(:momentum), ptr(:momentum_rate_bias),
+                            ptr(:momentum_matrix), ptr(:geometric_jacobian))
+    sign = path === nothing ? nothing : path_signs(state.model, path)
+    GC.@preserve state outs sign begin
+        check(ccall((:rbd_kinematics, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int8}, Ref{rbd_kinematics_out}, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v),
+                    sign === nothing ? C_NULL : pointer(sign), ko, stream_ptr()))
+    end
+    outs
+end
+
+RigidBodyDynamics.momentum_matrix!(A::AbstractMatrix, state::BatchedState) = (kinematics!(state; momentum_matrix = A); A)
+RigidBodyDynamics.geometric_jacobian!(J::AbstractMatrix, state::BatchedState, p::RigidBodyDynamics.TreePath) =
+    (kinematics!(state; path = p, geometric_jacobian = J); J)
+
 end # module

@@ -103,8 +103,11 @@ __device__ __forceinline__ void prefetch_rows(const T* base, int rows, int64_t l
 template <class T> struct AbaArgs {
   const T* q; const T* v; const T* tau; const T* wext;
   T* vd; T* qd;
-  T* scratch;            // [6 * nb][gridDim.x * NT] body-frame external wrenches (EXT only)
+  T* scratch;            // [6 * nb][scratch_ld] body-frame external wrenches (EXT only), one column per resident thread
   int64_t ld, B;
+  unsigned long long* counter;   // work queue shared by the two kernels of launch_duo
+  int64_t scratch_ld;            // columns of `scratch` (queue kernels)
+  int64_t scratch_off;           // first scratch column of the Tensor-Memory kernel's threads (after the shared-memory kernel's)
 };
 
 // KINDS: compile-time promise about the 1-DoF kinds present (kAllKinds, or 0 = revolute / sin-cos-revolute only).
@@ -149,11 +152,11 @@ __device__ __forceinline__ int64_t claim_group(unsigned long long* counter) {
   if ((threadIdx.x & 31) == 0) g = atomicAdd(counter, 1ull);
   return (int64_t)__shfl_sync(0xffffffffu, g, 0);
 }
-template <class T, class ST, int KINDS>
-__device__ __forceinline__ void aba_queue_loop(const ModelDev<T>& M, const AbaArgs<T>& a, const ST& st) {
+template <class T, class ST, int KINDS, bool EXT>
+__device__ __forceinline__ void aba_queue_loop(const ModelDev<T>& M, const AbaArgs<T>& a, const ST& st, int64_t tid) {
   constexpr int NT = 32;
   const int lane = threadIdx.x & 31;
-  unsigned long long* counter = reinterpret_cast<unsigned long long*>(a.scratch);
+  unsigned long long* counter = a.counter;
   const int64_t ngroups = (a.B + NT - 1) / NT;
   int64_t g = claim_group(counter);
   while (g < ngroups) {
@@ -163,39 +166,43 @@ __device__ __forceinline__ void aba_queue_loop(const ModelDev<T>& M, const AbaAr
       prefetch_rows(a.q, M.nq, a.ld, bn);
       prefetch_rows(a.v, M.nv, a.ld, bn);
       prefetch_rows(a.tau, M.nv, a.ld, bn);
+      if (EXT) prefetch_rows(a.wext, 6 * M.nb, a.ld, bn);
     }
     const int64_t b = g * NT + lane;
     const bool active = b < a.B;
     const int64_t bl = active ? b : a.B - 1;
-    AbaIO<T, false, KINDS> io;
+    AbaIO<T, EXT, KINDS> io;
     io.q = {a.q + bl, a.ld};
     io.v = {a.v + bl, a.ld};
     io.tau = {a.tau ? a.tau + bl : nullptr, a.ld};
-    io.wext = {nullptr, a.ld};
+    io.wext = {EXT ? a.wext + bl : nullptr, a.ld};
     io.vd = {a.vd + bl, a.ld, active};
     io.qd = {a.qd ? a.qd + bl : nullptr, a.ld, active};
-    io.ext = {nullptr, 0};
+    io.ext = {EXT ? a.scratch + tid : nullptr, a.scratch_ld};
+    if (EXT) ext_wrench_pass(M, io.q, io.wext, io.ext, st, M.slot_base, kSlotRowsAba);
     aba_sample<T, ST, false>(M, io, st);
     g = gn;
   }
 }
-template <class T, int KINDS>
+template <class T, int KINDS, bool EXT>
 __global__ void __launch_bounds__(32, sizeof(T) == 4 ? 16 : 1) aba_kernel_smem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  aba_queue_loop<T, Stash<T, 32>, KINDS>(M, a, Stash<T, 32>{reinterpret_cast<T*>(smem_raw) + threadIdx.x});
+  aba_queue_loop<T, Stash<T, 32>, KINDS, EXT>(M, a, Stash<T, 32>{reinterpret_cast<T*>(smem_raw) + threadIdx.x},
+                                              (int64_t)blockIdx.x * 32 + threadIdx.x);
 }
 // CTA of NW = 4 or 8 warps over COLS TMEM columns.  Warp w may only touch TMEM lane quadrant w % 4, so warps 0-3 keep their
 // stash in the first COLS / (NW / 4) columns and warps 4-7 (same lanes) in the second half: in fp32 (one column per row,
 // <= 256 rows) one CTA fills all 512 columns with the working sets of 8 warps; fp64 needs two columns per row, 4 warps.
 // Register budget: the CTA shares the SM with the 8 single-warp blocks of aba_kernel_smem_q, 16 warps x 32 x 128 = 64 K.
-template <class T, int COLS, int KINDS, int NW>
+template <class T, int COLS, int KINDS, int NW, bool EXT>
 __global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1)
 aba_kernel_tmem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   __shared__ uint32_t tm_slot;
   const uint32_t tm_base = tmem_alloc_cta<COLS>(&tm_slot);
   using ST = typename StashTMFor<T>::type;
   const uint32_t w = threadIdx.x >> 5;
-  aba_queue_loop<T, ST, KINDS>(M, a, ST{tm_base + (((w & 3u) * 32u) << 16) + (w >> 2) * (uint32_t)(COLS / (NW / 4))});
+  aba_queue_loop<T, ST, KINDS, EXT>(M, a, ST{tm_base + (((w & 3u) * 32u) << 16) + (w >> 2) * (uint32_t)(COLS / (NW / 4))},
+                                    a.scratch_off + (int64_t)blockIdx.x * (32 * NW) + threadIdx.x);
   tmem_free_cta<COLS>(tm_base);
 }
 
@@ -266,6 +273,8 @@ template <class T> struct RneaArgs {
   T* tau;
   T* scratch;
   int64_t ld, B;
+  unsigned long long* counter;
+  int64_t scratch_ld, scratch_off;
 };
 
 template <class T, int NT, bool EXT>
@@ -293,8 +302,58 @@ __global__ void __launch_bounds__(NT) rnea_kernel(const __grid_constant__ ModelD
     io.wext = {EXT ? a.wext + bl : nullptr, a.ld};
     io.tau = {a.tau + bl, a.ld, active};
     io.ext = {EXT ? a.scratch + (int64_t)blockIdx.x * NT + threadIdx.x : nullptr, (int64_t)gridDim.x * NT};
-    rnea_sample<T, NT>(M, io, st);
+    rnea_sample<T>(M, io, st);
   }
+}
+
+// Work-queue variants of the RNEA kernel (no external wrenches): shared-memory blocks + one Tensor-Memory CTA per SM.
+template <class T, class ST, bool EXT>
+__device__ __forceinline__ void rnea_queue_loop(const ModelDev<T>& M, const RneaArgs<T>& a, const ST& st, int64_t tid) {
+  constexpr int NT = 32;
+  const int lane = threadIdx.x & 31;
+  unsigned long long* counter = a.counter;
+  const int64_t ngroups = (a.B + NT - 1) / NT;
+  int64_t g = claim_group(counter);
+  while (g < ngroups) {
+    const int64_t gn = claim_group(counter);
+    if (gn < ngroups) {
+      const int64_t bn = gn * NT;
+      prefetch_rows(a.q, M.nq, a.ld, bn);
+      prefetch_rows(a.v, M.nv, a.ld, bn);
+      prefetch_rows(a.vd, M.nv, a.ld, bn);
+      if (EXT) prefetch_rows(a.wext, 6 * M.nb, a.ld, bn);
+    }
+    const int64_t b = g * NT + lane;
+    const bool active = b < a.B;
+    const int64_t bl = active ? b : a.B - 1;
+    RneaIO<T> io;
+    io.q = {a.q + bl, a.ld};
+    io.v = {a.v + bl, a.ld};
+    io.vd = {a.vd ? a.vd + bl : nullptr, a.ld};
+    io.wext = {EXT ? a.wext + bl : nullptr, a.ld};
+    io.tau = {a.tau + bl, a.ld, active};
+    io.ext = {EXT ? a.scratch + tid : nullptr, a.scratch_ld};
+    rnea_sample<T>(M, io, st);
+    g = gn;
+  }
+}
+template <class T, bool EXT>
+__global__ void __launch_bounds__(32, sizeof(T) == 4 ? 16 : 1) rnea_kernel_smem_q(const __grid_constant__ ModelDev<T> M,
+                                                                                   const RneaArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  rnea_queue_loop<T, Stash<T, 32>, EXT>(M, a, Stash<T, 32>{reinterpret_cast<T*>(smem_raw) + threadIdx.x},
+                                        (int64_t)blockIdx.x * 32 + threadIdx.x);
+}
+template <class T, int COLS, int NW, bool EXT>
+__global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1)
+rnea_kernel_tmem_q(const __grid_constant__ ModelDev<T> M, const RneaArgs<T> a) {
+  __shared__ uint32_t tm_slot;
+  const uint32_t tm_base = tmem_alloc_cta<COLS>(&tm_slot);
+  using ST = typename StashTMFor<T>::type;
+  const uint32_t w = threadIdx.x >> 5;
+  rnea_queue_loop<T, ST, EXT>(M, a, ST{tm_base + (((w & 3u) * 32u) << 16) + (w >> 2) * (uint32_t)(COLS / (NW / 4))},
+                              a.scratch_off + (int64_t)blockIdx.x * (32 * NW) + threadIdx.x);
+  tmem_free_cta<COLS>(tm_base);
 }
 
 template <class T> struct CrbaArgs {
@@ -401,6 +460,76 @@ template <class T> void set_scratch(CrbaArgs<T>&, T*) {}
 
 constexpr int kNT = 32;   // threads per block: one warp; warps never synchronise with each other
 
+// Shared-memory kernel on `stream` plus Tensor-Memory kernel (one CTA per SM, stash in TMEM, no shared memory) on the handle's
+// side stream, both claiming groups of 32 samples from one atomic counter.  fp32: one stash row = one TMEM column, so the 512
+// columns hold the stash of 8 warps (two column halves x four lane quadrants); fp64: two columns per row, 4 warps.  On Atlas
+// that is 8 + 8 resident warps/SM in fp32 (16 x 32 x 128 registers = the whole register file) and 4 + 4 in fp64.
+// `used` = false (and nothing launched) when the batch is too small to feed both kernels or RBD_NO_TMEM is set.
+template <class T, class KS, class KT, class Args>
+int launch_duo(const rbd_model* model, KS ks, KT kt, int tm_warps, const ModelDev<T>& M, Args a, int rows, int scratch_rows,
+               cudaStream_t stream, bool& used) {
+  used = false;
+  if (getenv("RBD_NO_TMEM")) return RBD_OK;
+  DeviceProps p;
+  if (int rc = get_props(p)) return rc;
+  const int64_t ngroups = (a.B + kNT - 1) / kNT;
+  const size_t smem = (size_t)rows * kNT * sizeof(T);
+  int bps = 0;
+  if (int rc = configure(ks, kNT, smem, p, bps)) return rc;
+  {
+    // leave room in the register file for the Tensor-Memory CTA: small models are not limited by shared memory and the
+    // persistent shared-memory blocks would otherwise keep that CTA off the SM until they drain the queue
+    cudaFuncAttributes fs{}, ft{};
+    CUDA_TRY(cudaFuncGetAttributes(&fs, ks));
+    CUDA_TRY(cudaFuncGetAttributes(&ft, kt));
+    const int rs = ((fs.numRegs + 7) / 8) * 8 * kNT, rt = ((ft.numRegs + 7) / 8) * 8 * 32 * tm_warps;
+    bps = std::max(1, std::min(bps, (65536 - rt) / rs));
+  }
+  if (getenv("RBD_SMEM_BLOCKS")) bps = std::max(1, std::min(bps, atoi(getenv("RBD_SMEM_BLOCKS"))));
+  if (ngroups < (int64_t)(bps + tm_warps / 2) * p.sms) return RBD_OK;     // not enough work to keep both kernels' warps busy
+  rbd_model* mm = const_cast<rbd_model*>(model);
+  cudaStream_t side = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(mm->side_mu);
+    if (!mm->side_stream) CUDA_TRY(cudaStreamCreateWithFlags(&mm->side_stream, cudaStreamNonBlocking));
+    side = mm->side_stream;
+    CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
+  cudaEvent_t fork = nullptr, join = nullptr;
+  CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+  void* counter = nullptr;
+  CUDA_TRY(cudaMallocAsync(&counter, 8, stream));
+  CUDA_TRY(cudaMemsetAsync(counter, 0, 8, stream));
+  a.counter = (unsigned long long*)counter;
+  void* scratch = nullptr;
+  if (scratch_rows > 0) {       // external wrenches in body frames: one column per resident thread of either kernel
+    a.scratch_off = (int64_t)bps * p.sms * kNT;
+    a.scratch_ld = a.scratch_off + (int64_t)p.sms * 32 * tm_warps;
+    CUDA_TRY(cudaMallocAsync(&scratch, (size_t)scratch_rows * a.scratch_ld * sizeof(T), stream));
+    a.scratch = (T*)scratch;
+  }
+  CUDA_TRY(cudaEventRecord(fork, stream));
+  CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
+  // (profiling aid: under ncu kernels are serialised and the first one drains the queue; RBD_ONLY=smem|tmem launches
+  //  just one of the two so each can be captured doing the whole batch)
+  const char* only = getenv("RBD_ONLY");
+  if (!only || only[0] == 's') ks<<<bps * p.sms, kNT, smem, stream>>>(M, a);
+  if (!only || only[0] == 't') kt<<<p.sms, 32 * tm_warps, 0, side>>>(M, a);
+  cudaError_t e = cudaGetLastError();
+  cudaEventRecord(join, side);
+  cudaStreamWaitEvent(stream, join, 0);
+  cudaFreeAsync(counter, stream);
+  if (scratch) cudaFreeAsync(scratch, stream);
+  cudaEventDestroy(fork);
+  cudaEventDestroy(join);
+  if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+  g_launch.kernels_launched += 2;
+  g_launch.grid = bps * p.sms; g_launch.block = kNT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
+  used = true;
+  return RBD_OK;
+}
+
 template <class T>
 int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, const void* v, const void* tau,
                const void* wext, void* vd, void* qd, cudaStream_t stream) {
@@ -411,59 +540,16 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   const int sr = wext ? 6 * hm.nb : 0;
   bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
   for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
-  {
-    // Default path for all-revolute trees whose stash fits Tensor Memory (<= 256 rows): the shared-memory kernel on `stream`
-    // plus the Tensor-Memory kernel (one CTA per SM, stash in TMEM, no shared memory) on the handle's side stream, both
-    // claiming groups from one atomic counter.  fp32: one row = one TMEM column, so the 512 columns hold the stash of 8 warps
-    // (two column halves x four lane quadrants); fp64: two columns per row, 4 warps.  On Atlas that is 8 + 8 resident
-    // warps/SM in fp32 (16 x 32 x 128 registers = the whole register file) and 4 + 4 in fp64.
-    const int64_t ngroups = (B + kNT - 1) / kNT;
-    if (!wext && !hm.general && !other_kinds && rows <= 256 && !getenv("RBD_NO_TMEM")) {
-      DeviceProps p;
-      if (int rc = get_props(p)) return rc;
-      auto ks = aba_kernel_smem_q<T, 0>;
-      constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;      // fp32: 2 x 256 columns, fp64: 1 x 512 columns
-      auto kt = aba_kernel_tmem_q<T, 512, 0, kTmWarps>;
-      const size_t smem = (size_t)rows * kNT * sizeof(T);
-      int bps = 0;
-      if (int rc = configure(ks, kNT, smem, p, bps)) return rc;
-      if (ngroups >= (int64_t)(bps + kTmWarps / 2) * p.sms) {   // enough work to keep both kernels' warps busy
-        rbd_model* mm = const_cast<rbd_model*>(model);
-        cudaStream_t side = nullptr;
-        {
-          std::lock_guard<std::mutex> lk(mm->side_mu);
-          if (!mm->side_stream) CUDA_TRY(cudaStreamCreateWithFlags(&mm->side_stream, cudaStreamNonBlocking));
-          side = mm->side_stream;
-          CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        }
-        cudaEvent_t fork = nullptr, join = nullptr;
-        CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-        void* counter = nullptr;
-        CUDA_TRY(cudaMallocAsync(&counter, 8, stream));
-        CUDA_TRY(cudaMemsetAsync(counter, 0, 8, stream));
-        AbaArgs<T> ah = a;
-        ah.scratch = (T*)counter;
-        CUDA_TRY(cudaEventRecord(fork, stream));
-        CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
-        // (profiling aid: under ncu kernels are serialised and the first one drains the queue; RBD_ONLY=smem|tmem launches
-        //  just one of the two so each can be captured doing the whole batch)
-        const char* only = getenv("RBD_ONLY");
-        if (getenv("RBD_SMEM_BLOCKS")) bps = std::min(bps, atoi(getenv("RBD_SMEM_BLOCKS")));
-        if (!only || only[0] == 's') ks<<<bps * p.sms, kNT, smem, stream>>>(M, ah);
-        if (!only || only[0] == 't') kt<<<p.sms, 32 * kTmWarps, 0, side>>>(M, ah);
-        cudaError_t e = cudaGetLastError();
-        cudaEventRecord(join, side);
-        cudaStreamWaitEvent(stream, join, 0);
-        cudaFreeAsync(counter, stream);
-        cudaEventDestroy(fork);
-        cudaEventDestroy(join);
-        if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
-        g_launch.kernels_launched += 2;
-        g_launch.grid = bps * p.sms; g_launch.block = kNT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
-        return RBD_OK;
-      }
-    }
+  if (!hm.general && !other_kinds && rows <= 256) {
+    // Default path for all-revolute trees whose stash fits Tensor Memory: see launch_duo
+    constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;
+    bool used = false;
+    const int rc = wext ? launch_duo<T>(model, aba_kernel_smem_q<T, 0, true>, aba_kernel_tmem_q<T, 512, 0, kTmWarps, true>,
+                                        kTmWarps, M, a, rows, sr, stream, used)
+                        : launch_duo<T>(model, aba_kernel_smem_q<T, 0, false>, aba_kernel_tmem_q<T, 512, 0, kTmWarps, false>,
+                                        kTmWarps, M, a, rows, 0, stream, used);
+    if (rc) return rc;
+    if (used) return RBD_OK;
   }
 #define RBD_ABA(G, E, K) launch<T>(aba_kernel<T, kNT, G, E, K>, M, a, kNT, rows, sr, stream)
   if (hm.general) return wext ? RBD_ABA(true, true, kAllKinds) : RBD_ABA(true, false, kAllKinds);
@@ -479,6 +565,16 @@ int inverse_dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void
   const ModelDev<T>& M = dev_model<T>(hm);
   RneaArgs<T> a{(const T*)q, (const T*)v, (const T*)vd, (const T*)wext, (T*)tau, nullptr, ld, B};
   const int rows = rnea_rows(hm);
+  if (rows <= 256) {
+    constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;
+    bool used = false;
+    const int rc = wext ? launch_duo<T>(model, rnea_kernel_smem_q<T, true>, rnea_kernel_tmem_q<T, 512, kTmWarps, true>, kTmWarps,
+                                        M, a, rows, 6 * hm.nb, stream, used)
+                        : launch_duo<T>(model, rnea_kernel_smem_q<T, false>, rnea_kernel_tmem_q<T, 512, kTmWarps, false>, kTmWarps,
+                                        M, a, rows, 0, stream, used);
+    if (rc) return rc;
+    if (used) return RBD_OK;
+  }
   return wext ? launch<T>(rnea_kernel<T, kNT, true>, M, a, kNT, rows, 6 * hm.nb, stream)
               : launch<T>(rnea_kernel<T, kNT, false>, M, a, kNT, rows, 0, stream);
 }

@@ -67,10 +67,13 @@ RBD_HD void ext_wrench_pass(const ModelDev<T>& M, const Col<T>& q, const Col<T>&
     else if (bd.flags & F_FIRST_CHILD) pp = cur;
     else {
       const int row = slot_base + bd.pslot * slot_rows;
+      T t[12];
+      st.fence_st();
+      st.template ldv<12>(row, t);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) pp.R[k] = st.ld(row + k);
+      for (int k = 0; k < 9; ++k) pp.R[k] = t[k];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) pp.p[k] = st.ld(row + 9 + k);
+      for (int k = 0; k < 3; ++k) pp.p[k] = t[9 + k];
     }
     T R[9], r[3], t[3];
     frame_any(bd, q, R, r);
@@ -105,8 +108,10 @@ template <class T> struct RneaIO {
   Scr<T> ext;
 };
 
-template <class T, int STRIDE>
-RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const Stash<T, STRIDE>& st) {
+// ST: Stash<T, STRIDE> (shared memory) or StashTM / StashTM64 (Tensor Memory, whose stores are asynchronous: fence_st()
+// stands wherever a thread re-reads a word it wrote; it is a no-op for shared memory)
+template <class T, class ST>
+RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const ST& st) {
   const int nb = M.nb;
   const int slot_base = nb * kRneaRowsPerBody;
   if (io.ext.valid()) ext_wrench_pass(M, io.q, io.wext, io.ext, st, slot_base, kSlotRowsRnea);
@@ -144,11 +149,11 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const Stash<T
       vp = vcur; ap = acur;
     } else {
       const int row = slot_base + bd.pslot * kSlotRowsRnea;
+      T t[12];
+      st.fence_st();
+      st.template ldv<12>(row, t);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        vp.w[k] = st.ld(row + k); vp.l[k] = st.ld(row + 3 + k);
-        ap.w[k] = st.ld(row + 6 + k); ap.l[k] = st.ld(row + 9 + k);
-      }
+      for (int k = 0; k < 3; ++k) { vp.w[k] = t[k]; vp.l[k] = t[3 + k]; ap.w[k] = t[6 + k]; ap.l[k] = t[9 + k]; }
     }
     T R[9], r[3];
     Mot<T> v, a;
@@ -210,6 +215,7 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const Stash<T
     vcur = v; acur = a;
   }
   // ---- pass 2 (inward): joint wrenches and torques ----
+  st.fence_st();
   T cn[3] = {T(0), T(0), T(0)}, cf[3] = {T(0), T(0), T(0)};   // contribution of the first child (registers)
   T q0c = T(0), q1c = T(0), dq = T(0), dv = T(0);
   fetch(nb - 1, false, q0n, q1n, dq, dv);
@@ -220,16 +226,23 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const Stash<T
     fetch(i - 1, false, q0n, q1n, dq, dv);
     const int row0 = i * kRneaRowsPerBody;
     T n[3], f[3];
+    {
+      T t[6];
+      st.template ldv<6>(row0, t);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { n[k] = st.ld(row0 + k); f[k] = st.ld(row0 + 3 + k); }
+      for (int k = 0; k < 3; ++k) { n[k] = t[k]; f[k] = t[3 + k]; }
+    }
     if (!(bd.flags & F_LEAF)) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) { n[k] += cn[k]; f[k] += cf[k]; }
     }
     if (bd.flags & F_HAS_PENDING) {
       const int row = slot_base + bd.oslot * kSlotRowsRnea;
+      T t[6];
+      st.fence_st();
+      st.template ldv<6>(row, t);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { n[k] += st.ld(row + k); f[k] += st.ld(row + 3 + k); }
+      for (int k = 0; k < 3; ++k) { n[k] += t[k]; f[k] += t[3 + k]; }
     }
     // tau_k = S_k . w  (one-hot subspaces)
     if (kind == K_REV || kind == K_SINCOS) io.tau.st(bd.vrow, n[2]);

@@ -51,7 +51,7 @@ void run_rnea(const HostModel& hm, int64_t B, const T* q, const T* v, const T* v
     io.wext = {wext ? wext + b : nullptr, B};
     io.tau = {tau + b, B, true};
     io.ext = {wext ? scratch.data() : nullptr, 1};
-    rnea_sample<T, 1>(M, io, Stash<T, 1>{stash.data()});
+    rnea_sample<T>(M, io, Stash<T, 1>{stash.data()});
   }
 }
 

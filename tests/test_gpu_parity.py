@@ -500,3 +500,42 @@ def test_kinematics_identities_at_scale_and_errors(built):
     assert rc == _cabi.RBD_EINVAL                                    # kinetic energy without v
     assert lib.rbd_kinematics(state.handle.ptr, 2, B, B, state.q.data_ptr(), None, None, ctypes.byref(ko), None) == _cabi.RBD_EUNSUPPORTED
     assert lib.rbd_kinematics(state.handle.ptr, 0, 0, 0, None, None, None, ctypes.byref(ko), None) == _cabi.RBD_OK
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_large_batch_rnea_and_extwrench_on_tensor_memory_path(built, dtype):
+    """inverse_dynamics! (with and without external wrenches) and dynamics! with external wrenches also run as the
+    shared-memory + Tensor-Memory kernel pair at batch 2^16; results must be bit-identical to the single-kernel path on the
+    same samples and match the oracle."""
+    mech = rbd.load_model("atlas", floating=True)
+    desc = mech.flatten()
+    B = 1 << 16
+    st = rbd.MechanismState(mech, B, dtype)
+    rbd.rand_(st, np.random.default_rng(22))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    vd = torch.rand((36, B), dtype=dtype, device="cuda", generator=g)
+    tau = torch.rand((36, B), dtype=dtype, device="cuda", generator=g)
+    wext = torch.rand((6 * desc.nb, B), dtype=dtype, device="cuda", generator=g)
+    idx = torch.arange(0, B, 733, device="cuda")
+    sub = rbd.MechanismState(mech, idx.numel(), dtype)
+    sub.q.copy_(st.q[:, idx]); sub.v.copy_(st.v[:, idx])
+    o = Oracle(desc)
+    qn, vn = sub.q.double().cpu().numpy(), sub.v.double().cpu().numpy()
+    vdn, taun, wn = (t[:, idx].double().cpu().numpy() for t in (vd, tau, wext))
+    for w in (None, wext):
+        out = torch.empty_like(vd)
+        rbd.inverse_dynamics_(out, st, vd, w)
+        assert rbd.launch_info().kernels_launched == 2
+        out2 = torch.empty((36, idx.numel()), dtype=dtype, device="cuda")
+        rbd.inverse_dynamics_(out2, sub, vd[:, idx].contiguous(), None if w is None else w[:, idx].contiguous())
+        assert rbd.launch_info().kernels_launched == 1
+        assert torch.equal(out2, out[:, idx])
+        ref = o.inverse_dynamics(qn, vn, vdn, None if w is None else wn)
+        assert rel_err(out2.double().cpu().numpy(), ref) < TOL[dtype]
+    res = rbd.DynamicsResult(mech, B, dtype)
+    rbd.dynamics_(res, st, tau, wext, want_qd=False)
+    assert rbd.launch_info().kernels_launched == 2
+    res2 = rbd.DynamicsResult(mech, idx.numel(), dtype)
+    rbd.dynamics_(res2, sub, tau[:, idx].contiguous(), wext[:, idx].contiguous(), want_qd=False)
+    assert torch.equal(res2.vd, res.vd[:, idx])
+    assert rel_err(res2.vd.double().cpu().numpy(), o.dynamics(qn, vn, taun, wn)) < TOL[dtype]
