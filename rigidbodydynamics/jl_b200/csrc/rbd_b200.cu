@@ -683,8 +683,12 @@ template <class T> struct StageArgs {
 // coordinates at (q_stage, v_stage); accumulators updated with the previous stage's v̇ and this stage's phid.
 template <class T>
 __global__ void __launch_bounds__(128) integrate_stage_kernel(const __grid_constant__ ModelDev<T> M, const StageArgs<T> a) {
+  // one thread per (sample, joint): every joint's coordinates map is independent of the others (blockIdx.y = body)
+  const BodyDev<T>& bd = M.body[blockIdx.y];
+  const int k0 = bd.vrow, k1 = bd.vrow + kind_nv_dev(bd.kind);
+  if (k1 == k0) return;                                    // fixed joint: no coordinates
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
-    for (int k = 0; k < M.nv; ++k) {
+    for (int k = k0; k < k1; ++k) {
       const int64_t e = (int64_t)k * a.B + b;
       const T vdp = a.first ? T(0) : a.vd[e];
       const T pdp = a.first ? T(0) : a.phid[e];
@@ -692,10 +696,11 @@ __global__ void __launch_bounds__(128) integrate_stage_kernel(const __grid_const
       a.vs[e] = a.v0[e] + a.wa * vdp;
       a.accv[e] = a.first ? T(0) : a.accv[e] + a.wb_prev * vdp;
     }
-    const Col<T> q0{a.q0 + b, a.B}, phi{a.phi + b, a.B}, vs{a.vs + b, a.B};
+    const Col<T> q0{a.q0 + b, a.B};
+    const ColRW<T> phi{a.phi + b, a.B}, vs{a.vs + b, a.B};           // written above by this thread
     const ColOut<T> qs{a.qs + b, a.B, true}, phid{a.phid + b, a.B, true};
-    for (int i = 0; i < M.nb; ++i) joint_stage(M.body[i], q0, phi, vs, qs, phid);
-    for (int k = 0; k < M.nv; ++k) {
+    joint_stage(bd, q0, phi, vs, qs, phid);
+    for (int k = k0; k < k1; ++k) {
       const int64_t e = (int64_t)k * a.B + b;
       a.accphi[e] = (a.first ? T(0) : a.accphi[e]) + a.wb * a.phid[e];
     }
@@ -710,17 +715,21 @@ template <class T> struct FinishArgs {
 // v = v0 + dt (accv + b_4 vd_4), q = global(q0, dt accphi)
 template <class T>
 __global__ void __launch_bounds__(128) integrate_finish_kernel(const __grid_constant__ ModelDev<T> M, const FinishArgs<T> a) {
+  const BodyDev<T>& bd = M.body[blockIdx.y];
+  const int k0 = bd.vrow, k1 = bd.vrow + kind_nv_dev(bd.kind);
+  if (k1 == k0) return;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
-    for (int k = 0; k < M.nv; ++k) {
+    for (int k = k0; k < k1; ++k) {
       const int64_t e = (int64_t)k * a.B + b;
       const T vn = a.v0[e] + a.dt * (a.accv[e] + a.wb_last * a.vd[e]);
       a.v[(int64_t)k * a.ld + b] = vn;
       a.scratch[e] = vn;
       a.phi[e] = a.dt * a.accphi[e];
     }
-    const Col<T> q0{a.q0 + b, a.B}, phi{a.phi + b, a.B}, vs{a.scratch + b, a.B};
+    const Col<T> q0{a.q0 + b, a.B};
+    const ColRW<T> phi{a.phi + b, a.B}, vs{a.scratch + b, a.B};      // written above by this thread
     const ColOut<T> q{a.q + b, a.ld, true}, dump{a.scratch + b, a.B, false};
-    for (int i = 0; i < M.nb; ++i) joint_stage(M.body[i], q0, phi, vs, q, dump);
+    joint_stage(bd, q0, phi, vs, q, dump);
   }
 }
 
@@ -750,7 +759,7 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
     CUDA_TRY(cudaMemcpy2DAsync(v0, B * sizeof(T), v, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
     for (int i = 0; i < 4 && rc == RBD_OK; ++i) {
       StageArgs<T> sa{q0, v0, phi, phid, vd, qs, vs, accphi, accv, (T)(dt * a[i]), (T)(i ? bw[i - 1] : 0.0), (T)bw[i], i == 0, B};
-      integrate_stage_kernel<T><<<grid, 128, 0, stream>>>(M, sa);
+      integrate_stage_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, sa);
       CUDA_TRY(cudaGetLastError());
       const int before = g_launch.kernels_launched;
       rc = dynamics_t<T>(model, B, B, qs, vs, tau_dense, nullptr, vd, nullptr, stream);
@@ -758,7 +767,7 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
     }
     if (rc != RBD_OK) break;
     FinishArgs<T> fa{q0, v0, vd, accphi, accv, phi, vs, (T*)q, (T*)v, (T)dt, (T)bw[3], B, ld};
-    integrate_finish_kernel<T><<<grid, 128, 0, stream>>>(M, fa);
+    integrate_finish_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, fa);
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   }

@@ -162,6 +162,14 @@ template <class T> struct Col {
   }
   RBD_HD bool valid() const { return p != nullptr; }
 };
+// Same view with plain (coherent) loads: for rows the SAME kernel has written earlier (ld.global.nc / __ldg must not be used
+// on data that is written during the kernel's lifetime).
+template <class T> struct ColRW {
+  const T* p;
+  int64_t ld;
+  RBD_HD T operator()(int row) const { return p[(int64_t)row * ld]; }
+  RBD_HD bool valid() const { return p != nullptr; }
+};
 template <class T> struct ColOut {
   T* p;
   int64_t ld;

@@ -70,8 +70,25 @@ RBD_HD void kin_sample(const ModelDev<T>& M, const KinDev<T>& K, const KinIO<T>&
   T hn[3] = {T(0), T(0), T(0)}, hf[3] = {T(0), T(0), T(0)}, bn[3] = {T(0), T(0), T(0)}, bf[3] = {T(0), T(0), T(0)};
 
   // ---- outward sweep: poses, twists, bias accelerations, sums ----
+  // software pipeline: the joint scalars of body i+1 are loaded while body i is processed (multi-DoF joints read theirs directly)
+  T q0n = T(0), q1n = T(0), qdn = T(0);
+  auto fetch = [&](int i, T& q0, T& q1, T& qd) {
+    q0 = q1 = qd = T(0);
+    if (i < nb) {
+      const BodyDev<T>& b = M.body[i];
+      if (b.kind == K_REV || b.kind == K_PRIS || b.kind == K_SINCOS) {
+        q0 = io.q(b.qrow);
+        if (b.kind == K_SINCOS) q1 = io.q(b.qrow + 1);
+        if (vel) qd = io.v(b.vrow);
+      }
+    }
+  };
+  fetch(0, q0n, q1n, qdn);
   for (int i = 0; i < nb; ++i) {
     const BodyDev<T>& bd = M.body[i];
+    const T q0c = q0n, q1c = q1n, qdc = qdn;
+    fetch(i + 1, q0n, q1n, qdn);
+    const bool one_dof = bd.kind == K_REV || bd.kind == K_PRIS || bd.kind == K_SINCOS;
     Pose<T> pp;
     Mot<T> twp, bp;
     if (bd.flags & F_ROOT_CHILD) {
@@ -92,7 +109,15 @@ RBD_HD void kin_sample(const ModelDev<T>& M, const KinDev<T>& K, const KinIO<T>&
       }
     }
     T R[9], r[3], t[3];
-    frame_any(bd, io.q, R, r);
+    if (one_dof || bd.kind == K_FIXED) {
+      Pre<T> pre;
+      pre.q0 = q0c; pre.q1 = q1c;
+      T sn, cs, d;
+      joint_scd(bd.kind, pre, sn, cs, d);
+      frame_1dof(bd, sn, cs, d, R, r);
+    } else {
+      frame_multi(bd, io.q, R, r);
+    }
     Pose<T> w;
     mat_mul3(pp.R, R, w.R);
     mat_vec(pp.R, r, t);
@@ -128,7 +153,7 @@ RBD_HD void kin_sample(const ModelDev<T>& M, const KinDev<T>& K, const KinIO<T>&
           for (int c = 0; c < 3; ++c) { io.J.st(row + c, sg * S.w[c]); io.J.st(row + 3 + c, sg * S.l[c]); }
         }
         if (vel) {
-          const T x = io.v(bd.vrow + k);
+          const T x = one_dof ? qdc : io.v(bd.vrow + k);
 #pragma unroll
           for (int c = 0; c < 3; ++c) { jt.w[c] += x * S.w[c]; jt.l[c] += x * S.l[c]; }
         }

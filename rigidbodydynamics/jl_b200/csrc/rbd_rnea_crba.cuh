@@ -97,6 +97,7 @@ RBD_HD void ext_wrench_pass(const ModelDev<T>& M, const Col<T>& q, const Col<T>&
     }
     cur = w;
   }
+  st.fence_st();     // the slots are re-used by the passes that follow
 }
 
 // ==================================================================================================================
