@@ -403,8 +403,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": B * bpe, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                          "note": "algorithmic bytes/eval x evals/s per GPU; traffic = ncu dram bytes per launch "
-                                 "(profiles/r1_traffic.json). The fused kernel is instruction-issue bound (~31k thread-instr/sample, "
-                                 "~68 % of the chip's issue rate), not HBM-bound: DESIGN.md section 4.1"},
+                                 "(profiles/r1_traffic.json). The fused kernel is instruction-issue bound (~27.5k thread-instr/sample, "
+                                 "~70 % of the chip's issue rate), not HBM-bound: DESIGN.md section 4.1"},
         }
         if gather:
             out["with_nccl_gather"] = gather

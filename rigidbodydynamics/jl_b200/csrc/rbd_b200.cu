@@ -465,6 +465,13 @@ constexpr int kNT = 32;   // threads per block: one warp; warps never synchronis
 // columns hold the stash of 8 warps (two column halves x four lane quadrants); fp64: two columns per row, 4 warps.  On Atlas
 // that is 8 + 8 resident warps/SM in fp32 (16 x 32 x 128 registers = the whole register file) and 4 + 4 in fp64.
 // `used` = false (and nothing launched) when the batch is too small to feed both kernels or RBD_NO_TMEM is set.
+// Which entry points use the kernel pair by default (RBD_DUO_RNEA=0/1, RBD_DUO_EXT=0/1 override).
+constexpr bool kDuoRneaDefault = true, kDuoExtDefault = true;
+inline bool duo_enabled(const char* env, bool dflt) {
+  const char* e = getenv(env);
+  return e ? (e[0] != '0') : dflt;
+}
+
 template <class T, class KS, class KT, class Args>
 int launch_duo(const rbd_model* model, KS ks, KT kt, int tm_warps, const ModelDev<T>& M, Args a, int rows, int scratch_rows,
                cudaStream_t stream, bool& used) {
@@ -483,7 +490,11 @@ int launch_duo(const rbd_model* model, KS ks, KT kt, int tm_warps, const ModelDe
     CUDA_TRY(cudaFuncGetAttributes(&fs, ks));
     CUDA_TRY(cudaFuncGetAttributes(&ft, kt));
     const int rs = ((fs.numRegs + 7) / 8) * 8 * kNT, rt = ((ft.numRegs + 7) / 8) * 8 * 32 * tm_warps;
-    bps = std::max(1, std::min(bps, (65536 - rt) / rs));
+    const int with_pair = std::max(1, std::min(bps, (65536 - rt) / rs));
+    // The pair only pays when shared memory (not the register file) limits the single kernel's residency: small models
+    // already fill the SM with shared-memory blocks and are faster on the single-kernel path.
+    if ((with_pair + tm_warps) * 100 < bps * 115) return RBD_OK;
+    bps = with_pair;
   }
   if (getenv("RBD_SMEM_BLOCKS")) bps = std::max(1, std::min(bps, atoi(getenv("RBD_SMEM_BLOCKS"))));
   if (ngroups < (int64_t)(bps + tm_warps / 2) * p.sms) return RBD_OK;     // not enough work to keep both kernels' warps busy
@@ -540,7 +551,7 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   const int sr = wext ? 6 * hm.nb : 0;
   bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
   for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
-  if (!hm.general && !other_kinds && rows <= 256) {
+  if (!hm.general && !other_kinds && rows <= 256 && (!wext || duo_enabled("RBD_DUO_EXT", kDuoExtDefault))) {
     // Default path for all-revolute trees whose stash fits Tensor Memory: see launch_duo
     constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;
     bool used = false;
@@ -565,7 +576,7 @@ int inverse_dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void
   const ModelDev<T>& M = dev_model<T>(hm);
   RneaArgs<T> a{(const T*)q, (const T*)v, (const T*)vd, (const T*)wext, (T*)tau, nullptr, ld, B};
   const int rows = rnea_rows(hm);
-  if (rows <= 256) {
+  if (rows <= 256 && duo_enabled("RBD_DUO_RNEA", kDuoRneaDefault) && (!wext || duo_enabled("RBD_DUO_EXT", kDuoExtDefault))) {
     constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;
     bool used = false;
     const int rc = wext ? launch_duo<T>(model, rnea_kernel_smem_q<T, true>, rnea_kernel_tmem_q<T, 512, kTmWarps, true>, kTmWarps,
