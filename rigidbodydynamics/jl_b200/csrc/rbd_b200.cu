@@ -856,7 +856,9 @@ int host_pipeline(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const 
                   int nout, Launch launch_chunk) {
   std::lock_guard<std::mutex> lk(model->host_mu);
   const size_t es = dtype == RBD_F32 ? 4 : 8;
-  const int64_t C = std::min<int64_t>(kChunk, B);
+  int64_t chunk = kChunk;
+  if (const char* e = getenv("RBD_HOST_CHUNK")) chunk = std::max<int64_t>(1024, atoll(e));     // tuning knob
+  const int64_t C = std::min<int64_t>(chunk, B);
   size_t rows_total = 0;
   for (int i = 0; i < nin; ++i) rows_total += ins[i].in ? ins[i].rows : 0;
   for (int i = 0; i < nout; ++i) rows_total += outs[i].out ? outs[i].rows : 0;

@@ -603,7 +603,18 @@ RBD_HD void art_shift(const T* r, const T* Ar, const T* Br, const T* Cr, const T
 // Child -> parent hand-over for the fast classes.  The child's inertia `b` has a vanishing angular-z row / column (a
 // revolute-z DoF was just eliminated).  Congruence by Rz acts on the xy-plane only: a symmetric 2x2 block turns by the
 // double angle ( (xx-yy)/2, xy ), the (xz, yz) pairs turn by the single angle, zz stays; P is an index relabelling.
-template <class T, int PERM> RBD_HD void art_to_parent_z(T s, T c, const T* r, const Art<T>& b, Art<T>& o) {
+// Origin shift with r = 0: the rotated blocks are the result.
+template <class T>
+RBD_HD void art_noshift(const T* Ar, const T* Br, const T* Cr, const T* nr, const T* fr, Art<T>& o) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { o.A[k] = Ar[k]; o.C[k] = Cr[k]; }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) o.B[k] = Br[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { o.n[k] = nr[k]; o.f[k] = fr[k]; }
+}
+template <class T, int PERM, bool ZERO_R = false>
+RBD_HD void art_to_parent_z(T s, T c, const T* r, const Art<T>& b, Art<T>& o) {
   const T c2 = c * c - s * s, s2 = (s + s) * c;
   T Ya[6], Yb[9], Yc[6], yn[3], yf[3];
   {  // A: only xx, xy, yy are non-zero
@@ -647,9 +658,11 @@ template <class T, int PERM> RBD_HD void art_to_parent_z(T s, T c, const T* r, c
       for (int j = 0; j < 3; ++j) Br[3 * i + j] = Yb[3 * sg[i] + sg[j]];
       nr[i] = yn[sg[i]]; fr[i] = yf[sg[i]];
     }
-    art_shift(r, Ar, Br, Cr, nr, fr, o);
+    if (ZERO_R) art_noshift(Ar, Br, Cr, nr, fr, o);
+    else art_shift(r, Ar, Br, Cr, nr, fr, o);
   } else {
-    art_shift(r, Ya, Yb, Yc, yn, yf, o);
+    if (ZERO_R) art_noshift(Ya, Yb, Yc, yn, yf, o);
+    else art_shift(r, Ya, Yb, Yc, yn, yf, o);
   }
 }
 
@@ -764,7 +777,7 @@ RBD_HD void prefetch_body(const ModelDev<T>& M, int i, const IO& io, Pre<T>& p) 
   if (i < 0 || i >= M.nb) return;
   const BodyDev<T>& bd = M.body[i];
   const int kind = bd.kind;
-  p.zflags = bd.flags & (F_ZPAR | F_ZPERP);      // fast-class bits and angle offset, fetched a body ahead like the joint scalars
+  p.zflags = bd.flags & (F_ZPAR | F_ZPERP | F_ZERO_R);      // fast-class bits and angle offset, fetched a body ahead like the joint scalars
   p.qoff = bd.qoff;
   if (PASS == 2 && IO::kExt) {
 #pragma unroll
@@ -924,7 +937,10 @@ RBD_HD void aba_pass2_1dof(const ModelDev<T>& M, int i, const IO& io, const ST& 
     for (int k = 0; k < 5; ++k) st.st(bd.row0 + k, tU[k]);
     st.st(bd.row0 + 5, tu);
     if (bd.flags & F_ROOT_CHILD) return;
-    if (pre.zflags & F_ZPERP) art_to_parent_z<T, 1>(sn, c, bd.pt, b, carry);
+    if (pre.zflags & F_ZERO_R) {
+      if (pre.zflags & F_ZPERP) art_to_parent_z<T, 1, true>(sn, c, bd.pt, b, carry);
+      else art_to_parent_z<T, 0, true>(sn, c, bd.pt, b, carry);
+    } else if (pre.zflags & F_ZPERP) art_to_parent_z<T, 1>(sn, c, bd.pt, b, carry);
     else if (pre.zflags & F_ZPAR) art_to_parent_z<T, 0>(sn, c, bd.pt, b, carry);
     else {
       T R[9], r[3];

@@ -305,6 +305,9 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
         b.qoff = std::atan2(Rc.m[3], Rc.m[0]);
       }
     }
+    if ((flags & (F_ZPAR | F_ZPERP)) && pc[0] == 0.0 && pc[1] == 0.0 && pc[2] == 0.0 &&
+        !(getenv("RBD_ZERO_R") && getenv("RBD_ZERO_R")[0] == '0'))
+      flags |= F_ZERO_R;
     b.flags = flags;
     // Pending slot of a branch node: live over the preorder interval [p, position of its last child] in BOTH directions
     // (inward: written when the last child's subtree is done, read at p; outward: written at p, last read by the last

@@ -31,6 +31,7 @@ enum BodyFlags : int32_t {
   // transform is then  E(q) = [P] Rz(q + qoff)  and the spatial transforms of the ABA passes use sparse z-rotations.
   F_ZPAR = 32,
   F_ZPERP = 64,
+  F_ZERO_R = 128,      // fast-class body whose frame origin coincides with its parent's (pt == 0): no origin shift inward
 };
 
 // Shared-memory "stash" rows per sample.  One row = one scalar per sample (lane); rows are private to a thread.
