@@ -238,7 +238,7 @@ def run_reference(args):
     el = time.perf_counter() - t0
     val = args.steps * n / el
     sample = f"{n} Atlas states per step (bounded sample of the 2^20 batch), {np.dtype(dt).name}, {cores} threads"
-    print(json.dumps({
+    _emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
@@ -248,7 +248,29 @@ def run_reference(args):
     }))
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write banners to file descriptor 1 (NCCL prints its version there at
+    communicator creation).  Keep a private duplicate of the real stdout for the result and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -420,7 +442,7 @@ def main():
             got = result.vd[:, :n].double().cpu().numpy()
             scale = np.maximum(1.0, np.abs(ref).max(0))
             out["accuracy"] = {"max_rel_err_vs_fp64_oracle": float((np.abs(got - ref).max(0) / scale).max()), "samples": n}
-        print(json.dumps(out))
+        _emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
