@@ -37,7 +37,7 @@ def _check(t: Optional[torch.Tensor], rows: int, state: MechanismState, name: st
         raise TypeError(f"{name}: dtype/device must match the state ({state.dtype}, {state.q.device})")
     if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != state.batch:
         raise DimensionMismatch(f"{name} has wrong size: expected ({rows}, {state.batch}), got {tuple(t.shape)}")
-    if t.stride(1) != 1 or t.stride(0) != state.batch:
+    if not t.is_contiguous():          # (strides of size-1 dimensions are irrelevant, which is_contiguous knows)
         raise ValueError(f"{name} must be [rows, B] contiguous (batch index fastest)")
 
 
