@@ -198,7 +198,26 @@ def other_configs(steps):
               ("momentum_rate_bias", 6))}
     ms = time_fn(lambda: rbd.kinematics_(st, None, **small), steps)
     out["atlas_f32_com_energies_momentum_fused_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms, "algorithmic_GBps": B * (37 + 36 + 17) * 4 / (ms * 1e-3) / 1e9}
-    del res, wext, tau, vd, tout, st, A, small
+    Mfull = torch.empty((36 * 36, 1 << 18), dtype=torch.float32, device="cuda")          # 5.2 KB/sample out: batch 2^18
+    st18 = rbd.MechanismState(atlas, 1 << 18, torch.float32)
+    rbd.rand_(st18, rng)
+    ms = time_fn(lambda: rbd.mass_matrix_(Mfull, st18), steps)
+    out["atlas_f32_mass_matrix_b262144"] = {"evals_per_s": (1 << 18) / (ms * 1e-3), "ms": ms, "algorithmic_GBps": (1 << 18) * (37 + 1296) * 4 / (ms * 1e-3) / 1e9}
+    del res, wext, tau, vd, tout, st, A, small, Mfull, st18
+    # config 4: dynamics! on ForwardDiff.Dual{Tag,Float64,6} (value + 6 partials per scalar), batch 8192
+    Bd = 8192
+    std = rbd.MechanismState(atlas, 1, torch.float64)
+    qd_ = torch.zeros((37, Bd, 7), dtype=torch.float64, device="cuda")
+    stq = rbd.MechanismState(atlas, Bd, torch.float64)
+    rbd.rand_(stq, rng)
+    qd_[..., 0] = stq.q
+    qd_[4:, :, 1:] = torch.rand((33, Bd, 6), dtype=torch.float64, device="cuda")          # partials of the non-quaternion coordinates
+    vdual = torch.rand((36, Bd, 7), dtype=torch.float64, device="cuda")
+    tdual = torch.rand((36, Bd, 7), dtype=torch.float64, device="cuda")
+    odual = torch.empty((36, Bd, 7), dtype=torch.float64, device="cuda")
+    ms = time_fn(lambda: rbd.dynamics_dual_(odual, std, qd_, vdual, tdual), max(3, steps // 2))
+    out["atlas_dual64x6_dynamics_b8192"] = {"evals_per_s": Bd / (ms * 1e-3), "ms": ms, "algorithmic_GBps": Bd * 8120 / (ms * 1e-3) / 1e9}
+    del std, stq, qd_, vdual, tdual, odual
     iiwa = rbd.load_model("iiwa14")
     st = rbd.MechanismState(iiwa, B, torch.float32)
     rbd.rand_(st, rng)
