@@ -268,6 +268,33 @@ __global__ void __launch_bounds__(NT) aba_dual_kernel(const __grid_constant__ Mo
   }
 }
 
+// Same evaluation with the stash split between shared memory (value parts) and Tensor Memory (partial parts): one 4-warp CTA/SM.
+__global__ void __launch_bounds__(128) aba_dual_kernel_tm(const __grid_constant__ ModelDev<Dual64> M, const DualArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t tm_slot;
+  const uint32_t tm_base = tmem_alloc_cta<512>(&tm_slot);
+  const StashDualTM st{reinterpret_cast<double*>(smem_raw) + threadIdx.x, tm_base + ((uint32_t)((threadIdx.x >> 5) * 32) << 16)};
+  const int64_t total = a.B * 6;
+  const int64_t ngroups = (total + 127) / 128;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t t = g * 128 + threadIdx.x;
+    const bool active = t < total;
+    const int64_t tl = active ? t : total - 1;
+    const int64_t b = tl / 6;
+    const int dir = (int)(tl - b * 6);
+    AbaIO<Dual64, false> io;
+    io.q = {a.q + b * kDualWidth, a.ld, dir};
+    io.v = {a.v + b * kDualWidth, a.ld, dir};
+    io.tau = {a.tau ? a.tau + b * kDualWidth : nullptr, a.ld, dir};
+    io.wext = {nullptr, a.ld, dir};
+    io.vd = {a.vd + b * kDualWidth, a.ld, dir, active};
+    io.qd = {nullptr, a.ld, dir, active};
+    io.ext = {nullptr, 0};
+    aba_sample<Dual64, StashDualTM, false>(M, io, st);
+  }
+  tmem_free_cta<512>(tm_base);
+}
+
 template <class T> struct RneaArgs {
   const T* q; const T* v; const T* vd; const T* wext;
   T* tau;
@@ -666,6 +693,19 @@ int dynamics_dual(const rbd_model* model, int64_t B, int64_t ld, const void* q, 
   const DualArgs a{(const double*)q, (const double*)v, (const double*)tau, (double*)vd, ld, B};
   DeviceProps p;
   if (int rc = get_props(p)) return rc;
+  // split stash (shared memory + Tensor Memory): 4 warps/SM instead of 2 on Atlas
+  const size_t smem_tm = (size_t)S.nrows * 128 * sizeof(double);
+  if (!hm.general && S.nrows <= 256 && (int)smem_tm <= p.max_smem_optin && B * 6 >= (int64_t)p.sms * 128 && !getenv("RBD_NO_TMEM")) {
+    int bps_tm = 0;
+    if (int rc = configure(aba_dual_kernel_tm, 128, smem_tm, p, bps_tm)) return rc;
+    const int64_t ng = (B * 6 + 127) / 128;
+    const int grid_tm = (int)std::min<int64_t>(ng, p.sms);
+    aba_dual_kernel_tm<<<grid_tm, 128, smem_tm, stream>>>(*Mp, a);
+    CUDA_TRY(cudaGetLastError());
+    g_launch.kernels_launched += 1;
+    g_launch.grid = grid_tm; g_launch.block = 128; g_launch.smem_bytes = (int)smem_tm; g_launch.blocks_per_sm = 1;
+    return RBD_OK;
+  }
   const size_t smem = (size_t)S.nrows * kNT * sizeof(Dual64);
   int bps = 0;
   if (int rc = hm.general ? configure(aba_dual_kernel<kNT, true>, kNT, smem, p, bps)

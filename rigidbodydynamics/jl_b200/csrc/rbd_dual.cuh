@@ -41,6 +41,7 @@ RBD_HD void sincos_t(const Dual1<double>& x, Dual1<double>& s, Dual1<double>& c)
 }
 
 using Dual64 = Dual1<double>;
+#define RBD_DUAL_TYPES 1
 constexpr int kDualWidth = 7;   // doubles per Dual{Float64,6}
 
 // rows x batch views over arrays of 7-double duals; `p` is pre-offset to this thread's sample, `dir` selects the partial

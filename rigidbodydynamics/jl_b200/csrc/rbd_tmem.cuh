@@ -63,6 +63,37 @@ struct StashTM64 {
   __device__ __forceinline__ void add(int row, double v) const { fence_st(); st(row, ld(row) + v); }
   __device__ __forceinline__ const StashTM64& slots() const { return *this; }
 };
+// Dual{Float64,1} stash split over both on-chip memories: the VALUE part of a row in shared memory ([row][thread], 8 bytes), the
+// PARTIAL part in Tensor Memory (two 32-bit columns per row).  A 128-thread CTA then needs rows x 1 KB of shared memory and
+// 2 x rows TMEM columns -- Atlas: 213 KB + 426 columns = 4 resident warps/SM instead of the 2 that fit in shared memory alone.
+#if defined(RBD_DUAL_TYPES)
+struct StashDualTM {
+  double* pv;        // shared memory, already offset by the thread index; row stride kThreads
+  uint32_t base;     // TMEM address of row 0 for this warp
+  static constexpr int kThreads = 128;
+  __device__ __forceinline__ void fence_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+  template <int N> __device__ __forceinline__ void ldv(int row, Dual64* out) const {
+    uint32_t lo[N], hi[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo[k]), "=r"(hi[k]) : "r"(base + 2u * (uint32_t)(row + k)) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = Dual64(pv[(row + k) * kThreads], __hiloint2double((int)hi[k], (int)lo[k]));
+  }
+  __device__ __forceinline__ Dual64 ld(int row) const {
+    Dual64 v;
+    ldv<1>(row, &v);
+    return v;
+  }
+  __device__ __forceinline__ void st(int row, const Dual64& x) const {
+    pv[row * kThreads] = x.v;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(base + 2u * (uint32_t)row), "r"((uint32_t)__double2loint(x.d)), "r"((uint32_t)__double2hiint(x.d)) : "memory");
+  }
+  __device__ __forceinline__ void add(int row, const Dual64& x) const { fence_st(); st(row, ld(row) + x); }
+  __device__ __forceinline__ const StashDualTM& slots() const { return *this; }
+};
+#endif
 template <class T> struct StashTMFor;
 template <> struct StashTMFor<float> { using type = StashTM; static constexpr int kColsPerRow = 1; };
 template <> struct StashTMFor<double> { using type = StashTM64; static constexpr int kColsPerRow = 2; };
