@@ -11,7 +11,7 @@ import torch
 
 import rigidbodydynamics.jl_b200 as rbd
 from oracle import Oracle
-from tests.util import config_distance, make_duals, rand_inputs, randmech, rel_err
+from tests.util import axis_aligned_tree, config_distance, make_duals, rand_inputs, randmech, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = {torch.float64: 1e-9, torch.float32: 2e-5}
@@ -539,3 +539,22 @@ def test_large_batch_rnea_and_extwrench_on_tensor_memory_path(built, dtype):
     rbd.dynamics_(res2, sub, tau[:, idx].contiguous(), wext[:, idx].contiguous(), want_qd=False)
     assert torch.equal(res2.vd, res.vd[:, idx])
     assert rel_err(res2.vd.double().cpu().numpy(), o.dynamics(qn, vn, taun, wn)) < TOL[dtype]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_axis_aligned_trees_fast_classes_gpu(built, seed):
+    """Random trees with coordinate-axis joints and 90-degree tree rotations (fast joint classes mixed with general bodies,
+    prismatic / fixed / sin-cos joints, zero tree offsets), fp64 and fp32, with and without external wrenches."""
+    mech = axis_aligned_tree(seed)
+    desc = mech.flatten()
+    q, v, tau, vd, w = rand_inputs(mech, 161, seed, wext=True)
+    o = Oracle(desc)
+    ref, ref_w, ref_id = o.dynamics(q, v, tau), o.dynamics(q, v, tau, w), o.inverse_dynamics(q, v, vd, w)
+    for dtype in (torch.float64, torch.float32):
+        got, _ = gpu_dynamics(mech, q, v, tau, dtype)
+        assert rel_err(got, ref) < (1e-9 if dtype == torch.float64 else 5e-4)
+        got_w, _ = gpu_dynamics(mech, q, v, tau, dtype, wext=w)
+        assert rel_err(got_w, ref_w) < (1e-9 if dtype == torch.float64 else 5e-4)
+        st = _gpu_state(mech, q, v, dtype)
+        out = rbd.inverse_dynamics(st, torch.from_numpy(vd).to(dtype).cuda(), torch.from_numpy(w).to(dtype).cuda())
+        assert rel_err(out.double().cpu().numpy(), ref_id) < (1e-9 if dtype == torch.float64 else 2e-4)

@@ -6,7 +6,7 @@ import pytest
 import rigidbodydynamics.jl_b200 as rbd
 from oracle import Oracle
 from tests import hostsim
-from tests.util import config_distance, make_duals, rand_inputs, randmech, rel_err
+from tests.util import axis_aligned_tree, config_distance, make_duals, rand_inputs, randmech, rel_err
 
 MODELS = [("atlas", True), ("atlas", False), ("valkyrie", True), ("iiwa14", False), ("double_pendulum", False)]
 
@@ -170,3 +170,22 @@ def test_energy_conservation_passive_pendulum():
     q, v = np.array([[0.3], [0.4]]), np.array([[1.0], [2.0]])
     q1, v1 = hostsim.integrate(d, q, v, None, dt=1e-2, nsteps=10)
     assert abs(energy(q1, v1) - energy(q, v)) < 1e-3
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_axis_aligned_trees_take_the_fast_classes(seed):
+    mech = axis_aligned_tree(seed)
+    desc = mech.flatten()
+    flags = hostsim.flags(desc)
+    npar, nperp, nzr = (sum(1 for f in flags if f & b) for b in (32, 64, 128))
+    assert npar + nperp >= 5, (npar, nperp)                       # the fast classes really are exercised
+    q, v, tau, vd, w = rand_inputs(mech, 5, seed, wext=True)
+    o = Oracle(desc)
+    assert rel_err(hostsim.dynamics(desc, q, v, tau), o.dynamics(q, v, tau)) < 1e-9
+    assert rel_err(hostsim.dynamics(desc, q, v, tau, w), o.dynamics(q, v, tau, w)) < 1e-9
+    assert rel_err(hostsim.dynamics(desc, q.astype(np.float32), v.astype(np.float32), tau.astype(np.float32)),
+                   o.dynamics(q, v, tau)) < 5e-4
+    assert rel_err(hostsim.inverse_dynamics(desc, q, v, vd, w), o.inverse_dynamics(q, v, vd, w)) < 1e-10
+    kin = hostsim.kinematics(desc, q, v, None, want=("transforms", "A"))
+    ref = o.kinematics(q, v, None, want=("transforms", "A"))
+    assert rel_err(kin["transforms"], ref["transforms"]) < 1e-11 and rel_err(kin["A"], ref["A"]) < 1e-10

@@ -94,3 +94,35 @@ def config_distance(mech, qa, qb):
             d = max(d, np.abs(a - b).max())
         qs += j.nq
     return d
+
+
+def axis_aligned_tree(seed, n=24):
+    """Random tree whose joint axes are coordinate axes and whose tree rotations are multiples of 90 degrees (like real robots),
+    with every joint type present, some zero tree offsets, and a floating base: exercises the fast joint classes of
+    csrc/rbd_model.cpp (parallel / perpendicular axes, zero origin shift) next to the general path."""
+    rng = np.random.default_rng(seed)
+    eye = np.eye(3)
+
+    def rot90():
+        perm = rng.permutation(3)
+        R = eye[:, perm] * rng.choice([-1.0, 1.0], 3)
+        if np.linalg.det(R) < 0:
+            R[:, 0] = -R[:, 0]
+        return R
+
+    def axis():
+        return eye[int(rng.integers(3))] * rng.choice([-1.0, 1.0])
+
+    mech = rbd.Mechanism(rbd.RigidBody("world"))
+    base = rbd.RigidBody("base", rbd.SpatialInertia.rand(rng))
+    mech.attach(mech.root_body, base, rbd.Joint("floating", rbd.QuaternionFloating()))
+    kinds = [rbd.Revolute] * (n - 6) + [rbd.Prismatic, rbd.Fixed, rbd.SinCosRevolute, rbd.Revolute, rbd.Prismatic, rbd.Revolute]
+    for i, K in enumerate(kinds):
+        parent = mech.bodies[int(rng.integers(1, len(mech.bodies)))]
+        jt = K() if K is rbd.Fixed else K(axis())
+        trans = np.zeros(3) if rng.random() < 0.3 else rng.standard_normal(3) * (rng.random(3) < 0.6)
+        general = rng.random() < 0.15            # a few arbitrary rotations: general path
+        R = rbd.Transform3D.rand(rng).rot if general else rot90()
+        mech.attach(parent, rbd.RigidBody(f"b{i}", rbd.SpatialInertia.rand(rng)), rbd.Joint(f"j{i}", jt),
+                    joint_pose=rbd.Transform3D(R, trans))
+    return mech
