@@ -721,66 +721,72 @@ int dynamics_dual(const rbd_model* model, int64_t B, int64_t ld, const void* q, 
 }
 
 // ---- Munthe-Kaas RK4 (rbd_integrate): elementwise stage kernels around the dynamics kernels -----------------------------
+// Stage i of a step, one thread per (sample, joint) -- every joint's coordinate map is independent of the others (blockIdx.y =
+// body).  The local coordinates of the stage and the stage velocity are functions of the previous stage's rates,
+//   phi = dt a_i phid_{i-1} ,  v_s = v0 + dt a_i vd_{i-1} ,
+// evaluated on the fly by the two accessors below (nothing but the kernel's real outputs is written):
+//   q_s = global(q0, phi) ,  v_s  -> inputs of the dynamics kernels ;  phid_i = d/dt local(q0, q_s, v_s) -> kept for the next stage
+// and for the final combination.  The four (phid_i, vd_i) pairs are stored separately; the finishing kernel forms the weighted sums.
+template <class T> struct ScaledRow {      // wa * p[row]  (zero when there is no previous stage)
+  const T* p; int64_t ld; T wa;
+  RBD_HD T operator()(int row) const { return p ? wa * p[(int64_t)row * ld] : T(0); }
+};
+template <class T> struct OffsetRow {      // base[row] + wa * p[row]
+  const T* base; const T* p; int64_t ld; T wa;
+  RBD_HD T operator()(int row) const {
+    const T b = base[(int64_t)row * ld];
+    return p ? b + wa * p[(int64_t)row * ld] : b;
+  }
+};
 template <class T> struct StageArgs {
-  const T* q0; const T* v0;     // state at the start of the step
-  T* phi; T* phid; T* vd;       // local coordinates of the stage, their rate (in: previous stage, out: this stage), v̇ of the previous stage
-  T* qs; T* vs;                 // stage state handed to the dynamics kernel
-  T* accphi; T* accv;           // sum_i b_i phid_i, sum_i b_i vd_i
-  T wa, wb_prev, wb;            // dt * a_i ; b_{i-1} ; b_i
-  int first;                    // stage 0: no previous stage
+  const T* q0; const T* v0;               // state at the start of the step
+  const T* phid_prev; const T* vd_prev;   // rates of the previous stage (NULL for stage 0)
+  T* phid; T* qs; T* vs;                  // outputs
+  T wa;                                   // dt * a_i
   int64_t B;
 };
-// One thread per sample.  phi = wa * phid_prev, v_stage = v0 + wa * vd_prev, q_stage = global(q0, phi), phid = rate of the local
-// coordinates at (q_stage, v_stage); accumulators updated with the previous stage's v̇ and this stage's phid.
 template <class T>
 __global__ void __launch_bounds__(128) integrate_stage_kernel(const __grid_constant__ ModelDev<T> M, const StageArgs<T> a) {
-  // one thread per (sample, joint): every joint's coordinates map is independent of the others (blockIdx.y = body)
   const BodyDev<T>& bd = M.body[blockIdx.y];
   const int k0 = bd.vrow, k1 = bd.vrow + kind_nv_dev(bd.kind);
   if (k1 == k0) return;                                    // fixed joint: no coordinates
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
-    for (int k = k0; k < k1; ++k) {
-      const int64_t e = (int64_t)k * a.B + b;
-      const T vdp = a.first ? T(0) : a.vd[e];
-      const T pdp = a.first ? T(0) : a.phid[e];
-      a.phi[e] = a.wa * pdp;
-      a.vs[e] = a.v0[e] + a.wa * vdp;
-      a.accv[e] = a.first ? T(0) : a.accv[e] + a.wb_prev * vdp;
-    }
     const Col<T> q0{a.q0 + b, a.B};
-    const ColRW<T> phi{a.phi + b, a.B}, vs{a.vs + b, a.B};           // written above by this thread
+    const ScaledRow<T> phi{a.phid_prev ? a.phid_prev + b : nullptr, a.B, a.wa};
+    const OffsetRow<T> vs{a.v0 + b, a.vd_prev ? a.vd_prev + b : nullptr, a.B, a.wa};
+    for (int k = k0; k < k1; ++k) a.vs[(int64_t)k * a.B + b] = vs(k);
     const ColOut<T> qs{a.qs + b, a.B, true}, phid{a.phid + b, a.B, true};
     joint_stage(bd, q0, phi, vs, qs, phid);
-    for (int k = k0; k < k1; ++k) {
-      const int64_t e = (int64_t)k * a.B + b;
-      a.accphi[e] = (a.first ? T(0) : a.accphi[e]) + a.wb * a.phid[e];
-    }
   }
 }
+// v = v0 + dt sum_i b_i vd_i ,  q = global(q0, dt sum_i b_i phid_i)        (ode_integrators.jl:283-296)
+template <class T> struct SumRow4 {        // [base[row] +] dt * sum_i w_i p_i[row]
+  const T* base; const T* p[4]; int64_t ld; T w[4]; T dt;
+  RBD_HD T operator()(int row) const {
+    const int64_t e = (int64_t)row * ld;
+    const T s = dt * (w[0] * p[0][e] + w[1] * p[1][e] + w[2] * p[2][e] + w[3] * p[3][e]);
+    return base ? base[e] + s : s;
+  }
+};
 template <class T> struct FinishArgs {
-  const T* q0; const T* v0; const T* vd; const T* accphi; const T* accv;
-  T* phi; T* scratch; T* q; T* v;    // q, v: user arrays (leading dimension ld)
-  T dt, wb_last;
+  const T* q0; const T* v0;
+  const T* phid[4]; const T* vd[4];
+  T* q; T* v;                              // user arrays (leading dimension ld)
+  T w[4]; T dt;
   int64_t B, ld;
 };
-// v = v0 + dt (accv + b_4 vd_4), q = global(q0, dt accphi)
 template <class T>
 __global__ void __launch_bounds__(128) integrate_finish_kernel(const __grid_constant__ ModelDev<T> M, const FinishArgs<T> a) {
   const BodyDev<T>& bd = M.body[blockIdx.y];
   const int k0 = bd.vrow, k1 = bd.vrow + kind_nv_dev(bd.kind);
   if (k1 == k0) return;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
-    for (int k = k0; k < k1; ++k) {
-      const int64_t e = (int64_t)k * a.B + b;
-      const T vn = a.v0[e] + a.dt * (a.accv[e] + a.wb_last * a.vd[e]);
-      a.v[(int64_t)k * a.ld + b] = vn;
-      a.scratch[e] = vn;
-      a.phi[e] = a.dt * a.accphi[e];
-    }
     const Col<T> q0{a.q0 + b, a.B};
-    const ColRW<T> phi{a.phi + b, a.B}, vs{a.scratch + b, a.B};      // written above by this thread
-    const ColOut<T> q{a.q + b, a.ld, true}, dump{a.scratch + b, a.B, false};
-    joint_stage(bd, q0, phi, vs, q, dump);
+    const SumRow4<T> phi{nullptr, {a.phid[0] + b, a.phid[1] + b, a.phid[2] + b, a.phid[3] + b}, a.B, {a.w[0], a.w[1], a.w[2], a.w[3]}, a.dt};
+    const SumRow4<T> vn{a.v0 + b, {a.vd[0] + b, a.vd[1] + b, a.vd[2] + b, a.vd[3] + b}, a.B, {a.w[0], a.w[1], a.w[2], a.w[3]}, a.dt};
+    for (int k = k0; k < k1; ++k) a.v[(int64_t)k * a.ld + b] = vn(k);
+    const ColOut<T> q{a.q + b, a.ld, true}, dump{nullptr, a.B, false};
+    joint_stage(bd, q0, phi, vn, q, dump);
   }
 }
 
@@ -792,11 +798,13 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
   DeviceProps p;
   if (int rc = get_props(p)) return rc;
   const size_t nq = hm.nq, nv = hm.nv;
-  const size_t rows = 2 * nq + 7 * nv + (tau && ld != B ? nv : 0);
+  const size_t rows = 2 * nq + 10 * nv + (tau && ld != B ? nv : 0);
   T* ws = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&ws, rows * (size_t)B * sizeof(T), stream));
-  T* q0 = ws; T* qs = q0 + nq * B; T* v0 = qs + nq * B; T* vs = v0 + nv * B; T* phi = vs + nv * B; T* phid = phi + nv * B;
-  T* vd = phid + nv * B; T* accphi = vd + nv * B; T* accv = accphi + nv * B; T* taud = accv + nv * B;
+  T* q0 = ws; T* qs = q0 + nq * B; T* v0 = qs + nq * B; T* vs = v0 + nv * B;
+  T* phid[4]; T* vd[4];
+  for (int i = 0; i < 4; ++i) { phid[i] = vs + (size_t)(1 + i) * nv * B; vd[i] = vs + (size_t)(5 + i) * nv * B; }
+  T* taud = vs + (size_t)9 * nv * B;
   const T* tau_dense = (const T*)tau;
   if (tau && ld != B) {
     CUDA_TRY(cudaMemcpy2DAsync(taud, B * sizeof(T), tau, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
@@ -809,15 +817,16 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
     CUDA_TRY(cudaMemcpy2DAsync(q0, B * sizeof(T), q, ld * sizeof(T), B * sizeof(T), nq, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(cudaMemcpy2DAsync(v0, B * sizeof(T), v, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
     for (int i = 0; i < 4 && rc == RBD_OK; ++i) {
-      StageArgs<T> sa{q0, v0, phi, phid, vd, qs, vs, accphi, accv, (T)(dt * a[i]), (T)(i ? bw[i - 1] : 0.0), (T)bw[i], i == 0, B};
+      StageArgs<T> sa{q0, v0, i ? phid[i - 1] : nullptr, i ? vd[i - 1] : nullptr, phid[i], qs, vs, (T)(dt * a[i]), B};
       integrate_stage_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, sa);
       CUDA_TRY(cudaGetLastError());
       const int before = g_launch.kernels_launched;
-      rc = dynamics_t<T>(model, B, B, qs, vs, tau_dense, nullptr, vd, nullptr, stream);
+      rc = dynamics_t<T>(model, B, B, qs, vs, tau_dense, nullptr, vd[i], nullptr, stream);
       launches += 1 + (g_launch.kernels_launched - before);
     }
     if (rc != RBD_OK) break;
-    FinishArgs<T> fa{q0, v0, vd, accphi, accv, phi, vs, (T*)q, (T*)v, (T)dt, (T)bw[3], B, ld};
+    FinishArgs<T> fa{q0, v0, {phid[0], phid[1], phid[2], phid[3]}, {vd[0], vd[1], vd[2], vd[3]}, (T*)q, (T*)v,
+                     {(T)bw[0], (T)bw[1], (T)bw[2], (T)bw[3]}, (T)dt, B, ld};
     integrate_finish_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, fa);
     CUDA_TRY(cudaGetLastError());
     launches += 1;

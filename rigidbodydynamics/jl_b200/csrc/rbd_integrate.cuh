@@ -172,9 +172,9 @@ template <class T> RBD_HD void qsph_local_rate(const T* q0, const T* q, const T*
 
 // ---- one joint: stage configuration from local coordinates, and the rate of the local coordinates ---------------------
 // q_stage = global(q0, phi);  phid = d/dt local(q0, q_stage, v_stage).  Rows are addressed through Col / ColOut views.
-// CP: Col<T>, or ColRW<T> when phi / vs were written by this kernel.
-template <class T, class CP>
-RBD_HD void joint_stage(const BodyDev<T>& bd, const Col<T>& q0, const CP& phi, const CP& vs, const ColOut<T>& qs,
+// CP / CV: any row accessor with operator()(row) -- Col<T>, ColRW<T>, or the on-the-fly combinations of the RK4 kernels.
+template <class T, class CP, class CV>
+RBD_HD void joint_stage(const BodyDev<T>& bd, const Col<T>& q0, const CP& phi, const CV& vs, const ColOut<T>& qs,
                         const ColOut<T>& phid) {
   const int q = bd.qrow, v = bd.vrow;
   switch (bd.kind) {
