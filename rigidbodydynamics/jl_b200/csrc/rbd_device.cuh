@@ -564,6 +564,13 @@ template <class T, int PERM> RBD_HD void motion_to_child_z(T s, T c, const T* r,
   t[0] += p.l[0]; t[1] += p.l[1]; t[2] += p.l[2];
   zrot_inv<T, PERM>(s, c, t, ch.l);
 }
+template <class T, int PERM> RBD_HD void force_to_parent_z(T s, T c, const T* r, const T* n, const T* f, T* np, T* fp) {
+  zrot_fwd<T, PERM>(s, c, f, fp);
+  zrot_fwd<T, PERM>(s, c, n, np);
+  np[0] += r[1] * fp[2] - r[2] * fp[1];
+  np[1] += r[2] * fp[0] - r[0] * fp[2];
+  np[2] += r[0] * fp[1] - r[1] * fp[0];
+}
 // Shared tail of the child -> parent hand-over: blocks already rotated into the parent's axes, now shift the origin by r.
 //   C' = Cr ;  B' = Br + r^ Cr ;  A' = Ar + P + P^T + W  with  P = r^ Br^T,  W = r^ (r^ Cr)^T ;  f' = fr ;  n' = nr + r x fr
 template <class T>

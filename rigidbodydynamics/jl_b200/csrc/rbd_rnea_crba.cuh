@@ -121,11 +121,15 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const ST& st)
 #pragma unroll
   for (int k = 0; k < 3; ++k) { vcur.w[k] = vcur.l[k] = acur.w[k] = acur.l[k] = T(0); }
   // software pipeline: scalars of body i+1 are loaded while body i is processed
-  T q0n = T(0), q1n = T(0), qdn = T(0), vdn = T(0);
+  T q0n = T(0), q1n = T(0), qdn = T(0), vdn = T(0), qon = T(0);
+  int zfn = 0;                       // fast-class bits / angle offset of the next body, fetched ahead like the joint scalars
   auto fetch = [&](int i, bool vel, T& q0, T& q1, T& qd, T& vd) {
     q0 = q1 = qd = vd = T(0);
+    zfn = 0; qon = T(0);
     if (i >= 0 && i < nb) {
       const BodyDev<T>& b = M.body[i];
+      zfn = b.flags & (F_ZPAR | F_ZPERP);
+      qon = b.qoff;
       if (b.kind == K_REV || b.kind == K_PRIS || b.kind == K_SINCOS) {
         q0 = io.q(b.qrow);
         if (b.kind == K_SINCOS) q1 = io.q(b.qrow + 1);
@@ -140,7 +144,8 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const ST& st)
   for (int i = 0; i < nb; ++i) {
     const BodyDev<T>& bd = M.body[i];
     const int kind = bd.kind;
-    const T q0 = q0n, q1 = q1n, qd = qdn, vdj = vdn;
+    const T q0 = q0n, q1 = q1n, qd = qdn, vdj = vdn, qoff = qon;
+    const int zf = zfn;
     fetch(i + 1, true, q0n, q1n, qdn, vdn);
     Mot<T> vp, ap;
     if (bd.flags & F_ROOT_CHILD) {
@@ -158,7 +163,15 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const ST& st)
     }
     T R[9], r[3];
     Mot<T> v, a;
-    if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
+    if (zf) {                      // fast class (revolute, E = [P] Rz(q + qoff), rbd_types.h)
+      T s, c;
+      sincos_t(q0 + qoff, s, c);
+      if (zf & F_ZPERP) { motion_to_child_z<T, 1>(s, c, bd.pt, vp, v); motion_to_child_z<T, 1>(s, c, bd.pt, ap, a); }
+      else { motion_to_child_z<T, 0>(s, c, bd.pt, vp, v); motion_to_child_z<T, 0>(s, c, bd.pt, ap, a); }
+      v.w[2] += qd;
+      a.w[0] += qd * v.w[1]; a.w[1] -= qd * v.w[0]; a.w[2] += vdj;
+      a.l[0] += qd * v.l[1]; a.l[1] -= qd * v.l[0];
+    } else if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       Pre<T> pre; pre.q0 = q0; pre.q1 = q1;
       T s, c, d;
       joint_scd(kind, pre, s, c, d);
@@ -224,6 +237,8 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const ST& st)
     const BodyDev<T>& bd = M.body[i];
     const int kind = bd.kind;
     q0c = q0n; q1c = q1n;
+    const int zf = zfn;
+    const T qoff = qon;
     fetch(i - 1, false, q0n, q1n, dq, dv);
     const int row0 = i * kRneaRowsPerBody;
     T n[3], f[3];
@@ -256,15 +271,22 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const ST& st)
     }
     if (bd.flags & F_ROOT_CHILD) continue;
     T R[9], r[3], np[3], fp[3];
-    if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
-      Pre<T> pre; pre.q0 = q0c; pre.q1 = q1c;
-      T s, c, d;
-      joint_scd(kind, pre, s, c, d);
-      frame_1dof(bd, s, c, d, R, r);
+    if (zf) {
+      T s, c;
+      sincos_t(q0c + qoff, s, c);
+      if (zf & F_ZPERP) force_to_parent_z<T, 1>(s, c, bd.pt, n, f, np, fp);
+      else force_to_parent_z<T, 0>(s, c, bd.pt, n, f, np, fp);
     } else {
-      frame_multi(bd, io.q, R, r);
+      if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
+        Pre<T> pre; pre.q0 = q0c; pre.q1 = q1c;
+        T s, c, d;
+        joint_scd(kind, pre, s, c, d);
+        frame_1dof(bd, s, c, d, R, r);
+      } else {
+        frame_multi(bd, io.q, R, r);
+      }
+      force_to_parent(R, r, n, f, np, fp);
     }
-    force_to_parent(R, r, n, f, np, fp);
     if (bd.flags & F_FIRST_CHILD) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) { cn[k] = np[k]; cf[k] = fp[k]; }
