@@ -378,7 +378,7 @@ RBD_HD void crba_sample(const ModelDev<T>& M, const CrbaIO<T>& io, const Stash<T
       pre.q0 = io.q(bd.qrow);
       pre.q1 = kind == K_SINCOS ? io.q(bd.qrow + 1) : T(0);
       T s, c, d;
-      joint_scd(kind, pre, s, c, d);
+      joint_scd(kind, pre, s, c, d, bd.qoff);        // fast classes (rbd_types.h): sin / cos of q + qoff, used with E = [P] Rz below
       st.st(2 * i, kind == K_PRIS ? d : s);
       st.st(2 * i + 1, c);
     }
@@ -386,7 +386,15 @@ RBD_HD void crba_sample(const ModelDev<T>& M, const CrbaIO<T>& io, const Stash<T
   auto frame_of = [&](int j, T* R, T* r) {
     const BodyDev<T>& b = M.body[j];
     const int kind = b.kind;
-    if (kind == K_REV || kind == K_SINCOS) frame_1dof(b, st.ld(2 * j), st.ld(2 * j + 1), T(0), R, r);
+    if (b.flags & (F_ZPAR | F_ZPERP)) {             // R = [P] Rz(s, c) written out, r = pt
+      const T sn = st.ld(2 * j), cs = st.ld(2 * j + 1);
+      if (b.flags & F_ZPERP) {
+        R[0] = T(0); R[1] = T(0); R[2] = T(1);  R[3] = cs; R[4] = -sn; R[5] = T(0);  R[6] = sn; R[7] = cs; R[8] = T(0);
+      } else {
+        R[0] = cs; R[1] = -sn; R[2] = T(0);  R[3] = sn; R[4] = cs; R[5] = T(0);  R[6] = T(0); R[7] = T(0); R[8] = T(1);
+      }
+      r[0] = b.pt[0]; r[1] = b.pt[1]; r[2] = b.pt[2];
+    } else if (kind == K_REV || kind == K_SINCOS) frame_1dof(b, st.ld(2 * j), st.ld(2 * j + 1), T(0), R, r);
     else if (kind == K_PRIS) frame_1dof(b, T(0), T(1), st.ld(2 * j), R, r);
     else if (kind == K_FIXED) frame_1dof(b, T(0), T(1), T(0), R, r);
     else frame_multi(b, io.q, R, r);
@@ -451,16 +459,31 @@ RBD_HD void crba_sample(const ModelDev<T>& M, const CrbaIO<T>& io, const Stash<T
         const BodyDev<T>& bj = M.body[jj];
         const int Kj = kind_nv_dev(bj.kind);
         if (jj == anc) {
-          T R[9], r[3];
-          frame_of(j, R, r);
+          const BodyDev<T>& bs = M.body[j];
+          if (bs.flags & (F_ZPAR | F_ZPERP)) {
+            const T sn = st.ld(2 * j), cs = st.ld(2 * j + 1);
+            const bool perp = (bs.flags & F_ZPERP) != 0;
 #pragma unroll
-          for (int k = 0; k < KMAX; ++k)
-            if (k < K) {
-              T np[3], fp[3];
-              force_to_parent(R, r, Fn[k], Ff[k], np, fp);
+            for (int k = 0; k < KMAX; ++k)
+              if (k < K) {
+                T np[3], fp[3];
+                if (perp) force_to_parent_z<T, 1>(sn, cs, bs.pt, Fn[k], Ff[k], np, fp);
+                else force_to_parent_z<T, 0>(sn, cs, bs.pt, Fn[k], Ff[k], np, fp);
 #pragma unroll
-              for (int d = 0; d < 3; ++d) { Fn[k][d] = np[d]; Ff[k][d] = fp[d]; }
-            }
+                for (int d = 0; d < 3; ++d) { Fn[k][d] = np[d]; Ff[k][d] = fp[d]; }
+              }
+          } else {
+            T R[9], r[3];
+            frame_of(j, R, r);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+              if (k < K) {
+                T np[3], fp[3];
+                force_to_parent(R, r, Fn[k], Ff[k], np, fp);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { Fn[k][d] = np[d]; Ff[k][d] = fp[d]; }
+              }
+          }
           j = jj;
           anc = bj.parent;
           for (int l = 0; l < Kj; ++l) {
