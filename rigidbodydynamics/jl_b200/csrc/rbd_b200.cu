@@ -416,7 +416,7 @@ template <class T> struct KinArgs {
 };
 
 template <class T, int NT>
-__global__ void __launch_bounds__(NT) kin_kernel(const __grid_constant__ ModelDev<T> M, const KinArgs<T> a,
+__global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 28 : 12) kin_kernel(const __grid_constant__ ModelDev<T> M, const KinArgs<T> a,
                                                   const __grid_constant__ KinDev<T> K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
