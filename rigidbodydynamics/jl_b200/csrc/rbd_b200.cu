@@ -305,7 +305,7 @@ template <class T> struct RneaArgs {
 };
 
 template <class T, int NT, bool EXT>
-__global__ void __launch_bounds__(NT) rnea_kernel(const __grid_constant__ ModelDev<T> M, const RneaArgs<T> a) {
+__global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 32 : 1) rnea_kernel(const __grid_constant__ ModelDev<T> M, const RneaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   const Stash<T, NT> st{sh + threadIdx.x};
@@ -390,7 +390,7 @@ template <class T> struct CrbaArgs {
 };
 
 template <class T, int NT, int KMAX>
-__global__ void __launch_bounds__(NT) crba_kernel(const __grid_constant__ ModelDev<T> M, const CrbaArgs<T> a) {
+__global__ void __launch_bounds__(NT, sizeof(T) == 4 ? (KMAX == 1 ? 28 : 20) : 1) crba_kernel(const __grid_constant__ ModelDev<T> M, const CrbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   const Stash<T, NT> st{sh + threadIdx.x};
