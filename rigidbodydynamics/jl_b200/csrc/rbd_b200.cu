@@ -112,7 +112,8 @@ template <class T> struct AbaArgs {
 
 // KINDS: compile-time promise about the 1-DoF kinds present (kAllKinds, or 0 = revolute / sin-cos-revolute only).
 template <class T, int NT, bool GENERAL, bool EXT, int KINDS>
-__global__ void __launch_bounds__(NT) aba_kernel(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
+__global__ void __launch_bounds__(NT, (sizeof(T) == 4 && !GENERAL && !EXT) ? 20 : 1)
+aba_kernel(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   using ST = Stash<T, NT>;
