@@ -4,8 +4,9 @@
 // tcgen05.mma accumulators, but tcgen05.ld / tcgen05.st move 32-bit words between registers and TMEM with the "32x32b"
 // shape: lane l of warp w touches TMEM lane 32*(w % 4) + l, one column per register.  That is exactly the access pattern of
 // this library's stash (one private scalar per thread and row), so a CTA of 128 threads that allocates N columns gets N
-// private words per thread -- a second on-chip home for the per-sample working set, doubling the number of samples an SM
-// can keep in flight for this latency-bound kernel.
+// private words per thread, and a CTA of 256 threads that allocates all 512 columns gets 256 per thread (warps 4-7 share the
+// lane quadrants of warps 0-3 and use the upper half of the columns) -- a second on-chip home for the per-sample working
+// set, doubling the number of samples an SM can keep in flight for this latency-bound kernel.
 #pragma once
 #include <stdint.h>
 
