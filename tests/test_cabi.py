@@ -70,3 +70,28 @@ def test_too_many_bodies_is_unsupported(built):
     with pytest.raises(rbd.RbdError) as e:
         _cabi.ModelHandle(mech.flatten())
     assert e.value.status == _cabi.RBD_EUNSUPPORTED
+
+
+def test_kinematics_and_integrate_argument_checks(built):
+    """rbd_kinematics / rbd_integrate validate their arguments on the host, before any CUDA call (no GPU needed)."""
+    lib = rbd.load_library()
+    h = _cabi.ModelHandle(rbd.load_model("iiwa14").flatten())
+    ko = _cabi.RbdKinematicsOut()
+    assert ctypes.sizeof(ko) == 8 * ctypes.sizeof(ctypes.c_void_p)           # eight output pointers, as in the header
+    dummy = ctypes.c_void_p(16)                                               # never dereferenced by the checks below
+    assert lib.rbd_kinematics(None, 0, 1, 1, dummy, None, None, ctypes.byref(ko), None) == _cabi.RBD_EINVAL
+    assert lib.rbd_kinematics(h.ptr, 0, 1, 1, dummy, None, None, None, None) == _cabi.RBD_EINVAL              # out == NULL
+    assert lib.rbd_kinematics(h.ptr, _cabi.RBD_DUAL64X6, 1, 1, dummy, None, None, ctypes.byref(ko), None) == _cabi.RBD_EUNSUPPORTED
+    assert lib.rbd_kinematics(h.ptr, 0, 4, 2, dummy, None, None, ctypes.byref(ko), None) == _cabi.RBD_EDIM    # ld < B
+    assert lib.rbd_kinematics(h.ptr, 0, 0, 0, None, None, None, ctypes.byref(ko), None) == _cabi.RBD_OK       # empty batch
+    assert lib.rbd_kinematics(h.ptr, 0, 1, 1, None, None, None, ctypes.byref(ko), None) == _cabi.RBD_EINVAL   # q == NULL
+    ko.kinetic_energy = 16
+    assert lib.rbd_kinematics(h.ptr, 0, 1, 1, dummy, None, None, ctypes.byref(ko), None) == _cabi.RBD_EINVAL  # needs v
+    ko.kinetic_energy = None
+    ko.geometric_jacobian = 16
+    assert lib.rbd_kinematics(h.ptr, 0, 1, 1, dummy, None, None, ctypes.byref(ko), None) == _cabi.RBD_EINVAL  # needs path_sign
+    bad = (ctypes.c_int8 * 7)(1, 1, 2, 0, 0, 0, 0)
+    assert lib.rbd_kinematics(h.ptr, 0, 1, 1, dummy, None, bad, ctypes.byref(ko), None) == _cabi.RBD_EINVAL   # sign not in {-1,0,1}
+    assert b"path_sign" in lib.rbd_last_error()
+    assert lib.rbd_integrate(None, 0, 1, 1, dummy, dummy, None, 1e-3, 1, None) == _cabi.RBD_EINVAL
+    assert lib.rbd_integrate(h.ptr, 0, 4, 2, dummy, dummy, None, 1e-3, 1, None) == _cabi.RBD_EDIM
