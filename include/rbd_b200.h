@@ -116,6 +116,7 @@ typedef struct rbd_launch_info {
   int32_t smem_bytes;
   int32_t blocks_per_sm;
   float last_kernel_ms; /* only filled by the *_host variants and rbd_*_timed helpers; else 0 */
+  int32_t specialised;  /* 1 if the call ran the model-specialised (run-time compiled) kernels, 0 = generic kernels */
 } rbd_launch_info;
 
 int32_t rbd_version(void);
@@ -130,6 +131,25 @@ int32_t rbd_model_get_info(const rbd_model* model, rbd_model_info* info);
 /* RBD_ESTALE if `modcount` differs from the one the handle was created with (@modcountcheck, util.jl:56-72). */
 int32_t rbd_model_check_modcount(const rbd_model* model, int64_t modcount);
 int32_t rbd_get_launch_info(rbd_launch_info* info);
+
+/*
+ * Model-specialised kernels.  For a given handle the library can generate straight-line CUDA code for dynamics! /
+ * inverse_dynamics! / dynamics_bias! of THAT mechanism (tree walk unrolled, joint classes resolved, model constants folded,
+ * structural zeros removed), compile it with NVRTC for sm_100a and keep the cubin in a disk cache
+ * ($RBD_JIT_CACHE, else <library dir>/jit_cache, else ~/.cache/rbd_b200).  This is the analogue of the reference compiling
+ * its generic functions for a concrete MechanismState{X,M,C} on first call (Julia's JIT).
+ * Entry points use a specialised kernel when its cubin is cached or the batch is at least RBD_JIT_MIN_BATCH (default 32768)
+ * samples -- the first such call then pays the compilation (seconds) -- and otherwise the generic kernels; RBD_JIT=0 disables.
+ * rbd_model_precompile compiles ahead of time: `what` = OR of the RBD_SPEC_* bits, `load` != 0 also loads the kernels on the
+ * current device (needs a GPU; load = 0 only fills the cache and works without one).  RBD_EUNSUPPORTED if NVRTC is not
+ * available or the model does not qualify (callers keep working on the generic kernels).
+ */
+#define RBD_SPEC_DYNAMICS 1          /* dynamics!(result, state, torques)                */
+#define RBD_SPEC_DYNAMICS_QDOT 2     /* ... with the q̇ output                             */
+#define RBD_SPEC_DYNAMICS_NOTAU 4    /* ... with the zero-torque default (with / without q̇) */
+#define RBD_SPEC_INVERSE_DYNAMICS 8  /* inverse_dynamics!                                */
+#define RBD_SPEC_DYNAMICS_BIAS 16    /* dynamics_bias!                                   */
+int32_t rbd_model_precompile(rbd_model* model, int32_t dtype, int32_t what, int32_t load);
 
 /*
  * dynamics!(result, state, torques, externalwrenches)         src/mechanism_algorithms.jl:845-864

@@ -15,6 +15,8 @@ RBD_MAX_BODIES = 64
 
 RBD_OK, RBD_EINVAL, RBD_EDIM, RBD_ELOOP, RBD_ESTALE, RBD_ECUDA, RBD_EUNSUPPORTED, RBD_ENOMEM = range(8)
 RBD_F32, RBD_F64, RBD_DUAL64X6 = 0, 1, 2
+RBD_SPEC_DYNAMICS, RBD_SPEC_DYNAMICS_QDOT, RBD_SPEC_DYNAMICS_NOTAU, RBD_SPEC_INVERSE_DYNAMICS, RBD_SPEC_DYNAMICS_BIAS = 1, 2, 4, 8, 16
+RBD_SPEC_ALL = 31
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librbd_b200.so")
@@ -48,7 +50,7 @@ class RbdModelInfo(Structure):
 class RbdLaunchInfo(Structure):
     _fields_ = [
         ("kernels_launched", c_int32), ("grid", c_int32), ("block", c_int32),
-        ("smem_bytes", c_int32), ("blocks_per_sm", c_int32), ("last_kernel_ms", c_float),
+        ("smem_bytes", c_int32), ("blocks_per_sm", c_int32), ("last_kernel_ms", c_float), ("specialised", c_int32),
     ]
 
 
@@ -101,6 +103,7 @@ SYMBOLS = {
     "rbd_model_get_info": (c_int32, [_vp, POINTER(RbdModelInfo)]),
     "rbd_model_check_modcount": (c_int32, [_vp, _i64]),
     "rbd_get_launch_info": (c_int32, [POINTER(RbdLaunchInfo)]),
+    "rbd_model_precompile": (c_int32, [_vp, _i32, _i32, _i32]),
     "rbd_dynamics": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rbd_inverse_dynamics": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rbd_dynamics_bias": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -157,6 +160,11 @@ class ModelHandle:
 
     def check_modcount(self, modcount: int):
         check(self._lib.rbd_model_check_modcount(self._h, int(modcount)))
+
+    def precompile(self, dtype: int = RBD_F32, what: int = RBD_SPEC_ALL, load: bool = False):
+        """rbd_model_precompile: generate + NVRTC-compile the model-specialised kernels into the cubin cache (no GPU needed
+        unless ``load``)."""
+        check(self._lib.rbd_model_precompile(self._h, int(dtype), int(what), 1 if load else 0))
 
     def close(self):
         if getattr(self, "_h", None):

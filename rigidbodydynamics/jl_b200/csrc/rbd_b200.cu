@@ -19,6 +19,7 @@
 #include <memory>
 #include <mutex>
 #include <new>
+#include <set>
 #include <string>
 #include <type_traits>
 
@@ -35,22 +36,12 @@ using namespace rbd;
 // ------------------------------------------------------------------------------------------------------------------
 // handle, errors
 // ------------------------------------------------------------------------------------------------------------------
-struct rbd_model {
-  HostModel hm;
-  // staging for the *_host entry points (allocated on first use, owned by the handle)
-  std::mutex host_mu;
-  void* d_stage[3] = {nullptr, nullptr, nullptr};
-  size_t stage_bytes = 0;
-  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-  cudaStream_t side_stream = nullptr;   // Tensor-Memory kernel runs here, next to the shared-memory kernel
-  std::mutex side_mu;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
+#include "rbd_handle.h"
 
 namespace {
 
 thread_local std::string g_err;
-thread_local rbd_launch_info g_launch = {0, 0, 0, 0, 0, 0.f};
+thread_local rbd_launch_info g_launch = {0, 0, 0, 0, 0, 0.f, 0};
 
 int fail(int status, const std::string& msg) { g_err = msg; return status; }
 int fail_cuda(cudaError_t e, const char* what) {
@@ -59,7 +50,7 @@ int fail_cuda(cudaError_t e, const char* what) {
 }
 #define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail_cuda(e_, #expr); } while (0)
 
-struct DeviceProps { int sms = 0; int max_smem_optin = 0; int smem_per_sm = 0; bool ok = false; };
+struct DeviceProps { int dev = 0; int sms = 0; int max_smem_optin = 0; int smem_per_sm = 0; bool ok = false; };
 int get_props(DeviceProps& p) {
   static std::mutex mu;
   static DeviceProps cache[64];
@@ -68,6 +59,7 @@ int get_props(DeviceProps& p) {
   std::lock_guard<std::mutex> lk(mu);
   if (dev >= 0 && dev < 64 && cache[dev].ok) { p = cache[dev]; return RBD_OK; }
   DeviceProps q;
+  q.dev = dev;
   CUDA_TRY(cudaDeviceGetAttribute(&q.sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&q.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&q.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -444,10 +436,23 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 28 : 12) kin_kernel(const
   }
 }
 
+// Opt a kernel into large dynamic shared memory ONCE per (kernel, device): the attribute is process-global per kernel, so
+// setting it to each call's exact size would race between host threads using different model handles.
+int configure_once(const void* kernel, const DeviceProps& p) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({kernel, p.dev})) return RBD_OK;
+  cudaFuncAttributes fa{};
+  CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.max_smem_optin - (int)fa.sharedSizeBytes));
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  done.insert({kernel, p.dev});
+  return RBD_OK;
+}
 template <class K> int configure(K kernel, int nt, size_t smem, const DeviceProps& p, int& blocks_per_sm) {
   if ((int)smem > p.max_smem_optin) return fail(RBD_EUNSUPPORTED, "model working set exceeds shared memory per block");
-  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (int rc = configure_once((const void*)kernel, p)) return rc;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, nt, smem));
   if (blocks_per_sm < 1) return fail(RBD_EUNSUPPORTED, "kernel does not fit on an SM");
   return RBD_OK;
@@ -504,13 +509,16 @@ template <class T, class KS, class KT, class Args>
 int launch_duo(const rbd_model* model, KS ks, KT kt, int tm_warps, const ModelDev<T>& M, Args a, int rows, int scratch_rows,
                cudaStream_t stream, bool& used) {
   used = false;
-  if (getenv("RBD_NO_TMEM")) return RBD_OK;
+  static const bool no_tmem = getenv("RBD_NO_TMEM") != nullptr;
+  static const int smem_blocks = getenv("RBD_SMEM_BLOCKS") ? atoi(getenv("RBD_SMEM_BLOCKS")) : 0;
+  if (no_tmem) return RBD_OK;
   DeviceProps p;
   if (int rc = get_props(p)) return rc;
   const int64_t ngroups = (a.B + kNT - 1) / kNT;
   const size_t smem = (size_t)rows * kNT * sizeof(T);
   int bps = 0;
   if (int rc = configure(ks, kNT, smem, p, bps)) return rc;
+  if (int rc = configure_once((const void*)kt, p)) return rc;
   {
     // leave room in the register file for the Tensor-Memory CTA: small models are not limited by shared memory and the
     // persistent shared-memory blocks would otherwise keep that CTA off the SM until they drain the queue
@@ -524,23 +532,14 @@ int launch_duo(const rbd_model* model, KS ks, KT kt, int tm_warps, const ModelDe
     if ((with_pair + tm_warps) * 100 < bps * 115) return RBD_OK;
     bps = with_pair;
   }
-  if (getenv("RBD_SMEM_BLOCKS")) bps = std::max(1, std::min(bps, atoi(getenv("RBD_SMEM_BLOCKS"))));
+  if (smem_blocks > 0) bps = std::max(1, std::min(bps, smem_blocks));
   if (ngroups < (int64_t)(bps + tm_warps / 2) * p.sms) return RBD_OK;     // not enough work to keep both kernels' warps busy
   rbd_model* mm = const_cast<rbd_model*>(model);
-  cudaStream_t side = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(mm->side_mu);
-    if (!mm->side_stream) CUDA_TRY(cudaStreamCreateWithFlags(&mm->side_stream, cudaStreamNonBlocking));
-    side = mm->side_stream;
-    CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  }
-  cudaEvent_t fork = nullptr, join = nullptr;
-  CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-  void* counter = nullptr;
-  CUDA_TRY(cudaMallocAsync(&counter, 8, stream));
-  CUDA_TRY(cudaMemsetAsync(counter, 0, 8, stream));
-  a.counter = (unsigned long long*)counter;
+  PairCtx ctx;      // side stream, fork / join events and a zeroed queue counter, all cached in the handle
+  CUDA_TRY(pair_begin(mm, stream, ctx));
+  cudaStream_t side = ctx.side;
+  cudaEvent_t fork = ctx.fork, join = ctx.join;
+  a.counter = ctx.counter;
   void* scratch = nullptr;
   if (scratch_rows > 0) {       // external wrenches in body frames: one column per resident thread of either kernel
     a.scratch_off = (int64_t)bps * p.sms * kNT;
@@ -552,16 +551,13 @@ int launch_duo(const rbd_model* model, KS ks, KT kt, int tm_warps, const ModelDe
   CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
   // (profiling aid: under ncu kernels are serialised and the first one drains the queue; RBD_ONLY=smem|tmem launches
   //  just one of the two so each can be captured doing the whole batch)
-  const char* only = getenv("RBD_ONLY");
+  static const char* const only = getenv("RBD_ONLY");
   if (!only || only[0] == 's') ks<<<bps * p.sms, kNT, smem, stream>>>(M, a);
   if (!only || only[0] == 't') kt<<<p.sms, 32 * tm_warps, 0, side>>>(M, a);
   cudaError_t e = cudaGetLastError();
   cudaEventRecord(join, side);
   cudaStreamWaitEvent(stream, join, 0);
-  cudaFreeAsync(counter, stream);
   if (scratch) cudaFreeAsync(scratch, stream);
-  cudaEventDestroy(fork);
-  cudaEventDestroy(join);
   if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
   g_launch.kernels_launched += 2;
   g_launch.grid = bps * p.sms; g_launch.block = kNT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
@@ -577,6 +573,14 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   AbaArgs<T> a{(const T*)q, (const T*)v, (const T*)tau, (const T*)wext, (T*)vd, (T*)qd, nullptr, ld, B};
   const int rows = M.nrows;
   const int sr = wext ? 6 * hm.nb : 0;
+  if (!wext) {      // model-specialised kernels (rbd_spec.cpp): straight-line code generated for this mechanism
+    SpecKey key; key.algo = SPEC_ABA; key.f64 = sizeof(T) == 8; key.has_in2 = tau != nullptr; key.has_out1 = qd != nullptr;
+    const SpecLaunchArgs sa{q, v, tau, vd, qd, ld, B};
+    bool used = false;
+    std::string err;
+    if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, err)) return fail(rc, err);
+    if (used) { g_launch.specialised = 1; return RBD_OK; }
+  }
   bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
   for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
   if (!hm.general && !other_kinds && rows <= 256 && (!wext || duo_enabled("RBD_DUO_EXT", kDuoExtDefault))) {
@@ -604,6 +608,14 @@ int inverse_dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void
   const ModelDev<T>& M = dev_model<T>(hm);
   RneaArgs<T> a{(const T*)q, (const T*)v, (const T*)vd, (const T*)wext, (T*)tau, nullptr, ld, B};
   const int rows = rnea_rows(hm);
+  if (!wext) {
+    SpecKey key; key.algo = SPEC_RNEA; key.f64 = sizeof(T) == 8; key.has_in2 = vd != nullptr;
+    const SpecLaunchArgs sa{q, v, vd, tau, nullptr, ld, B};
+    bool used = false;
+    std::string err;
+    if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, err)) return fail(rc, err);
+    if (used) { g_launch.specialised = 1; return RBD_OK; }
+  }
   if (rows <= 256 && duo_enabled("RBD_DUO_RNEA", kDuoRneaDefault) && (!wext || duo_enabled("RBD_DUO_EXT", kDuoExtDefault))) {
     constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;
     bool used = false;
@@ -837,10 +849,12 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
   return rc;
 }
 
-int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld) {
+int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, bool allow_dual = false) {
   if (!model) return fail(RBD_EINVAL, "model handle is NULL");
   if (dtype != RBD_F32 && dtype != RBD_F64 && dtype != RBD_DUAL64X6)
     return fail(RBD_EINVAL, "dtype must be RBD_F32, RBD_F64 or RBD_DUAL64X6");
+  if (dtype == RBD_DUAL64X6 && !allow_dual)
+    return fail(RBD_EUNSUPPORTED, "RBD_DUAL64X6 is supported by rbd_dynamics only; use the reference's generic path");
   if (B < 0 || ld < B) return fail(RBD_EDIM, "batch size / leading dimension mismatch (need ld >= B >= 0)");
   return RBD_OK;
 }
@@ -853,7 +867,7 @@ int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld) {
 int32_t rbd_kinematics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                        const int8_t* path_sign, const rbd_kinematics_out* out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (dtype != RBD_F32 && dtype != RBD_F64) return fail(RBD_EUNSUPPORTED, "rbd_kinematics: fp32 and fp64 only");
   if (!out) return fail(RBD_EINVAL, "rbd_kinematics: out must not be NULL");
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
@@ -985,7 +999,12 @@ int32_t rbd_model_destroy(rbd_model* m) {
     if (m->d_stage[i]) cudaFree(m->d_stage[i]);
     if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
   }
-  if (m->side_stream) cudaStreamDestroy(m->side_stream);
+  spec_release(m);
+  if (m->side_stream) {
+    cudaStreamDestroy(m->side_stream);
+    for (int i = 0; i < kEventRing; ++i) { cudaEventDestroy(m->fork_ev[i]); cudaEventDestroy(m->join_ev[i]); }
+    cudaFree(m->counters);
+  }
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   delete m;
@@ -1021,10 +1040,29 @@ int32_t rbd_get_launch_info(rbd_launch_info* info) {
   return RBD_OK;
 }
 
+int32_t rbd_model_precompile(rbd_model* model, int32_t dtype, int32_t what, int32_t load) {
+  if (!model) return fail(RBD_EINVAL, "model handle is NULL");
+  if (dtype != RBD_F32 && dtype != RBD_F64) return fail(RBD_EUNSUPPORTED, "rbd_model_precompile: fp32 / fp64 only");
+  int rc_all = RBD_OK;
+  std::string err;
+  auto one = [&](int algo, bool in2, bool out1) {
+    SpecKey key; key.algo = algo; key.f64 = dtype == RBD_F64; key.has_in2 = in2; key.has_out1 = out1;
+    std::string e;
+    const int rc = spec_prepare(model, key, load != 0, e);
+    if (rc != RBD_OK) { rc_all = rc; err = e; }
+  };
+  if (what & RBD_SPEC_DYNAMICS) one(SPEC_ABA, true, false);
+  if (what & RBD_SPEC_DYNAMICS_QDOT) one(SPEC_ABA, true, true);
+  if (what & RBD_SPEC_DYNAMICS_NOTAU) { one(SPEC_ABA, false, false); one(SPEC_ABA, false, true); }
+  if (what & RBD_SPEC_INVERSE_DYNAMICS) one(SPEC_RNEA, true, false);
+  if (what & RBD_SPEC_DYNAMICS_BIAS) one(SPEC_RNEA, false, false);
+  return rc_all == RBD_OK ? RBD_OK : fail(rc_all, err);
+}
+
 int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                      const void* tau, const void* wext, void* vd_out, void* qd_out, void* stream) {
-  if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  if (int rc = check_common(model, dtype, B, ld, true)) return rc;
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !v || !vd_out) return fail(RBD_EINVAL, "rbd_dynamics: q, v and vd_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1041,7 +1079,7 @@ int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t 
   if (int rc = check_common(model, dtype, B, ld)) return rc;
   if (dtype == RBD_DUAL64X6) return fail(RBD_EUNSUPPORTED, "rbd_integrate: RBD_DUAL64X6 is not supported");
   if (nsteps < 0 || !(dt > 0)) return fail(RBD_EINVAL, "rbd_integrate: need dt > 0 and nsteps >= 0");
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0 || nsteps == 0) return RBD_OK;
   if (!q || !v) return fail(RBD_EINVAL, "rbd_integrate: q and v must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1052,7 +1090,7 @@ int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t 
 int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                              const void* v, const void* vd, const void* wext, void* tau_out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !v || !vd || !tau_out) return fail(RBD_EINVAL, "rbd_inverse_dynamics: q, v, vd and tau_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1063,7 +1101,7 @@ int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, i
 int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                           const void* v, const void* wext, void* c_out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !v || !c_out) return fail(RBD_EINVAL, "rbd_dynamics_bias: q, v and c_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1074,7 +1112,7 @@ int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int6
 int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
                         void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix: q and M_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1087,7 +1125,7 @@ int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_
 int32_t rbd_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                           const void* tau, const void* wext, void* vd_out, void* qd_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !v || !vd_out) return fail(RBD_EINVAL, "rbd_dynamics_host: q, v and vd_out must not be NULL");
   const HostModel& hm = model->hm;
@@ -1104,7 +1142,7 @@ int32_t rbd_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld
 int32_t rbd_inverse_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                                   const void* v, const void* vd, const void* wext, void* tau_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !v || !vd || !tau_out) return fail(RBD_EINVAL, "rbd_inverse_dynamics_host: q, v, vd and tau_out must not be NULL");
   const HostModel& hm = model->hm;
@@ -1121,7 +1159,7 @@ int32_t rbd_inverse_dynamics_host(rbd_model* model, int32_t dtype, int64_t B, in
 int32_t rbd_dynamics_bias_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                                const void* v, const void* wext, void* c_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !v || !c_out) return fail(RBD_EINVAL, "rbd_dynamics_bias_host: q, v and c_out must not be NULL");
   const HostModel& hm = model->hm;
@@ -1137,7 +1175,7 @@ int32_t rbd_dynamics_bias_host(rbd_model* model, int32_t dtype, int64_t B, int64
 
 int32_t rbd_mass_matrix_host(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  g_launch = {0, 0, 0, 0, 0, 0.f};
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix_host: q and M_out must not be NULL");
   const HostModel& hm = model->hm;

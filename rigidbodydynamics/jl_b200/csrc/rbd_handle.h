@@ -1,0 +1,81 @@
+// The opaque model handle of the C ABI (include/rbd_b200.h), shared by rbd_b200.cu (generic kernels, entry points) and
+// rbd_spec.cpp (model-specialised kernels).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "../../../include/rbd_b200.h"
+#include "rbd_codegen.h"
+#include "rbd_model.h"
+
+namespace rbd {
+
+// One model-specialised kernel pair (shared-memory + Tensor-Memory stash), loaded from a cubin.
+struct SpecEntry {
+  int state = 0;                 // 0 = not tried, 1 = ready, -1 = unavailable (generic kernels are used)
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t k_smem = nullptr, k_tmem = nullptr, k_smem32 = nullptr;   // k_smem32: packed mode, unaligned / odd-tail I/O
+  int regs_smem = 0, regs_tmem = 0;
+  int rows = 0;
+  int smem_warps = 8;            // warps per shared-memory CTA (SpecTuning)
+  bool from_cache = false;
+  std::string why;               // reason for state -1
+};
+
+constexpr int kCounterRing = 256;   // work-queue counters, one per call in flight
+constexpr int kEventRing = 8;
+
+}  // namespace rbd
+
+struct rbd_model {
+  rbd::HostModel hm;
+  // staging for the *_host entry points (allocated on first use, owned by the handle)
+  std::mutex host_mu;
+  void* d_stage[3] = {nullptr, nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // kernel pairs: the Tensor-Memory kernel runs on the side stream next to the shared-memory kernel (per device)
+  std::mutex side_mu;
+  int side_device = -1;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t fork_ev[rbd::kEventRing] = {}, join_ev[rbd::kEventRing] = {};
+  unsigned long long* counters = nullptr;     // [kCounterRing] device memory
+  unsigned next_call = 0;
+  // model-specialised kernels, keyed by SpecKey bits
+  std::mutex spec_mu;
+  std::map<uint32_t, rbd::SpecEntry> spec;
+};
+
+namespace rbd {
+
+// Resources of one kernel-pair launch: side stream, fork/join events and a zeroed work-queue counter (enqueued on `stream`).
+struct PairCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  unsigned long long* counter = nullptr;
+};
+// Returns a cudaError_t (cudaSuccess = 0).
+cudaError_t pair_begin(rbd_model* m, cudaStream_t stream, PairCtx& ctx);
+
+inline uint32_t spec_key_bits(const SpecKey& k) {
+  return (uint32_t)k.algo | (k.f64 ? 8u : 0u) | (k.has_in2 ? 16u : 0u) | (k.has_out1 ? 32u : 0u) | (k.lower ? 64u : 0u) | (k.packed ? 128u : 0u);
+}
+
+struct SpecLaunchArgs {
+  const void* q; const void* v; const void* in2;
+  void* o0; void* o1;
+  int64_t ld, B;
+};
+// Tries the model-specialised kernels for (model, key).  `used` = false (and RBD_OK) when they are unavailable, not yet
+// compiled and the batch is below the compile threshold, or the batch is too small: the caller then runs the generic kernels.
+int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, cudaStream_t stream, bool& used,
+                    rbd_launch_info& li, std::string& err);
+// Compile (or load from the cubin cache) without launching; RBD_OK / RBD_EUNSUPPORTED.
+int spec_prepare(rbd_model* m, const SpecKey& key, bool load_on_device, std::string& err);
+void spec_release(rbd_model* m);
+
+}  // namespace rbd

@@ -58,8 +58,13 @@ class MechanismState:
         return self.nv
 
     def check_modcount(self):
-        """@modcountcheck (src/util.jl:56-72)."""
+        """@modcountcheck (src/util.jl:56-72).  Every operator calls this first, so it also checks that the state's tensors
+        live on the CURRENT CUDA device: the library launches on the current device and stream, and pointers into another
+        GPU's memory would fault (or silently cross NVLink)."""
         self.handle.check_modcount(self.mechanism.modcount)
+        if self.q.is_cuda and self.q.device.index != torch.cuda.current_device():
+            raise ValueError(f"MechanismState lives on {self.q.device} but the current CUDA device is "
+                             f"cuda:{torch.cuda.current_device()}; wrap the call in `with torch.cuda.device(state.q.device):`")
 
     def to_vector(self) -> torch.Tensor:
         """``Vector(state)`` = [q; v] per sample (mechanism_state.jl:482-506) -> [nq + nv, B]."""

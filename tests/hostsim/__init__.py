@@ -13,7 +13,8 @@ def build(force=False):
                                                    if f.endswith((".cuh", ".h", ".cpp"))]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB,
-                               os.path.join(_HERE, "hostsim.cpp"), os.path.join(_CSRC, "rbd_model.cpp")])
+                               os.path.join(_HERE, "hostsim.cpp"), os.path.join(_CSRC, "rbd_model.cpp"),
+                               os.path.join(_CSRC, "rbd_codegen.cpp")])
     return _LIB
 
 
@@ -143,3 +144,59 @@ def flags(desc):
     rc = lib().hostsim_flags(ctypes.byref(d), out)
     assert rc == 0, rc
     return list(out)
+
+
+SPEC_STATS = ("nodes_traced", "nodes_live", "add", "mul", "div", "neg", "sincos", "load", "store", "sld", "sst", "stash_rows")
+
+
+def spec_source(desc, algo="aba", dtype=np.float64, has_in2=True, has_out1=False, flavor=0):
+    """Source text + statistics of the model-specialised program csrc/rbd_codegen.cpp generates for this mechanism."""
+    d, keep = make_desc(desc)
+    fn = lib().hostsim_spec_source
+    fn.restype = ctypes.c_void_p
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc)] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    stats = (ctypes.c_int * 12)()
+    p = fn(ctypes.byref(d), {"aba": 0, "rnea": 1, "crba": 2}[algo], 0 if np.dtype(dtype) == np.float32 else 1, int(has_in2),
+           int(has_out1), flavor, stats)
+    assert p, "specialisation failed"
+    src = ctypes.string_at(p).decode()
+    lib().hostsim_free.argtypes = [ctypes.c_void_p]
+    lib().hostsim_free(p)
+    return src, dict(zip(SPEC_STATS, stats))
+
+
+class SpecProgram:
+    """The specialised program compiled for the CPU (g++) -- the same straight-line code the NVRTC kernels run."""
+
+    def __init__(self, desc, algo="aba", dtype=np.float64, has_in2=True, has_out1=False):
+        import hashlib, tempfile
+        self.desc, self.algo, self.dtype = desc, algo, np.dtype(dtype)
+        src, self.stats = spec_source(desc, algo, dtype, has_in2, has_out1, 0)
+        tag = hashlib.sha1(src.encode()).hexdigest()[:16]
+        d = os.path.join(tempfile.gettempdir(), "rbd_spec_cpu")
+        os.makedirs(d, exist_ok=True)
+        so = os.path.join(d, f"spec_{tag}.so")
+        if not os.path.exists(so):
+            cpp = os.path.join(d, f"spec_{tag}.cpp")
+            with open(cpp, "w") as f:
+                f.write(src)
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",
+                                   "-I", _CSRC, "-o", so + ".tmp", cpp])
+            os.replace(so + ".tmp", so)
+        self.fn = ctypes.CDLL(so).rbd_spec_cpu
+        self.fn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_longlong, ctypes.c_void_p]
+        self.has_in2, self.has_out1 = has_in2, has_out1
+
+    def run(self, q, v, in2=None, out0_rows=None, out1_rows=None):
+        dt = self.dtype
+        q = np.ascontiguousarray(q, dt); v = np.ascontiguousarray(v, dt)
+        in2 = None if in2 is None else np.ascontiguousarray(in2, dt)
+        B = q.shape[1]
+        o0 = np.full((out0_rows or self.desc.nv, B), np.nan, dt)
+        o1 = np.full((out1_rows or self.desc.nq, B), np.nan, dt) if self.has_out1 else None
+        sh = np.zeros(self.stats["stash_rows"] + 8, dt)
+        es = dt.itemsize
+        for b in range(B):
+            self.fn(q.ctypes.data + b * es, v.ctypes.data + b * es, None if in2 is None else in2.ctypes.data + b * es,
+                    o0.ctypes.data + b * es, None if o1 is None else o1.ctypes.data + b * es, B, sh.ctypes.data)
+        return (o0, o1) if self.has_out1 else o0

@@ -11,6 +11,7 @@
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_dual.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_integrate.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_model.h"
+#include "../../rigidbodydynamics/jl_b200/csrc/rbd_codegen.h"
 
 using namespace rbd;
 
@@ -135,6 +136,31 @@ void run_integrate(const HostModel& hm, int64_t B, T* q, T* v, const T* tau, dou
 }
 
 extern "C" {
+// Model-specialised program (csrc/rbd_codegen.cpp) for the mechanism: flavor 0 = self-contained C++ (one sample per call),
+// 1 / 2 = the per-sample CUDA function bodies, 3 = the whole NVRTC translation unit, 4 = same in packed-fp32 mode.  Returns a malloc'ed string (free with
+// hostsim_free) or NULL; stats = {nodes_traced, nodes_live, add, mul, div, neg, sincos, load, store, sld, sst, stash_rows}.
+char* hostsim_spec_source(const rbd_model_desc* d, int algo, int dtype, int has_in2, int has_out1, int flavor, int* stats) {
+  HostModel hm; std::string err;
+  if (build_host_model(d, hm, err) != RBD_OK) return nullptr;
+  SpecKey key; key.algo = algo; key.f64 = dtype == 1; key.has_in2 = has_in2 != 0; key.has_out1 = has_out1 != 0;
+  SpecStats st; std::string out;
+  bool ok;
+  if (flavor == 0) ok = spec_emit_cpu_tu(hm, key, "rbd_spec_cpu", out, &st, err);
+  else if (flavor == 3) ok = spec_emit_cuda_tu(hm, key, spec_default_tuning(hm, key), out, &st, err);
+  else if (flavor == 4) { key.packed = !key.f64; ok = spec_emit_cuda_tu(hm, key, spec_default_tuning(hm, key), out, &st, err); }
+  else ok = spec_emit_function(hm, key, flavor, "rbd_spec_fn", out, &st, err);
+  if (!ok) return nullptr;
+  if (stats) {
+    const int v[12] = {st.nodes_traced, st.nodes_live, st.n_add, st.n_mul, st.n_div, st.n_neg, st.n_sincos, st.n_load, st.n_store,
+                       st.n_sld, st.n_sst, st.stash_rows};
+    for (int k = 0; k < 12; ++k) stats[k] = v[k];
+  }
+  char* r = (char*)malloc(out.size() + 1);
+  std::memcpy(r, out.c_str(), out.size() + 1);
+  return r;
+}
+void hostsim_free(char* p) { free(p); }
+
 int hostsim_integrate(const rbd_model_desc* d, int dtype, int64_t B, void* q, void* v, const void* tau, double dt, int nsteps) {
   HostModel hm; std::string err;
   int rc = build_host_model(d, hm, err);

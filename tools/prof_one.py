@@ -1,5 +1,6 @@
 """Run ONE Atlas floating fp32 dynamics call (batch from argv, default 2^18) -- the target of the ncu captures in profiles/."""
-import sys
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import rigidbodydynamics.jl_b200 as rbd
