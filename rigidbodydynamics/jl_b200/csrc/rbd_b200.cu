@@ -100,12 +100,14 @@ template <class T> struct AbaArgs {
   unsigned long long* counter;   // work queue shared by the two kernels of launch_duo
   int64_t scratch_ld;            // columns of `scratch` (queue kernels)
   int64_t scratch_off;           // first scratch column of the Tensor-Memory kernel's threads (after the shared-memory kernel's)
+  const int* gate;               // non-NULL: run only if *gate != 0 (fallback behind the model-specialised kernels, rbd_spec.cpp)
 };
 
 // KINDS: compile-time promise about the 1-DoF kinds present (kAllKinds, or 0 = revolute / sin-cos-revolute only).
 template <class T, int NT, bool GENERAL, bool EXT, int KINDS>
 __global__ void __launch_bounds__(NT, (sizeof(T) == 4 && !GENERAL && !EXT) ? 20 : 1)
 aba_kernel(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
+  if (a.gate && *a.gate == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   using ST = Stash<T, NT>;
@@ -295,10 +297,12 @@ template <class T> struct RneaArgs {
   int64_t ld, B;
   unsigned long long* counter;
   int64_t scratch_ld, scratch_off;
+  const int* gate;               // see AbaArgs
 };
 
 template <class T, int NT, bool EXT>
 __global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 32 : 1) rnea_kernel(const __grid_constant__ ModelDev<T> M, const RneaArgs<T> a) {
+  if (a.gate && *a.gate == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   const Stash<T, NT> st{sh + threadIdx.x};
@@ -573,16 +577,30 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
   AbaArgs<T> a{(const T*)q, (const T*)v, (const T*)tau, (const T*)wext, (T*)vd, (T*)qd, nullptr, ld, B};
   const int rows = M.nrows;
   const int sr = wext ? 6 * hm.nb : 0;
+  bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
+  for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
+#define RBD_ABA(G, E, K) launch<T>(aba_kernel<T, kNT, G, E, K>, M, a, kNT, rows, sr, stream)
   if (!wext) {      // model-specialised kernels (rbd_spec.cpp): straight-line code generated for this mechanism
     SpecKey key; key.algo = SPEC_ABA; key.f64 = sizeof(T) == 8; key.has_in2 = tau != nullptr; key.has_out1 = qd != nullptr;
     const SpecLaunchArgs sa{q, v, tau, vd, qd, ld, B};
     bool used = false;
     std::string err;
-    if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, err)) return fail(rc, err);
-    if (used) { g_launch.specialised = 1; return RBD_OK; }
+    const int* gate = nullptr;
+    if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, &gate, err)) return fail(rc, err);
+    if (used) {
+      g_launch.specialised = 1;
+      if (!gate) return RBD_OK;
+      // fp32: the specialised program has no slow sin / cos path; if any sample met an angle beyond 1e4 rad (flag raised on the
+      // device) this generic launch redoes the batch with the library path, otherwise it exits at once
+      const rbd_launch_info keep = g_launch;
+      a.gate = gate;
+      const int rc = hm.general ? RBD_ABA(true, false, kAllKinds) : (other_kinds ? RBD_ABA(false, false, kAllKinds) : RBD_ABA(false, false, 0));
+      const int n = g_launch.kernels_launched;
+      g_launch = keep;
+      g_launch.kernels_launched = n;
+      return rc;
+    }
   }
-  bool other_kinds = false;          // prismatic / fixed joints anywhere -> kernels with those code paths
-  for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
   if (!hm.general && !other_kinds && rows <= 256 && (!wext || duo_enabled("RBD_DUO_EXT", kDuoExtDefault))) {
     // Default path for all-revolute trees whose stash fits Tensor Memory: see launch_duo
     constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;
@@ -594,7 +612,6 @@ int dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, con
     if (rc) return rc;
     if (used) return RBD_OK;
   }
-#define RBD_ABA(G, E, K) launch<T>(aba_kernel<T, kNT, G, E, K>, M, a, kNT, rows, sr, stream)
   if (hm.general) return wext ? RBD_ABA(true, true, kAllKinds) : RBD_ABA(true, false, kAllKinds);
   if (other_kinds) return wext ? RBD_ABA(false, true, kAllKinds) : RBD_ABA(false, false, kAllKinds);
   return wext ? RBD_ABA(false, true, 0) : RBD_ABA(false, false, 0);
@@ -613,8 +630,19 @@ int inverse_dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void
     const SpecLaunchArgs sa{q, v, vd, tau, nullptr, ld, B};
     bool used = false;
     std::string err;
-    if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, err)) return fail(rc, err);
-    if (used) { g_launch.specialised = 1; return RBD_OK; }
+    const int* gate = nullptr;
+    if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, &gate, err)) return fail(rc, err);
+    if (used) {
+      g_launch.specialised = 1;
+      if (!gate) return RBD_OK;
+      const rbd_launch_info keep = g_launch;      // gated generic fallback, see dynamics_t
+      a.gate = gate;
+      const int rc = launch<T>(rnea_kernel<T, kNT, false>, M, a, kNT, rows, 0, stream);
+      const int n = g_launch.kernels_launched;
+      g_launch = keep;
+      g_launch.kernels_launched = n;
+      return rc;
+    }
   }
   if (rows <= 256 && duo_enabled("RBD_DUO_RNEA", kDuoRneaDefault) && (!wext || duo_enabled("RBD_DUO_EXT", kDuoExtDefault))) {
     constexpr int kTmWarps = sizeof(T) == 4 ? 8 : 4;

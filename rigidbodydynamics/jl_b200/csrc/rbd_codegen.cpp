@@ -14,7 +14,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 7;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 8;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -67,7 +67,7 @@ struct Emitter {
   std::string out;
   SpecStats stats;
 
-  int convoy_every = 0;      // CUDA flavours: RBD_CONVOY() every this many statements
+  int split_every = 0;           // CUDA flavours: RBD_SPLIT() (a never-taken branch = basic-block boundary) every N statements
   std::vector<int32_t> uses;     // live uses of every node
   std::vector<uint8_t> fused;    // product folded into the FMA of its single consumer
 
@@ -122,15 +122,7 @@ struct Emitter {
   }
   std::string ref(int id) const {
     const SymNode& n = tr.nodes[id];
-    if (n.op == S_CONST) {
-      if (!key.packed) return "RBD_K(" + lit(n.c) + ")";
-      const float f = (float)n.c;
-      uint32_t u;
-      std::memcpy(&u, &f, 4);
-      char buf[48];
-      snprintf(buf, sizeof buf, "RBD_K(0x%08x%08xull)", u, u);      // both halves of the 64-bit operand
-      return buf;
-    }
+    if (n.op == S_CONST) return "RBD_K(" + lit(n.c) + ")";
     return "t" + std::to_string(id);
   }
   static const char* arr_name(int arr) {
@@ -158,8 +150,8 @@ struct Emitter {
       const SymNode& n = N[i];
       if (n.op != S_CONST) ++stats.nodes_live;
       if (fused[i]) continue;
-      if (convoy_every > 0 && n.op != S_CONST && n.op != S_COS && ++since >= convoy_every && !(n.op == S_SLD && n.grp != (int)i)) {
-        out += "RBD_CONVOY();\n";
+      if (split_every > 0 && n.op != S_CONST && n.op != S_COS && ++since >= split_every && !(n.op == S_SLD && n.grp != (int)i)) {
+        out += "RBD_SPLIT();\n";
         since = 0;
       }
       switch (n.op) {
@@ -256,7 +248,7 @@ void regroup_batches(SymTrace& tr, const std::vector<uint8_t>& live) {
 }  // namespace
 
 bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, const std::string& name, std::string& out,
-                        SpecStats* stats, std::string& err, int convoy_every) {
+                        SpecStats* stats, std::string& err) {
   SymTrace tr;
   int rows = 0;
   if (!run_trace(hm, key, tr, rows, err)) return false;
@@ -266,7 +258,12 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
     regroup_batches(tr, pre.live);
   }
   Emitter em(tr, key, flavor);
-  em.convoy_every = flavor == FLAVOR_CPU ? 0 : convoy_every;
+  if (flavor != FLAVOR_CPU) {
+    // One basic block of 10^4 instructions lets ptxas stretch live ranges until it spills (Atlas: 128 registers + 350 B of
+    // local memory, -10 % throughput); a never-taken branch every few hundred statements bounds its scheduling regions.
+    em.split_every = 192;
+    if (const char* e = getenv("RBD_JIT_SPLIT")) em.split_every = atoi(e);
+  }
   em.emit();
   em.stats.stash_rows = rows;
   if (stats) *stats = em.stats;
@@ -276,34 +273,27 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
     sig = std::string("extern \"C\" void ") + name + "(const " + F + "* q, const " + F + "* v, const " + F + "* in2, " + F + "* o0, " +
           F + "* o1, long long ld, " + F + "* sh)";
   } else {
-    sig = std::string("__device__ __forceinline__ void ") + name + "(RBD_IO_ARGS, RBD_STASH_ARG)";
+    sig = std::string("__device__ __forceinline__ void ") + name + "(const rbd_f* __restrict__ q, const rbd_f* __restrict__ v, "
+          "const rbd_f* __restrict__ in2, rbd_f* __restrict__ o0, rbd_f* __restrict__ o1, const long long ld, const bool active, "
+          "int* flag, RBD_STASH_ARG)";
   }
   out += sig + " {\n";
+  if (flavor != FLAVOR_CPU) out += "RBD_FN_BEGIN\n";
   out += em.out;
+  if (flavor != FLAVOR_CPU) out += "RBD_FN_END\n";
   out += "}\n";
   return true;
 }
 
 int spec_stash_rows(const HostModel& hm, const SpecKey& key) { return key.algo == SPEC_ABA ? hm.dev64.nrows : rnea_rows(hm); }
 
-SpecTuning spec_default_tuning(const HostModel& hm, const SpecKey& key) {
-  SpecTuning t;
-  if (const char* e = getenv("RBD_JIT_CONVOY")) t.convoy_every = atoi(e);
-  const int rows = std::max(1, spec_stash_rows(hm, key));
-  const int per_warp = rows * 32 * ((key.f64 || key.packed) ? 8 : 4);
-  t.smem_warps = std::max(1, std::min((key.f64 || key.packed) ? 4 : 8, (227 * 1024 - 64) / per_warp));
-  if (const char* e = getenv("RBD_JIT_SMEM_WARPS")) t.smem_warps = std::max(1, std::min(t.smem_warps, atoi(e)));
-  return t;
-}
-
-uint64_t spec_hash(const HostModel& hm, const SpecKey& key, const SpecTuning& tune) {
+uint64_t spec_hash(const HostModel& hm, const SpecKey& key) {
   uint64_t h = 0xcbf29ce484222325ull;
   auto mix = [&](const void* p, size_t n) {
     const unsigned char* b = (const unsigned char*)p;
     for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ull; }
   };
-  const int hdr[11] = {kGeneratorVersion, key.algo, key.f64, key.has_in2, key.has_out1, key.lower, hm.nb, hm.general,
-                       tune.convoy_every, tune.smem_warps, key.packed};
+  const int hdr[8] = {kGeneratorVersion, key.algo, key.f64, key.has_in2, key.has_out1, key.lower, hm.nb, hm.general};
   mix(hdr, sizeof hdr);
   if (key.f64) {
     const ModelDev<double>& M = hm.dev64;
@@ -315,28 +305,20 @@ uint64_t spec_hash(const HostModel& hm, const SpecKey& key, const SpecTuning& tu
   return h;
 }
 
-bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, const SpecTuning& tune, std::string& out, SpecStats* stats,
-                       std::string& err) {
+bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, std::string& out, SpecStats* stats, std::string& err) {
   char buf[640];
   const int rows = spec_stash_rows(hm, key);
   snprintf(buf, sizeof buf,
-           "#define RBD_SPEC_PACKED %d\n#define RBD_SPEC_F64 %d\n#define RBD_SPEC_NQ %d\n#define RBD_SPEC_NV %d\n#define RBD_SPEC_ROWS %d\n"
+           "#define RBD_SPEC_F64 %d\n#define RBD_SPEC_NQ %d\n#define RBD_SPEC_NV %d\n#define RBD_SPEC_ROWS %d\n"
            "#define RBD_SPEC_HAS_IN2 %d\n#define RBD_SPEC_HAS_OUT1 %d\n#define RBD_SPEC_OUT0_ROWS %d\n#define RBD_SPEC_OUT1_ROWS %d\n"
-           "#define RBD_SMEM_WARPS %d\n%s"
            "#include \"rbd_jit_prelude.cuh\"\n",
-           key.packed ? 1 : 0, key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, hm.nv, hm.nq, tune.smem_warps,
-           tune.convoy_every > 0 ? "" : "#define RBD_CONVOY()\n");
+           key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, hm.nv, hm.nq);
   out += buf;
   out += "#define RBD_FLAVOR_SMEM 1\n#include \"rbd_jit_flavor.cuh\"\n";
-  if (!spec_emit_function(hm, key, FLAVOR_SMEM, "rbd_spec_smem", out, stats, err, tune.convoy_every)) return false;
+  if (!spec_emit_function(hm, key, FLAVOR_SMEM, "rbd_spec_smem", out, stats, err)) return false;
   out += "#undef RBD_FLAVOR_SMEM\n#define RBD_FLAVOR_TMEM 1\n#include \"rbd_jit_flavor.cuh\"\n";
-  if (!spec_emit_function(hm, key, FLAVOR_TMEM, "rbd_spec_tmem", out, nullptr, err, tune.convoy_every)) return false;
+  if (!spec_emit_function(hm, key, FLAVOR_TMEM, "rbd_spec_tmem", out, nullptr, err)) return false;
   out += "#undef RBD_FLAVOR_TMEM\n";
-  if (key.packed) {
-    out += "#define RBD_FLAVOR_SMEM 1\n#define RBD_IO32 1\n#include \"rbd_jit_flavor.cuh\"\n";
-    if (!spec_emit_function(hm, key, FLAVOR_SMEM, "rbd_spec_smem32", out, nullptr, err, tune.convoy_every)) return false;
-    out += "#undef RBD_FLAVOR_SMEM\n#undef RBD_IO32\n";
-  }
   out += "#include \"rbd_jit_kernels.cuh\"\n";
   return true;
 }

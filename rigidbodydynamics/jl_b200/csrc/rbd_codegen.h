@@ -15,13 +15,6 @@ struct SpecKey {
   bool has_in2 = true;   // ABA: tau given (else zero torques); RNEA: vd given (else dynamics_bias)
   bool has_out1 = false; // ABA: q̇ output requested
   bool lower = false;    // CRBA: lower triangle only
-  bool packed = false;   // fp32 only: two samples per thread, packed f32x2 arithmetic (rbd_jit_prelude.cuh)
-};
-
-// Code-shape parameters of the CUDA translation unit (not part of what is computed).
-struct SpecTuning {
-  int convoy_every = 256;   // plant a CTA barrier every this many emitted statements (0 = none)
-  int smem_warps = 8;       // warps per shared-memory CTA
 };
 
 struct SpecStats {
@@ -35,13 +28,10 @@ enum SpecFlavor : int { FLAVOR_CPU = 0, FLAVOR_SMEM = 1, FLAVOR_TMEM = 2 };
 // Body of one per-sample function `name(...)` for the given flavour (see rbd_jit_prelude.cuh for the calling convention).
 // Returns false (with `err`) if the model / key cannot be specialised.
 bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, const std::string& name, std::string& out,
-                        SpecStats* stats, std::string& err, int convoy_every = 0);
+                        SpecStats* stats, std::string& err);
 
 // Whole NVRTC translation unit for `key`: defines + the smem and tmem sample functions + the kernel shells of the prelude.
-bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, const SpecTuning& tune, std::string& out, SpecStats* stats,
-                       std::string& err);
-// Defaults for this model: warps per shared-memory CTA from the stash size, barrier spacing from $RBD_JIT_CONVOY.
-SpecTuning spec_default_tuning(const HostModel& hm, const SpecKey& key);
+bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, std::string& out, SpecStats* stats, std::string& err);
 int spec_stash_rows(const HostModel& hm, const SpecKey& key);
 
 // Self-contained C++ translation unit (needs csrc/ on the include path) defining `extern "C" void name(q, v, in2, o0, o1, ld, sh)`
@@ -50,6 +40,6 @@ bool spec_emit_cpu_tu(const HostModel& hm, const SpecKey& key, const std::string
                       std::string& err);
 
 // 64-bit content hash of a model + key + generator version (cubin cache key).
-uint64_t spec_hash(const HostModel& hm, const SpecKey& key, const SpecTuning& tune);
+uint64_t spec_hash(const HostModel& hm, const SpecKey& key);
 
 }  // namespace rbd

@@ -17,10 +17,9 @@ namespace rbd {
 struct SpecEntry {
   int state = 0;                 // 0 = not tried, 1 = ready, -1 = unavailable (generic kernels are used)
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t k_smem = nullptr, k_tmem = nullptr, k_smem32 = nullptr;   // k_smem32: packed mode, unaligned / odd-tail I/O
+  cudaKernel_t k_smem = nullptr, k_tmem = nullptr;
   int regs_smem = 0, regs_tmem = 0;
   int rows = 0;
-  int smem_warps = 8;            // warps per shared-memory CTA (SpecTuning)
   bool from_cache = false;
   std::string why;               // reason for state -1
 };
@@ -43,7 +42,7 @@ struct rbd_model {
   int side_device = -1;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t fork_ev[rbd::kEventRing] = {}, join_ev[rbd::kEventRing] = {};
-  unsigned long long* counters = nullptr;     // [kCounterRing] device memory
+  unsigned long long* counters = nullptr;     // [kCounterRing][2] device memory: work-queue counter, "needs generic kernel" flag
   unsigned next_call = 0;
   // model-specialised kernels, keyed by SpecKey bits
   std::mutex spec_mu;
@@ -57,12 +56,13 @@ struct PairCtx {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
   unsigned long long* counter = nullptr;
+  int* flag = nullptr;       // zeroed with the counter; raised by a specialised kernel that met an angle beyond its fast sin / cos
 };
 // Returns a cudaError_t (cudaSuccess = 0).
 cudaError_t pair_begin(rbd_model* m, cudaStream_t stream, PairCtx& ctx);
 
 inline uint32_t spec_key_bits(const SpecKey& k) {
-  return (uint32_t)k.algo | (k.f64 ? 8u : 0u) | (k.has_in2 ? 16u : 0u) | (k.has_out1 ? 32u : 0u) | (k.lower ? 64u : 0u) | (k.packed ? 128u : 0u);
+  return (uint32_t)k.algo | (k.f64 ? 8u : 0u) | (k.has_in2 ? 16u : 0u) | (k.has_out1 ? 32u : 0u) | (k.lower ? 64u : 0u);
 }
 
 struct SpecLaunchArgs {
@@ -72,8 +72,10 @@ struct SpecLaunchArgs {
 };
 // Tries the model-specialised kernels for (model, key).  `used` = false (and RBD_OK) when they are unavailable, not yet
 // compiled and the batch is below the compile threshold, or the batch is too small: the caller then runs the generic kernels.
+// `gate` (fp32 only, else NULL): device flag the specialised kernels raise when a sample needs the library sin / cos; the caller
+// must enqueue the generic kernel gated on it right behind.
 int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, cudaStream_t stream, bool& used,
-                    rbd_launch_info& li, std::string& err);
+                    rbd_launch_info& li, const int** gate, std::string& err);
 // Compile (or load from the cubin cache) without launching; RBD_OK / RBD_EUNSUPPORTED.
 int spec_prepare(rbd_model* m, const SpecKey& key, bool load_on_device, std::string& err);
 void spec_release(rbd_model* m);

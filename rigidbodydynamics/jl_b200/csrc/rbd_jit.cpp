@@ -35,7 +35,9 @@ Nvrtc& nvrtc() {
   static Nvrtc n;
   static std::once_flag once;
   std::call_once(once, [] {
-    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    // the toolkit's own NVRTC first (by path): by soname dlopen would hand back whatever libnvrtc.so.12 the process has
+    // already loaded (PyTorch bundles an older one)
+    const char* names[] = {"/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so.12", "libnvrtc.so"};
     for (const char* nm : names) {
       n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
       if (n.h) break;
@@ -54,10 +56,10 @@ bool dir_writable(const std::string& d) {
   return access(d.c_str(), W_OK | X_OK) == 0;
 }
 
-std::string key_name(const HostModel& hm, const SpecKey& k, const SpecTuning& tune) {
+std::string key_name(const HostModel& hm, const SpecKey& k) {
   char buf[96];
   const char* algo = k.algo == SPEC_ABA ? "aba" : (k.algo == SPEC_RNEA ? "rnea" : "crba");
-  snprintf(buf, sizeof buf, "%016llx_%s_%s_%d%d%d", (unsigned long long)spec_hash(hm, k, tune), algo, k.f64 ? "f64" : (k.packed ? "f32x2" : "f32"),
+  snprintf(buf, sizeof buf, "%016llx_%s_%s_%d%d%d", (unsigned long long)spec_hash(hm, k), algo, k.f64 ? "f64" : "f32",
            (int)k.has_in2, (int)k.has_out1, (int)k.lower);
   return buf;
 }
@@ -105,9 +107,9 @@ std::string jit_cache_dir() {
   return "/tmp";
 }
 
-bool jit_get_cubin(const HostModel& hm, const SpecKey& key, const SpecTuning& tune, std::vector<char>& cubin, bool compile_if_missing,
-                   bool* from_cache, SpecStats* stats, std::string& err) {
-  const std::string path = jit_cache_dir() + "/" + key_name(hm, key, tune) + ".cubin";
+bool jit_get_cubin(const HostModel& hm, const SpecKey& key, std::vector<char>& cubin, bool compile_if_missing, bool* from_cache,
+                   SpecStats* stats, std::string& err) {
+  const std::string path = jit_cache_dir() + "/" + key_name(hm, key) + ".cubin";
   if (from_cache) *from_cache = false;
   if (!getenv("RBD_JIT_NO_CACHE") && read_file(path, cubin)) {
     if (from_cache) *from_cache = true;
@@ -117,7 +119,7 @@ bool jit_get_cubin(const HostModel& hm, const SpecKey& key, const SpecTuning& tu
   Nvrtc& n = nvrtc();
   if (!n.h) { err = n.err; return false; }
   std::string src;
-  if (!spec_emit_cuda_tu(hm, key, tune, src, stats, err)) return false;
+  if (!spec_emit_cuda_tu(hm, key, src, stats, err)) return false;
   const int nh = (int)(sizeof(kEmbeddedHeaders) / sizeof(kEmbeddedHeaders[0]));
   std::vector<const char*> hn, ht;
   for (int i = 0; i < nh; ++i) { hn.push_back(kEmbeddedHeaders[i].name); ht.push_back(kEmbeddedHeaders[i].text); }

@@ -13,8 +13,8 @@ namespace rbd {
 
 // Compiles (or fetches from the cache) the cubin for (model, key).  `from_cache` reports a cache hit.  Returns false with
 // `err` set when NVRTC is unavailable or compilation fails -- callers fall back to the generic kernels.
-bool jit_get_cubin(const HostModel& hm, const SpecKey& key, const SpecTuning& tune, std::vector<char>& cubin, bool compile_if_missing,
-                   bool* from_cache, SpecStats* stats, std::string& err);
+bool jit_get_cubin(const HostModel& hm, const SpecKey& key, std::vector<char>& cubin, bool compile_if_missing, bool* from_cache,
+                   SpecStats* stats, std::string& err);
 
 // Directory of the cubin cache: $RBD_JIT_CACHE, else <directory of librbd_b200.so>/jit_cache, else ~/.cache/rbd_b200.
 std::string jit_cache_dir();

@@ -30,21 +30,8 @@ RBD_HD int float_bits(float x) {
   int i; std::memcpy(&i, &x, sizeof(i)); return i;
 #endif
 }
-// huge / non-finite angles: library path, kept OUT of line (it is ~150 instructions of Payne-Hanek reduction that would
-// otherwise be inlined at every call site of the fully unrolled model-specialised kernels)
-#if defined(__CUDACC__)
-__device__ __noinline__ float2 sincos_slow(float x) { float2 r; sincosf(x, &r.x, &r.y); return r; }
-#endif
-RBD_HD void sincos_t(float x, float& s, float& c) {
-  if (__builtin_expect(!(x >= -1.0e4f && x <= 1.0e4f), 0)) {
-#if defined(__CUDA_ARCH__)
-    const float2 r = sincos_slow(x);      // by value: s and c stay in registers at the call site
-    s = r.x; c = r.y;
-#else
-    s = std::sin(x); c = std::cos(x);
-#endif
-    return;
-  }
+// Fast path: accurate for |x| <= 1e4 (see above); callers are responsible for larger / non-finite arguments.
+RBD_HD void sincos_fast(float x, float& s, float& c) {
   const float t = fma_f(x, 0.6366197466850281f, 12582912.0f);   // 1.5 * 2^23: low mantissa bits = round(x * 2/pi)
   const int n = float_bits(t);
   const float j = t - 12582912.0f;
@@ -62,6 +49,22 @@ RBD_HD void sincos_t(float x, float& s, float& c) {
   const float cc = (n & 1) ? sr : cr;
   s = (n & 2) ? -ss : ss;
   c = ((n + 1) & 2) ? -cc : cc;
+}
+// huge / non-finite angles: library path, kept OUT of line (~150 instructions of Payne-Hanek reduction per call site otherwise)
+#if defined(__CUDACC__)
+__device__ __noinline__ float2 sincos_slow(float x) { float2 r; sincosf(x, &r.x, &r.y); return r; }
+#endif
+RBD_HD void sincos_t(float x, float& s, float& c) {
+  if (!(x >= -1.0e4f && x <= 1.0e4f)) {
+#if defined(__CUDA_ARCH__)
+    const float2 r = sincos_slow(x);      // by value: s and c stay in registers at the call site
+    s = r.x; c = r.y;
+#else
+    s = std::sin(x); c = std::cos(x);
+#endif
+    return;
+  }
+  sincos_fast(x, s, c);
 }
 RBD_HD void sincos_t(double x, double& s, double& c) {
 #if defined(__CUDA_ARCH__)

@@ -137,7 +137,7 @@ void run_integrate(const HostModel& hm, int64_t B, T* q, T* v, const T* tau, dou
 
 extern "C" {
 // Model-specialised program (csrc/rbd_codegen.cpp) for the mechanism: flavor 0 = self-contained C++ (one sample per call),
-// 1 / 2 = the per-sample CUDA function bodies, 3 = the whole NVRTC translation unit, 4 = same in packed-fp32 mode.  Returns a malloc'ed string (free with
+// 1 / 2 = the per-sample CUDA function bodies, 3 = the whole NVRTC translation unit.  Returns a malloc'ed string (free with
 // hostsim_free) or NULL; stats = {nodes_traced, nodes_live, add, mul, div, neg, sincos, load, store, sld, sst, stash_rows}.
 char* hostsim_spec_source(const rbd_model_desc* d, int algo, int dtype, int has_in2, int has_out1, int flavor, int* stats) {
   HostModel hm; std::string err;
@@ -146,8 +146,7 @@ char* hostsim_spec_source(const rbd_model_desc* d, int algo, int dtype, int has_
   SpecStats st; std::string out;
   bool ok;
   if (flavor == 0) ok = spec_emit_cpu_tu(hm, key, "rbd_spec_cpu", out, &st, err);
-  else if (flavor == 3) ok = spec_emit_cuda_tu(hm, key, spec_default_tuning(hm, key), out, &st, err);
-  else if (flavor == 4) { key.packed = !key.f64; ok = spec_emit_cuda_tu(hm, key, spec_default_tuning(hm, key), out, &st, err); }
+  else if (flavor == 3) ok = spec_emit_cuda_tu(hm, key, out, &st, err);
   else ok = spec_emit_function(hm, key, flavor, "rbd_spec_fn", out, &st, err);
   if (!ok) return nullptr;
   if (stats) {

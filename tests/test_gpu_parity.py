@@ -85,8 +85,9 @@ def test_host_pointer_entry_point(built):
     rbd._cabi.check(lib.rbd_dynamics_host(state.handle.ptr, 0, B, B, hq.data_ptr(), hv.data_ptr(), ht.data_ptr(), None,
                                           out.data_ptr(), None))
     assert np.array_equal(out.numpy().astype(np.float64), got_dev)
-    # two chunks; the full one runs as the shared-memory + Tensor-Memory kernel pair, the 777-sample tail as one kernel
-    assert rbd.launch_info().kernels_launched in (2, 3, 4)
+    # two chunks; the full one runs as a shared-memory + Tensor-Memory kernel pair, the 777-sample tail as one kernel (each
+    # followed by the gated generic fallback when the model-specialised kernels serve the call)
+    assert 2 <= rbd.launch_info().kernels_launched <= 6
 
 
 def test_errors_match_reference_behaviour(built):
@@ -351,13 +352,16 @@ def test_large_batch_uses_tensor_memory_path(built, dtype):
     tau = torch.rand((36, B), dtype=dtype, device="cuda")
     res = rbd.DynamicsResult(mech, B, dtype)
     rbd.dynamics_(res, st, tau, want_qd=False)
-    assert rbd.launch_info().kernels_launched == 2
+    info = rbd.launch_info()
+    # the pair, plus -- when the fp32 model-specialised kernels serve the call -- the gated generic fallback behind them
+    assert info.kernels_launched == (3 if info.specialised and dtype == torch.float32 else 2)
     idx = torch.arange(0, B, 509, device="cuda")
     sub = rbd.MechanismState(mech, idx.numel(), dtype)
     sub.q.copy_(st.q[:, idx]); sub.v.copy_(st.v[:, idx])
     res2 = rbd.DynamicsResult(mech, idx.numel(), dtype)
     rbd.dynamics_(res2, sub, tau[:, idx].contiguous(), want_qd=False)
-    assert rbd.launch_info().kernels_launched == 1
+    info2 = rbd.launch_info()
+    assert info2.kernels_launched == (2 if info2.specialised and dtype == torch.float32 else 1)
     assert torch.equal(res2.vd, res.vd[:, idx])
     ref = Oracle(mech.flatten()).dynamics(sub.q.double().cpu().numpy(), sub.v.double().cpu().numpy(),
                                           tau[:, idx].double().cpu().numpy())
