@@ -14,7 +14,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 8;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 11;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -145,6 +145,7 @@ struct Emitter {
     char line[256];
     stats.nodes_traced = (int)N.size();
     int since = 0;
+    size_t sst_done = 0;
     for (size_t i = 0; i < N.size(); ++i) {
       if (!live[i]) continue;
       const SymNode& n = N[i];
@@ -197,7 +198,7 @@ struct Emitter {
           break;
         case S_SLD: {
           ++stats.n_sld;
-          if (flavor != FLAVOR_TMEM) {
+          if (flavor != FLAVOR_TMEM && flavor != FLAVOR_UNI) {
             snprintf(line, sizeof line, "const rbd_v t%zu = RBD_SLD(%d);\n", i, n.row);
             out += line;
             break;
@@ -209,6 +210,21 @@ struct Emitter {
           bool any = false;
           for (size_t k = i; k < e; ++k) if (live[k]) any = true;
           if (!any) break;
+          if (flavor == FLAVOR_UNI) {          // one warp-uniform branch per batch: Tensor Memory or shared memory
+            for (size_t k = i; k < e; ++k)
+              if (live[k]) { snprintf(line, sizeof line, "rbd_v t%zu;\n", k); out += line; }
+            out += "if (use_tm) {\n";
+            for (size_t k = i; k < e; ++k)
+              if (live[k]) { snprintf(line, sizeof line, "RBD_TM_REG u%zu; RBD_TM_LD(u%zu, %d);\n", k, k, N[k].row); out += line; }
+            out += "RBD_TM_WAIT_LD();\n";
+            for (size_t k = i; k < e; ++k)
+              if (live[k]) { snprintf(line, sizeof line, "t%zu = RBD_TM_VAL(u%zu);\n", k, k); out += line; }
+            out += "} else {\n";
+            for (size_t k = i; k < e; ++k)
+              if (live[k]) { snprintf(line, sizeof line, "t%zu = RBD_SLD(%d);\n", k, N[k].row); out += line; }
+            out += "}\n";
+            break;
+          }
           for (size_t k = i; k < e; ++k)
             if (live[k]) { snprintf(line, sizeof line, "RBD_TM_REG u%zu; RBD_TM_LD(u%zu, %d);\n", k, k, N[k].row); out += line; }
           out += "RBD_TM_WAIT_LD();\n";
@@ -216,11 +232,27 @@ struct Emitter {
             if (live[k]) { snprintf(line, sizeof line, "const rbd_v t%zu = RBD_TM_VAL(u%zu);\n", k, k); out += line; }
           break;
         }
-        case S_SST:
+        case S_SST: {
           ++stats.n_sst;
-          snprintf(line, sizeof line, "RBD_SST(%d, %s);\n", n.row, ref(n.a).c_str());
-          out += line;
+          if (flavor != FLAVOR_UNI) {
+            snprintf(line, sizeof line, "RBD_SST(%d, %s);\n", n.row, ref(n.a).c_str());
+            out += line;
+            break;
+          }
+          if (sst_done > i) break;             // part of a run already emitted
+          // run of adjacent stash stores (only dead nodes / constants in between): one warp-uniform branch for the run
+          size_t e = i;
+          std::vector<size_t> run;
+          while (e < N.size() && (N[e].op == S_SST || !live[e] || N[e].op == S_CONST || fused[e])) { if (N[e].op == S_SST) run.push_back(e); ++e; }
+          sst_done = e;
+          stats.n_sst += (int)run.size() - 1;
+          out += "if (use_tm) {\n";
+          for (size_t k : run) { snprintf(line, sizeof line, "RBD_TM_ST(%d, %s);\n", N[k].row, ref(N[k].a).c_str()); out += line; }
+          out += "} else {\n";
+          for (size_t k : run) { snprintf(line, sizeof line, "RBD_SST(%d, %s);\n", N[k].row, ref(N[k].a).c_str()); out += line; }
+          out += "}\n";
           break;
+        }
         case S_SFENCE: out += "RBD_SFENCE();\n"; break;
         case S_XLD: snprintf(line, sizeof line, "const rbd_v t%zu = RBD_XLD(%d);\n", i, n.row); out += line; break;
         case S_XST: snprintf(line, sizeof line, "RBD_XST(%d, %s);\n", n.row, ref(n.a).c_str()); out += line; break;
@@ -287,6 +319,13 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
 
 int spec_stash_rows(const HostModel& hm, const SpecKey& key) { return key.algo == SPEC_ABA ? hm.dev64.nrows : rnea_rows(hm); }
 
+int spec_uni_smem_warps(const HostModel& hm, const SpecKey& key) {
+  const int per_warp = std::max(1, spec_stash_rows(hm, key)) * 32 * (key.f64 ? 8 : 4);
+  const int fit = (227 * 1024 - 1024) / per_warp;
+  const int want = key.f64 ? 4 : 8;
+  return fit >= want ? want : (fit >= 4 ? 4 : 0);
+}
+
 uint64_t spec_hash(const HostModel& hm, const SpecKey& key) {
   uint64_t h = 0xcbf29ce484222325ull;
   auto mix = [&](const void* p, size_t n) {
@@ -311,14 +350,17 @@ bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, std::string& out
   snprintf(buf, sizeof buf,
            "#define RBD_SPEC_F64 %d\n#define RBD_SPEC_NQ %d\n#define RBD_SPEC_NV %d\n#define RBD_SPEC_ROWS %d\n"
            "#define RBD_SPEC_HAS_IN2 %d\n#define RBD_SPEC_HAS_OUT1 %d\n#define RBD_SPEC_OUT0_ROWS %d\n#define RBD_SPEC_OUT1_ROWS %d\n"
-           "#include \"rbd_jit_prelude.cuh\"\n",
-           key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, hm.nv, hm.nq);
+           "#define RBD_UNI_SW %d\n#include \"rbd_jit_prelude.cuh\"\n",
+           key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, hm.nv, hm.nq,
+           std::max(4, spec_uni_smem_warps(hm, key)));
   out += buf;
   out += "#define RBD_FLAVOR_SMEM 1\n#include \"rbd_jit_flavor.cuh\"\n";
   if (!spec_emit_function(hm, key, FLAVOR_SMEM, "rbd_spec_smem", out, stats, err)) return false;
   out += "#undef RBD_FLAVOR_SMEM\n#define RBD_FLAVOR_TMEM 1\n#include \"rbd_jit_flavor.cuh\"\n";
   if (!spec_emit_function(hm, key, FLAVOR_TMEM, "rbd_spec_tmem", out, nullptr, err)) return false;
-  out += "#undef RBD_FLAVOR_TMEM\n";
+  out += "#undef RBD_FLAVOR_TMEM\n#define RBD_FLAVOR_UNI 1\n#include \"rbd_jit_flavor.cuh\"\n";
+  if (!spec_emit_function(hm, key, FLAVOR_UNI, "rbd_spec_uni", out, nullptr, err)) return false;
+  out += "#undef RBD_FLAVOR_UNI\n";
   out += "#include \"rbd_jit_kernels.cuh\"\n";
   return true;
 }

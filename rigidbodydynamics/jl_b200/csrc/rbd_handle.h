@@ -17,8 +17,10 @@ namespace rbd {
 struct SpecEntry {
   int state = 0;                 // 0 = not tried, 1 = ready, -1 = unavailable (generic kernels are used)
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t k_smem = nullptr, k_tmem = nullptr;
-  int regs_smem = 0, regs_tmem = 0;
+  cudaKernel_t k_smem = nullptr, k_tmem = nullptr, k_uni = nullptr;   // shared-memory blocks / Tensor-Memory CTA / unified CTA
+  int regs_smem = 0, regs_tmem = 0, regs_uni = 0;
+  int choice = 0;                // 0 = not tuned yet, 1 = kernel pair, 2 = unified CTA (for batches that fill the SMs)
+  int uni_sw = 0;                // warps with a shared-memory stash in the unified CTA (0 = unified kernel unusable)
   int rows = 0;
   bool from_cache = false;
   std::string why;               // reason for state -1

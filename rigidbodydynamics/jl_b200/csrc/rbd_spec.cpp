@@ -15,16 +15,16 @@ namespace {
 struct Env {
   bool jit = true, no_tmem = false, force_pair = false, no_gate = false;
   int64_t min_batch = 1 << 15;      // below this a missing cubin is not compiled on the fly (generic kernels serve the call)
-  const char* only = nullptr;       // RBD_ONLY=smem|tmem: launch one kernel of the pair (profiling aid)
   int smem_blocks = 0;
+  int variant = 0;                  // RBD_JIT_VARIANT=1 (pair) / 2 (unified): skip the tuning
   Env() {
     if (const char* e = getenv("RBD_JIT")) jit = e[0] != '0';
     no_tmem = getenv("RBD_NO_TMEM") != nullptr;
     force_pair = getenv("RBD_FORCE_PAIR") != nullptr;       // experiments only
     no_gate = getenv("RBD_NO_GATE") != nullptr;
     if (const char* e = getenv("RBD_JIT_MIN_BATCH")) min_batch = atoll(e);
-    only = getenv("RBD_ONLY");
     if (const char* e = getenv("RBD_SMEM_BLOCKS")) smem_blocks = atoi(e);
+    if (const char* e = getenv("RBD_JIT_VARIANT")) variant = atoi(e);
   }
 };
 const Env& env() { static const Env e; return e; }
@@ -109,14 +109,19 @@ int spec_prepare(rbd_model* m, const SpecKey& key, bool load_on_device, std::str
   cudaError_t e = cudaLibraryLoadData(&se.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&se.k_smem, se.lib, "rbd_jit_smem");
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&se.k_tmem, se.lib, "rbd_jit_tmem");
+  if (e == cudaSuccess) e = cudaLibraryGetKernel(&se.k_uni, se.lib, "rbd_jit_uni");
   cudaFuncAttributes fa{};
   if (e == cudaSuccess) { e = cudaFuncGetAttributes(&fa, (const void*)se.k_smem); se.regs_smem = fa.numRegs; }
   if (e == cudaSuccess) { e = cudaFuncGetAttributes(&fa, (const void*)se.k_tmem); se.regs_tmem = fa.numRegs; }
+  if (e == cudaSuccess) { e = cudaFuncGetAttributes(&fa, (const void*)se.k_uni); se.regs_uni = fa.numRegs; }
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)se.k_tmem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   se.rows = spec_stash_rows(m->hm, key);
   const size_t smem = (size_t)std::max(1, se.rows) * 32 * (key.f64 ? 8 : 4);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)se.k_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)se.k_smem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)se.k_tmem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  se.uni_sw = spec_uni_smem_warps(m->hm, key);
+  if (e == cudaSuccess && se.uni_sw > 0) e = cudaFuncSetAttribute((const void*)se.k_uni, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * se.uni_sw));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)se.k_uni, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) {
     cudaGetLastError();
     se.state = -1;
@@ -165,40 +170,80 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
     err = cudaGetErrorString(e); return RBD_ECUDA;
   }
   if (bps < 1) return RBD_OK;
-  // Register-file room for the Tensor-Memory CTA next to the shared-memory blocks.  The pair only pays when shared memory (not
-  // the register file) limits the single kernel's residency, and when there is enough work for both kernels' warps.
+  // Three ways to fill an SM (rbd_jit_kernels.cuh): shared-memory blocks alone, the kernel pair, the unified CTA.  The two
+  // Tensor-Memory variants are used when they put at least 15 % more warps on the SM than shared memory alone and there is work
+  // for them; which of the two is decided by timing both once, on the first call large enough to tell (not while capturing).
+  if (ev.smem_blocks > 0) bps = std::max(1, std::min(bps, ev.smem_blocks));
   const int rs = ((se->regs_smem + 7) / 8) * 8 * 32, rt = ((se->regs_tmem + 7) / 8) * 8 * 32 * tm_warps;
-  int bps_pair = std::max(1, std::min(bps, (65536 - rt) / rs));
-  bool pair = !ev.no_tmem && (bps_pair + tm_warps) * 100 >= bps * 115;
-  if (ev.smem_blocks > 0) { bps_pair = std::max(1, std::min(bps_pair, ev.smem_blocks)); bps = std::max(1, std::min(bps, ev.smem_blocks)); }
-  if (ev.force_pair) pair = true;
-  if (pair && ngroups < (int64_t)(bps_pair + tm_warps / 2) * p.sms) pair = false;
-  PairCtx ctx;
-  if (cudaError_t e = pair_begin(m, stream, ctx)) { err = cudaGetErrorString(e); return RBD_ECUDA; }
-  struct { const void* q; const void* v; const void* in2; void* o0; void* o1; long long ld, B; unsigned long long* counter; int* flag; } ka =
-      {a.q, a.v, a.in2, a.o0, a.o1, (long long)a.ld, (long long)a.B, ctx.counter, ctx.flag};
-  void* params[] = {&ka};
-  cudaError_t e = cudaSuccess;
+  const int bps_pair = std::max(1, std::min(bps, (65536 - rt) / rs));
+  const bool pair_ok = !ev.no_tmem && rt + rs <= 65536 && (bps_pair + tm_warps) * 100 >= bps * 115 &&
+                       ngroups >= (int64_t)(bps_pair + tm_warps / 2) * p.sms;
+  const int uni_warps = se->uni_sw > 0 ? se->uni_sw + tm_warps : 0;
+  const bool uni_ok = !ev.no_tmem && uni_warps * 100 >= bps * 115 && ((se->regs_uni + 7) / 8) * 8 * 32 * uni_warps <= 65536 &&
+                      ngroups >= (int64_t)(uni_warps - tm_warps / 2) * p.sms;
+  struct KArgs { const void* q; const void* v; const void* in2; void* o0; void* o1; long long ld, B; unsigned long long* counter; int* flag; };
   int launched = 0;
-  if (pair) {
-    const bool do_s = !ev.only || ev.only[0] == 's', do_t = !ev.only || ev.only[0] == 't';
-    e = cudaEventRecord(ctx.fork, stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx.side, ctx.fork, 0);
-    if (e == cudaSuccess && do_s) { e = cudaLaunchKernel((const void*)se->k_smem, dim3(bps_pair * p.sms), dim3(32), params, smem, stream); ++launched; }
-    if (e == cudaSuccess && do_t) { e = cudaLaunchKernel((const void*)se->k_tmem, dim3(p.sms), dim3(32 * tm_warps), params, 0, ctx.side); ++launched; }
-    if (e == cudaSuccess) e = cudaEventRecord(ctx.join, ctx.side);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, ctx.join, 0);
-    li.grid = bps_pair * p.sms; li.blocks_per_sm = bps_pair;
-  } else {
-    const int grid = (int)std::min<int64_t>(ngroups, (int64_t)bps * p.sms);
-    e = cudaLaunchKernel((const void*)se->k_smem, dim3(grid), dim3(32), params, smem, stream);
-    ++launched;
-    li.grid = grid; li.blocks_per_sm = bps;
-  }
+  int* last_flag = nullptr;
+  auto run = [&](int variant) -> cudaError_t {        // 0 = shared memory alone, 1 = pair, 2 = unified
+    PairCtx ctx;
+    cudaError_t e = pair_begin(m, stream, ctx);
+    if (e != cudaSuccess) return e;
+    KArgs ka = {a.q, a.v, a.in2, a.o0, a.o1, (long long)a.ld, (long long)a.B, ctx.counter, ctx.flag};
+    void* params[] = {&ka};
+    if (variant == 2) {
+      e = cudaLaunchKernel((const void*)se->k_uni, dim3(p.sms), dim3(32 * uni_warps), params, smem * se->uni_sw, stream);
+      ++launched;
+      li.grid = p.sms; li.block = 32 * uni_warps; li.blocks_per_sm = 1; li.smem_bytes = (int)(smem * se->uni_sw);
+    } else if (variant == 1) {
+      e = cudaEventRecord(ctx.fork, stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx.side, ctx.fork, 0);
+      if (e == cudaSuccess) { e = cudaLaunchKernel((const void*)se->k_smem, dim3(bps_pair * p.sms), dim3(32), params, smem, stream); ++launched; }
+      if (e == cudaSuccess) { e = cudaLaunchKernel((const void*)se->k_tmem, dim3(p.sms), dim3(32 * tm_warps), params, 0, ctx.side); ++launched; }
+      if (e == cudaSuccess) e = cudaEventRecord(ctx.join, ctx.side);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, ctx.join, 0);
+      li.grid = bps_pair * p.sms; li.block = 32; li.blocks_per_sm = bps_pair; li.smem_bytes = (int)smem;
+    } else {
+      const int grid = (int)std::min<int64_t>(ngroups, (int64_t)bps * p.sms);
+      e = cudaLaunchKernel((const void*)se->k_smem, dim3(grid), dim3(32), params, smem, stream);
+      ++launched;
+      li.grid = grid; li.block = 32; li.blocks_per_sm = bps; li.smem_bytes = (int)smem;
+    }
+    last_flag = ctx.flag;
+    return e;
+  };
+  cudaError_t e = cudaSuccess;
+  int variant = 0;
+  if (pair_ok && uni_ok) {
+    variant = ev.variant ? ev.variant : se->choice;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    if (variant == 0 && cap == cudaStreamCaptureStatusNone && a.B >= (int64_t)p.sms * 32 * 64) {
+      // tune: each variant once to warm up, then timed; outputs are simply overwritten with the same values
+      float best = 0.f;
+      cudaEvent_t t0, t1;
+      cudaEventCreate(&t0); cudaEventCreate(&t1);
+      for (int v = 1; v <= 2 && e == cudaSuccess; ++v) {
+        e = run(v);
+        if (e == cudaSuccess) e = cudaEventRecord(t0, stream);
+        if (e == cudaSuccess) e = run(v);
+        if (e == cudaSuccess) e = cudaEventRecord(t1, stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(t1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, t0, t1);
+        if (e == cudaSuccess && (variant == 0 || ms < best)) { best = ms; variant = v; }
+      }
+      cudaEventDestroy(t0); cudaEventDestroy(t1);
+      if (e == cudaSuccess) se->choice = variant;
+      launched = 0;
+    }
+    if (variant == 0) variant = 1;
+  } else if (uni_ok) variant = 2;
+  else if (pair_ok) variant = 1;
+  if (ev.force_pair && uni_warps) variant = 2;
+  if (e == cudaSuccess) e = run(variant);
   if (e != cudaSuccess) { err = std::string("specialised kernel launch: ") + cudaGetErrorString(e); return RBD_ECUDA; }
   li.kernels_launched += launched;
-  li.block = 32; li.smem_bytes = (int)smem;
-  if (gate && !key.f64 && !ev.no_gate) *gate = ctx.flag;
+  if (gate && !key.f64 && !ev.no_gate) *gate = last_flag;
   used = true;
   return RBD_OK;
 }
