@@ -149,6 +149,7 @@ int32_t rbd_get_launch_info(rbd_launch_info* info);
 #define RBD_SPEC_DYNAMICS_NOTAU 4    /* ... with the zero-torque default (with / without q̇) */
 #define RBD_SPEC_INVERSE_DYNAMICS 8  /* inverse_dynamics!                                */
 #define RBD_SPEC_DYNAMICS_BIAS 16    /* dynamics_bias!                                   */
+#define RBD_SPEC_DYNAMICS_GATHER 32  /* rbd_dynamics_gather (stores to peer GPUs)        */
 int32_t rbd_model_precompile(rbd_model* model, int32_t dtype, int32_t what, int32_t load);
 
 /*
@@ -161,6 +162,21 @@ int32_t rbd_model_precompile(rbd_model* model, int32_t dtype, int32_t what, int3
  */
 int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                      const void* tau, const void* wext, void* vd_out, void* qd_out, void* stream);
+
+/*
+ * dynamics! on a batch SHARDED over the GPUs of one box, with the result gather fused into the kernel (BASELINE
+ * config 5).  Every process evaluates its own B samples exactly like rbd_dynamics, but v̇ is written into the GATHERED array
+ * [nv x peer_ld] of EVERY GPU: vd_peers[p] is GPU p's array (peer-mapped into this process: CUDA IPC / symmetric memory / VMM;
+ * this GPU's own array is one of them) and sample b lands in column col0 + b of each.  The output store is the gather: remote
+ * rows are posted writes over NVLink / NVSwitch, no collective follows, and nothing in the kernel waits for them.  The caller
+ * synchronises the GPUs (a barrier after the stream has drained) before reading the gathered arrays.
+ * vd_multicast: NVLS multicast mapping of the same arrays (cuMulticast* / symmetric memory's multicast pointer) or NULL; with it
+ * each row is ONE multimem.st that the NVSwitch replicates to all GPUs instead of npeers stores.
+ * tau may be NULL (zero torques).  fp32 / fp64; no external wrenches / q̇ in this entry point.
+ */
+int32_t rbd_dynamics_gather(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                            const void* tau, int32_t npeers, void* const* vd_peers, void* vd_multicast, int64_t peer_ld,
+                            int64_t col0, void* stream);
 
 /* inverse_dynamics!(torquesout, jointwrenchesout, accelerations, state, v̇, externalwrenches)
  *                                                             src/mechanism_algorithms.jl:542-553

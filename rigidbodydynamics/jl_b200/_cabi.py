@@ -16,7 +16,8 @@ RBD_MAX_BODIES = 64
 RBD_OK, RBD_EINVAL, RBD_EDIM, RBD_ELOOP, RBD_ESTALE, RBD_ECUDA, RBD_EUNSUPPORTED, RBD_ENOMEM = range(8)
 RBD_F32, RBD_F64, RBD_DUAL64X6 = 0, 1, 2
 RBD_SPEC_DYNAMICS, RBD_SPEC_DYNAMICS_QDOT, RBD_SPEC_DYNAMICS_NOTAU, RBD_SPEC_INVERSE_DYNAMICS, RBD_SPEC_DYNAMICS_BIAS = 1, 2, 4, 8, 16
-RBD_SPEC_ALL = 31
+RBD_SPEC_DYNAMICS_GATHER = 32
+RBD_SPEC_ALL = 63
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librbd_b200.so")
@@ -105,6 +106,7 @@ SYMBOLS = {
     "rbd_get_launch_info": (c_int32, [POINTER(RbdLaunchInfo)]),
     "rbd_model_precompile": (c_int32, [_vp, _i32, _i32, _i32]),
     "rbd_dynamics": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rbd_dynamics_gather": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _i32, POINTER(_vp), _vp, _i64, _i64, _vp]),
     "rbd_inverse_dynamics": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rbd_dynamics_bias": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rbd_mass_matrix": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp]),

@@ -877,6 +877,79 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
   return rc;
 }
 
+// rbd_dynamics_gather.  Fast path: the model-specialised kernels store v̇ straight into every GPU's gathered array (peer-mapped
+// memory, posted writes over NVLink) -- the output store IS the gather.  Fallback (no specialised kernel for this model / dtype,
+// or -- gated on their flag -- a sample beyond their fast sin / cos range): the generic kernels evaluate into a dense scratch
+// and this kernel scatters it to the peers.
+template <class T> struct ScatterArgs {
+  const T* src; int64_t src_ld;
+  T* dst[8]; int64_t dst_ld;
+  int ndst, rows;
+  int64_t B;
+  const int* gate;
+};
+template <class T> __global__ void __launch_bounds__(256) gather_scatter_kernel(const ScatterArgs<T> a) {
+  if (a.gate && *a.gate == 0) return;
+  const int64_t total = (int64_t)a.rows * a.B;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = e / a.B, b = e - k * a.B;
+    const T x = a.src[k * a.src_ld + b];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      if (p < a.ndst) a.dst[p][k * a.dst_ld + b] = x;
+  }
+}
+
+template <class T>
+int dynamics_gather_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, const void* v, const void* tau, int npeers,
+                      void* const* peers, void* mc, int64_t peer_ld, int64_t col0, cudaStream_t stream) {
+  const HostModel& hm = model->hm;
+  const ModelDev<T>& M = dev_model<T>(hm);
+  const int* gate = nullptr;
+  bool used = false;
+  {
+    SpecKey key; key.algo = SPEC_ABA; key.f64 = sizeof(T) == 8; key.has_in2 = tau != nullptr; key.peers = true;
+    SpecLaunchArgs sa{q, v, tau, nullptr, nullptr, ld, B};
+    sa.peers = peers; sa.npeers = npeers; sa.peer_ld = peer_ld; sa.peer_col0 = col0; sa.mc = mc;
+    std::string err;
+    if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, &gate, err)) return fail(rc, err);
+    if (used) g_launch.specialised = 1;
+    if (used && !gate) return RBD_OK;
+  }
+  const rbd_launch_info keep = g_launch;
+  // the generic kernels use ONE leading dimension for inputs and outputs, so the scratch is [nv x ld]
+  T* scratch = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&scratch, (size_t)hm.nv * (size_t)ld * sizeof(T), stream));
+  int rc;
+  if (!used) {
+    rc = dynamics_t<T>(model, B, ld, q, v, tau, nullptr, scratch, nullptr, stream);
+  } else {
+    AbaArgs<T> a{(const T*)q, (const T*)v, (const T*)tau, nullptr, scratch, nullptr, nullptr, ld, B};
+    a.gate = gate;
+    bool other_kinds = false;
+    for (int i = 0; i < hm.nb; ++i) other_kinds |= (M.body[i].kind == K_PRIS || M.body[i].kind == K_FIXED);
+    const int rows = M.nrows;
+#define RBD_ABA_G(G, K) launch<T>(aba_kernel<T, kNT, G, false, K>, M, a, kNT, rows, 0, stream)
+    rc = hm.general ? RBD_ABA_G(true, kAllKinds) : (other_kinds ? RBD_ABA_G(false, kAllKinds) : RBD_ABA_G(false, 0));
+#undef RBD_ABA_G
+  }
+  if (rc == RBD_OK) {
+    ScatterArgs<T> sc{};
+    sc.src = scratch; sc.src_ld = ld; sc.dst_ld = peer_ld; sc.ndst = npeers; sc.rows = hm.nv; sc.B = B; sc.gate = gate;
+    for (int p = 0; p < npeers; ++p) sc.dst[p] = (T*)peers[p] + col0;
+    DeviceProps p;
+    if ((rc = get_props(p)) == RBD_OK) {
+      gather_scatter_kernel<T><<<p.sms * 8, 256, 0, stream>>>(sc);
+      if (cudaGetLastError() != cudaSuccess) rc = fail(RBD_ECUDA, "gather_scatter_kernel launch failed");
+      g_launch.kernels_launched += 1;
+    }
+  }
+  cudaFreeAsync(scratch, stream);
+  const int n = g_launch.kernels_launched;
+  if (used) { g_launch = keep; g_launch.kernels_launched = n; }
+  return rc;
+}
+
 int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, bool allow_dual = false) {
   if (!model) return fail(RBD_EINVAL, "model handle is NULL");
   if (dtype != RBD_F32 && dtype != RBD_F64 && dtype != RBD_DUAL64X6)
@@ -1084,6 +1157,12 @@ int32_t rbd_model_precompile(rbd_model* model, int32_t dtype, int32_t what, int3
   if (what & RBD_SPEC_DYNAMICS_NOTAU) { one(SPEC_ABA, false, false); one(SPEC_ABA, false, true); }
   if (what & RBD_SPEC_INVERSE_DYNAMICS) one(SPEC_RNEA, true, false);
   if (what & RBD_SPEC_DYNAMICS_BIAS) one(SPEC_RNEA, false, false);
+  if (what & RBD_SPEC_DYNAMICS_GATHER) {
+    SpecKey key; key.algo = SPEC_ABA; key.f64 = dtype == RBD_F64; key.has_in2 = true; key.peers = true;
+    std::string e;
+    const int rc = spec_prepare(model, key, load != 0, e);
+    if (rc != RBD_OK) { rc_all = rc; err = e; }
+  }
   return rc_all == RBD_OK ? RBD_OK : fail(rc_all, err);
 }
 
@@ -1100,6 +1179,21 @@ int32_t rbd_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t l
   }
   return dtype == RBD_F32 ? dynamics_t<float>(model, B, ld, q, v, tau, wext, vd_out, qd_out, s)
                           : dynamics_t<double>(model, B, ld, q, v, tau, wext, vd_out, qd_out, s);
+}
+
+int32_t rbd_dynamics_gather(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                            const void* tau, int32_t npeers, void* const* vd_peers, void* vd_multicast, int64_t peer_ld, int64_t col0,
+                            void* stream) {
+  if (int rc = check_common(model, dtype, B, ld)) return rc;
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
+  if (npeers < 1 || npeers > 8 || !vd_peers) return fail(RBD_EINVAL, "rbd_dynamics_gather: need 1..8 peer arrays");
+  for (int p = 0; p < npeers; ++p) if (!vd_peers[p]) return fail(RBD_EINVAL, "rbd_dynamics_gather: NULL peer array");
+  if (col0 < 0 || peer_ld < col0 + B) return fail(RBD_EDIM, "rbd_dynamics_gather: columns [col0, col0 + B) exceed the gathered array");
+  if (B == 0) return RBD_OK;
+  if (!q || !v) return fail(RBD_EINVAL, "rbd_dynamics_gather: q and v must not be NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == RBD_F32 ? dynamics_gather_t<float>(model, B, ld, q, v, tau, npeers, vd_peers, vd_multicast, peer_ld, col0, s)
+                          : dynamics_gather_t<double>(model, B, ld, q, v, tau, npeers, vd_peers, vd_multicast, peer_ld, col0, s);
 }
 
 int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,

@@ -14,7 +14,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 11;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 12;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -193,7 +193,8 @@ struct Emitter {
           break;
         case S_STORE:
           ++stats.n_store;
-          snprintf(line, sizeof line, "RBD_STG(%s, %d, %s);\n", arr_name(n.arr), n.row, ref(n.a).c_str());
+          if (key.peers && n.arr == A_OUT0 && flavor != FLAVOR_CPU) snprintf(line, sizeof line, "RBD_STG_PEERS(%d, %s);\n", n.row, ref(n.a).c_str());
+          else snprintf(line, sizeof line, "RBD_STG(%s, %d, %s);\n", arr_name(n.arr), n.row, ref(n.a).c_str());
           out += line;
           break;
         case S_SLD: {
@@ -307,7 +308,7 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
   } else {
     sig = std::string("__device__ __forceinline__ void ") + name + "(const rbd_f* __restrict__ q, const rbd_f* __restrict__ v, "
           "const rbd_f* __restrict__ in2, rbd_f* __restrict__ o0, rbd_f* __restrict__ o1, const long long ld, const bool active, "
-          "int* flag, RBD_STASH_ARG)";
+          "int* flag, const RbdJitArgs& pa, const long long pb, RBD_STASH_ARG)";
   }
   out += sig + " {\n";
   if (flavor != FLAVOR_CPU) out += "RBD_FN_BEGIN\n";
@@ -332,7 +333,7 @@ uint64_t spec_hash(const HostModel& hm, const SpecKey& key) {
     const unsigned char* b = (const unsigned char*)p;
     for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ull; }
   };
-  const int hdr[8] = {kGeneratorVersion, key.algo, key.f64, key.has_in2, key.has_out1, key.lower, hm.nb, hm.general};
+  const int hdr[9] = {kGeneratorVersion, key.algo, key.f64, key.has_in2, key.has_out1, key.lower, hm.nb, hm.general, key.peers};
   mix(hdr, sizeof hdr);
   if (key.f64) {
     const ModelDev<double>& M = hm.dev64;

@@ -15,6 +15,7 @@ struct SpecKey {
   bool has_in2 = true;   // ABA: tau given (else zero torques); RNEA: vd given (else dynamics_bias)
   bool has_out1 = false; // ABA: q̇ output requested
   bool lower = false;    // CRBA: lower triangle only
+  bool peers = false;    // ABA: v̇ is stored into every peer GPU's gathered array (rbd_dynamics_gather) instead of o0
 };
 
 struct SpecStats {

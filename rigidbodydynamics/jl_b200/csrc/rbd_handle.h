@@ -64,13 +64,18 @@ struct PairCtx {
 cudaError_t pair_begin(rbd_model* m, cudaStream_t stream, PairCtx& ctx);
 
 inline uint32_t spec_key_bits(const SpecKey& k) {
-  return (uint32_t)k.algo | (k.f64 ? 8u : 0u) | (k.has_in2 ? 16u : 0u) | (k.has_out1 ? 32u : 0u) | (k.lower ? 64u : 0u);
+  return (uint32_t)k.algo | (k.f64 ? 8u : 0u) | (k.has_in2 ? 16u : 0u) | (k.has_out1 ? 32u : 0u) | (k.lower ? 64u : 0u) | (k.peers ? 128u : 0u);
 }
 
 struct SpecLaunchArgs {
   const void* q; const void* v; const void* in2;
   void* o0; void* o1;
   int64_t ld, B;
+  // key.peers: o0 is unused; row k of sample b goes to peers[p][k * peer_ld + peer_col0 + b] for every p < npeers
+  void* const* peers = nullptr;
+  void* mc = nullptr;            // NVLS multicast mapping of the peers' arrays, or NULL
+  int npeers = 0;
+  int64_t peer_ld = 0, peer_col0 = 0;
 };
 // Tries the model-specialised kernels for (model, key).  `used` = false (and RBD_OK) when they are unavailable, not yet
 // compiled and the batch is below the compile threshold, or the batch is too small: the caller then runs the generic kernels.

@@ -25,14 +25,14 @@
     const bool active = b < a.B;                                                                    \
     const long long bl = active ? b : a.B - 1;   /* inactive lanes recompute the last sample, stores are masked */ \
     CALL(a.q + bl, a.v + bl, RBD_SPEC_HAS_IN2 ? a.in2 + bl : (const rbd_f*)0, a.o0 + bl,             \
-         RBD_SPEC_HAS_OUT1 ? a.o1 + bl : (rbd_f*)0, a.ld, active, a.flag);                           \
+         RBD_SPEC_HAS_OUT1 ? a.o1 + bl : (rbd_f*)0, a.ld, active, a.flag, a, bl);                    \
     g = gn;                                                                                         \
   }
 
 extern "C" __global__ void __launch_bounds__(32, RBD_SPEC_F64 ? 1 : 16) rbd_jit_smem(const RbdJitArgs a) {
   extern __shared__ __align__(16) unsigned char rbd_smem_raw[];
   volatile rbd_f* sh = reinterpret_cast<volatile rbd_f*>(rbd_smem_raw) + threadIdx.x;
-#define RBD_CALL_SMEM(q_, v_, i_, o0_, o1_, ld_, act_, fl_) rbd_spec_smem(q_, v_, i_, o0_, o1_, ld_, act_, fl_, sh)
+#define RBD_CALL_SMEM(q_, v_, i_, o0_, o1_, ld_, act_, fl_, pa_, pb_) rbd_spec_smem(q_, v_, i_, o0_, o1_, ld_, act_, fl_, pa_, pb_, sh)
   RBD_QUEUE_LOOP(RBD_CALL_SMEM)
 }
 
@@ -52,7 +52,7 @@ extern "C" __global__ void __launch_bounds__(32 * RBD_TM_WARPS, RBD_SPEC_F64 ? 1
   const unsigned tm_base = tm_slot;
   const unsigned w = threadIdx.x >> 5;
   const unsigned tm = tm_base + (((w & 3u) * 32u) << 16) + (w >> 2) * 256u;
-#define RBD_CALL_TMEM(q_, v_, i_, o0_, o1_, ld_, act_, fl_) rbd_spec_tmem(q_, v_, i_, o0_, o1_, ld_, act_, fl_, tm)
+#define RBD_CALL_TMEM(q_, v_, i_, o0_, o1_, ld_, act_, fl_, pa_, pb_) rbd_spec_tmem(q_, v_, i_, o0_, o1_, ld_, act_, fl_, pa_, pb_, tm)
   {
     RBD_QUEUE_LOOP(RBD_CALL_TMEM)
   }
@@ -84,7 +84,7 @@ extern "C" __global__ void __launch_bounds__(32 * (RBD_UNI_SW + RBD_TM_WARPS), 1
   const unsigned tm = tm_base + (((w & 3u) * 32u) << 16) + (wt >> 2) * 256u;
   const unsigned ws = use_tm ? 0u : w;
   volatile rbd_f* sh = reinterpret_cast<volatile rbd_f*>(rbd_smem_raw) + ws * (RBD_SPEC_ROWS * 32u) + (threadIdx.x & 31u);
-#define RBD_CALL_UNI(q_, v_, i_, o0_, o1_, ld_, act_, fl_) rbd_spec_uni(q_, v_, i_, o0_, o1_, ld_, act_, fl_, tm, sh, use_tm)
+#define RBD_CALL_UNI(q_, v_, i_, o0_, o1_, ld_, act_, fl_, pa_, pb_) rbd_spec_uni(q_, v_, i_, o0_, o1_, ld_, act_, fl_, pa_, pb_, tm, sh, use_tm)
   {
     RBD_QUEUE_LOOP(RBD_CALL_UNI)
   }

@@ -181,14 +181,19 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
   const int uni_warps = se->uni_sw > 0 ? se->uni_sw + tm_warps : 0;
   const bool uni_ok = !ev.no_tmem && uni_warps * 100 >= bps * 115 && ((se->regs_uni + 7) / 8) * 8 * 32 * uni_warps <= 65536 &&
                       ngroups >= (int64_t)(uni_warps - tm_warps / 2) * p.sms;
-  struct KArgs { const void* q; const void* v; const void* in2; void* o0; void* o1; long long ld, B; unsigned long long* counter; int* flag; };
+  struct KArgs {
+    const void* q; const void* v; const void* in2; void* o0; void* o1; long long ld, B; unsigned long long* counter; int* flag;
+    void* peers[8]; long long peer_ld, peer_col0; void* mc; int npeers;
+  };
   int launched = 0;
   int* last_flag = nullptr;
   auto run = [&](int variant) -> cudaError_t {        // 0 = shared memory alone, 1 = pair, 2 = unified
     PairCtx ctx;
     cudaError_t e = pair_begin(m, stream, ctx);
     if (e != cudaSuccess) return e;
-    KArgs ka = {a.q, a.v, a.in2, a.o0, a.o1, (long long)a.ld, (long long)a.B, ctx.counter, ctx.flag};
+    KArgs ka = {a.q, a.v, a.in2, a.o0, a.o1, (long long)a.ld, (long long)a.B, ctx.counter, ctx.flag, {}, (long long)a.peer_ld,
+                (long long)a.peer_col0, a.mc, a.npeers};
+    for (int i = 0; i < a.npeers && i < 8; ++i) ka.peers[i] = a.peers[i];
     void* params[] = {&ka};
     if (variant == 2) {
       e = cudaLaunchKernel((const void*)se->k_uni, dim3(p.sms), dim3(32 * uni_warps), params, smem * se->uni_sw, stream);
