@@ -184,6 +184,24 @@ int32_t rbd_dynamics_gather(const rbd_model* model, int32_t dtype, int64_t B, in
 int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                              const void* v, const void* vd, const void* wext, void* tau_out, void* stream);
 
+/* The per-body arguments of inverse_dynamics!(torquesout, jointwrenchesout, accelerations, state, v̇, externalwrenches)
+ *                                                             src/mechanism_algorithms.jl:542-553, :387-459
+ *   accelerations_out [6*nb x B]: rows 6 i .. 6 i + 5 = spatial acceleration [angular; linear] of the successor of tree joint i,
+ *     expressed in the ROOT frame, gravity folded in as the root's fictitious acceleration -g exactly like spatial_accelerations!;
+ *   jointwrenches_out [6*nb x B]: the wrench [torque; force] transmitted by tree joint i, ROOT frame (net wrench of the subtree,
+ *     joint_wrenches_and_torques!).  Either may be NULL.  vd NULL = zero accelerations (the dynamics_bias! variant), wext as usual. */
+int32_t rbd_inverse_dynamics_bodies(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                                    const void* vd, const void* wext, void* accelerations_out, void* jointwrenches_out, void* stream);
+
+/* dynamics!(result, ...) INCLUDING the by-products the reference leaves in the DynamicsResult (src/dynamics_result.jl:11-85,
+ * mechanism_algorithms.jl:849-863): besides v̇ / q̇, any of  result.massmatrix (M_out [nv*nv x B], see rbd_mass_matrix),
+ * result.dynamicsbias (c_out [nv x B]), result.accelerations and result.jointwrenches (see rbd_inverse_dynamics_bodies, evaluated
+ * at the v̇ just computed).  NULL = not wanted.  The forward dynamics itself does not need M or c (it is the Articulated-Body
+ * Algorithm), so they cost extra launches only when asked for. */
+int32_t rbd_dynamics_result(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                            const void* tau, const void* wext, void* vd_out, void* qd_out, void* M_out, void* c_out,
+                            void* accelerations_out, void* jointwrenches_out, void* stream);
+
 /* dynamics_bias!(result, state) / dynamics_bias!(torques, biasaccelerations, wrenches, state, externalwrenches)
  *                                                             src/mechanism_algorithms.jl:484-498
  *   -> c_out [nv x B] = c(q, v, wext) = inverse_dynamics with v̇ = 0. */
@@ -195,6 +213,14 @@ int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int6
  *   triangles are written (the reference fills the lower one and wraps it in Symmetric(:L)). */
 int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
                         void* stream);
+
+/* Same with a choice of triangle (SURVEY 8(b) "full symmetric or lower-only flagged"): RBD_UPLO_LOWER writes only the entries
+ * with row >= column -- exactly what the reference's mass_matrix! fills in M.data (Symmetric(:L)) -- and leaves the rest of
+ * M_out untouched: half the output bytes (Atlas: 2.7 KB instead of 5.3 KB per sample). */
+#define RBD_UPLO_FULL 0
+#define RBD_UPLO_LOWER 1
+int32_t rbd_mass_matrix_uplo(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
+                             int32_t uplo, void* stream);
 
 /* Next row of the scope table, the main caller of dynamics!:
  * simulate(state0, final_time, control!; dt) with the default passive / constant-torque control

@@ -33,6 +33,7 @@ def _load():
     lib.rbdo_dynamics_dual6.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32]
     lib.rbdo_integrate.argtypes = [vp, i64, vp, vp, vp, ctypes.c_double, i32, i32]
     lib.rbdo_inverse_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32]
+    lib.rbdo_inverse_dynamics_bodies.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
     lib.rbdo_mass_matrix.argtypes = [vp, i32, i64, vp, vp, i32]
     lib.rbdo_kinematics.argtypes = [vp, i32, i64] + [vp] * 11 + [i32]
     return lib
@@ -125,6 +126,17 @@ class Oracle:
         tau = np.empty((self.nv, B), dt)
         _lib.rbdo_inverse_dynamics(self._h, self._code(dt), B, _ptr(q), _ptr(v), _ptr(vd), _ptr(wext), _ptr(tau), nthreads)
         return tau
+
+    def inverse_dynamics_bodies(self, q, v, vd=None, wext=None, *, dtype=None):
+        """The per-body caches inverse_dynamics! fills: (accelerations, jointwrenches), each [6*nb, B], root frame, rows
+        6i..6i+5 = [angular; linear] / [torque; force] of the successor of tree joint i (mechanism_algorithms.jl:387-459)."""
+        dt = np.dtype(dtype or np.asarray(q).dtype)
+        q = self._prep(q, self.nq, dt); v = self._prep(v, self.nv, dt)
+        vd = self._prep(vd, self.nv, dt); wext = self._prep(wext, self.nb * 6, dt)
+        B = q.shape[1]
+        acc = np.empty((6 * self.nb, B), dt); jw = np.empty((6 * self.nb, B), dt)
+        _lib.rbdo_inverse_dynamics_bodies(self._h, self._code(dt), B, _ptr(q), _ptr(v), _ptr(vd), _ptr(wext), _ptr(acc), _ptr(jw))
+        return acc, jw
 
     def dynamics_bias(self, q, v, wext=None, *, nthreads=1, dtype=None):
         return self.inverse_dynamics(q, v, None, wext, nthreads=nthreads, dtype=dtype)

@@ -102,6 +102,28 @@ int inverse_dynamics_t(const Model& m, int64_t B, const T* q, const T* v, const 
   return 0;
 }
 
+// per-body caches of inverse_dynamics!: `accelerations` (spatial_accelerations! :387-417) and the joint wrenches left in
+// `jointwrenchesout` by joint_wrenches_and_torques! (:442-459), both in the root frame, [6*nb x B]
+template <class T>
+int inverse_dynamics_bodies_t(const Model& m, int64_t B, const T* q, const T* v, const T* vd, const T* wext, T* acc, T* jw) {
+  Workspace<T> w(m);
+  const int nw = m.nb * 6;
+  std::vector<T> ql(m.nq), vl(m.nv), vdl(m.nv), wl(nw), tl(m.nv);
+  for (int64_t b = 0; b < B; ++b) {
+    for (int k = 0; k < m.nq; ++k) ql[k] = q[(size_t)k * B + b];
+    for (int k = 0; k < m.nv; ++k) { vl[k] = v[(size_t)k * B + b]; vdl[k] = vd ? vd[(size_t)k * B + b] : T(0); }
+    for (int k = 0; k < nw; ++k) wl[k] = wext ? wext[(size_t)k * B + b] : T(0);
+    if (vd) inverse_dynamics(w, ql.data(), vl.data(), vdl.data(), wext ? wl.data() : nullptr, tl.data());
+    else dynamics_bias(w, ql.data(), vl.data(), wext ? wl.data() : nullptr, tl.data());
+    for (int i = 0; i < m.nb; ++i)
+      for (int k = 0; k < 3; ++k) {
+        if (acc) { acc[(size_t)(6 * i + k) * B + b] = w.accel[i].ang[k]; acc[(size_t)(6 * i + 3 + k) * B + b] = w.accel[i].lin[k]; }
+        if (jw) { jw[(size_t)(6 * i + k) * B + b] = w.wrench[i].ang[k]; jw[(size_t)(6 * i + 3 + k) * B + b] = w.wrench[i].lin[k]; }
+      }
+  }
+  return 0;
+}
+
 template <class T> int mass_matrix_t(const Model& m, int64_t B, const T* q, T* M, int nthreads) {
   parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
     Workspace<T> w(m);
@@ -244,6 +266,12 @@ int rbdo_inverse_dynamics(void* mp, int dtype, int64_t B, const void* q, const v
   const Model& m = *static_cast<Model*>(mp);
   if (dtype == 0) return inverse_dynamics_t<float>(m, B, (const float*)q, (const float*)v, (const float*)vd, (const float*)wext, (float*)tau, nthreads);
   return inverse_dynamics_t<double>(m, B, (const double*)q, (const double*)v, (const double*)vd, (const double*)wext, (double*)tau, nthreads);
+}
+int rbdo_inverse_dynamics_bodies(void* mp, int dtype, int64_t B, const void* q, const void* v, const void* vd, const void* wext,
+                                 void* acc, void* jw) {
+  const Model& m = *static_cast<Model*>(mp);
+  if (dtype == 0) return inverse_dynamics_bodies_t<float>(m, B, (const float*)q, (const float*)v, (const float*)vd, (const float*)wext, (float*)acc, (float*)jw);
+  return inverse_dynamics_bodies_t<double>(m, B, (const double*)q, (const double*)v, (const double*)vd, (const double*)wext, (double*)acc, (double*)jw);
 }
 int rbdo_mass_matrix(void* mp, int dtype, int64_t B, const void* q, void* M, int nthreads) {
   const Model& m = *static_cast<Model*>(mp);

@@ -50,19 +50,33 @@ def _call(status):
 
 
 def dynamics_(result: DynamicsResult, state: MechanismState, torques: Optional[torch.Tensor] = None,
-              externalwrenches: Optional[torch.Tensor] = None, want_qd: bool = True):
+              externalwrenches: Optional[torch.Tensor] = None, want_qd: bool = True, byproducts=()):
     """``dynamics!(result, state, torques, externalwrenches)``: fills ``result.vd`` (v̇) and ``result.qd`` (q̇).
 
     ``torques`` [nv, B] or None (zero, the ConstVector default); ``externalwrenches`` [6*nb, B] root-frame wrenches
-    (rows 6i..6i+5 = [torque; force] on the successor of tree joint i) or None (the NullDict default)."""
+    (rows 6i..6i+5 = [torque; force] on the successor of tree joint i) or None (the NullDict default).
+
+    The reference's ``dynamics!`` also leaves ``result.massmatrix``, ``result.dynamicsbias`` (it solves M v̇ = tau - c) and, on
+    request, ``result.accelerations`` / ``result.jointwrenches`` behind (dynamics_result.jl:11-85).  The Articulated-Body kernel
+    needs none of them, so they are computed only when named in ``byproducts`` (any of "massmatrix", "dynamicsbias",
+    "accelerations", "jointwrenches", or "all") -- a drop-in caller that reads those fields passes ``byproducts="all"``."""
     state.check_modcount()
     lib = _cabi.load_library()
     _check(torques, state.nv, state, "torques")
     _check(externalwrenches, 6 * len(state.mechanism.joints), state, "externalwrenches")
     _check(result.vd, state.nv, state, "result.vd")
-    _call(lib.rbd_dynamics(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(state.v),
-                           _ptr(torques), _ptr(externalwrenches), _ptr(result.vd),
-                           _ptr(result.qd) if want_qd else None, _stream()))
+    want = {"massmatrix", "dynamicsbias", "accelerations", "jointwrenches"} if byproducts == "all" else set(byproducts or ())
+    if not want:
+        _call(lib.rbd_dynamics(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(state.v),
+                               _ptr(torques), _ptr(externalwrenches), _ptr(result.vd),
+                               _ptr(result.qd) if want_qd else None, _stream()))
+        return result
+    _call(lib.rbd_dynamics_result(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(state.v),
+                                  _ptr(torques), _ptr(externalwrenches), _ptr(result.vd), _ptr(result.qd) if want_qd else None,
+                                  _ptr(result.massmatrix) if "massmatrix" in want else None,
+                                  _ptr(result.dynamicsbias) if "dynamicsbias" in want else None,
+                                  _ptr(result.accelerations) if "accelerations" in want else None,
+                                  _ptr(result.jointwrenches) if "jointwrenches" in want else None, _stream()))
     return result
 
 
@@ -115,16 +129,25 @@ def simulate_(state: MechanismState, final_time: float, torques: Optional[torch.
 
 
 def inverse_dynamics_(torquesout: torch.Tensor, state: MechanismState, vd: torch.Tensor,
-                      externalwrenches: Optional[torch.Tensor] = None):
-    """``inverse_dynamics!``: tau = M(q) v̇ + c(q, v, w_ext).  (The per-body joint wrench / acceleration outputs of the
-    reference signature are not materialised by the batched kernel.)"""
+                      externalwrenches: Optional[torch.Tensor] = None, jointwrenchesout: Optional[torch.Tensor] = None,
+                      accelerations: Optional[torch.Tensor] = None):
+    """``inverse_dynamics!(torquesout, jointwrenchesout, accelerations, state, v̇, externalwrenches)`` (mechanism_algorithms.jl:542-553):
+    tau = M(q) v̇ + c(q, v, w_ext).  ``jointwrenchesout`` / ``accelerations`` [6*nb, B] (optional) receive the reference's per-body
+    outputs, root frame, rows 6i..6i+5 for the successor of tree joint i."""
     state.check_modcount()
     lib = _cabi.load_library()
+    nb6 = 6 * len(state.mechanism.joints)
     _check(vd, state.nv, state, "v̇")
     _check(torquesout, state.nv, state, "torquesout")
-    _check(externalwrenches, 6 * len(state.mechanism.joints), state, "externalwrenches")
+    _check(externalwrenches, nb6, state, "externalwrenches")
+    _check(jointwrenchesout, nb6, state, "jointwrenchesout")
+    _check(accelerations, nb6, state, "accelerations")
     _call(lib.rbd_inverse_dynamics(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q),
                                    _ptr(state.v), _ptr(vd), _ptr(externalwrenches), _ptr(torquesout), _stream()))
+    if jointwrenchesout is not None or accelerations is not None:
+        _call(lib.rbd_inverse_dynamics_bodies(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q),
+                                              _ptr(state.v), _ptr(vd), _ptr(externalwrenches), _ptr(accelerations),
+                                              _ptr(jointwrenchesout), _stream()))
     return torquesout
 
 
@@ -148,16 +171,19 @@ def dynamics_bias(state: MechanismState, externalwrenches: Optional[torch.Tensor
     return dynamics_bias_(torch.empty_like(state.v), state, externalwrenches)
 
 
-def mass_matrix_(result_or_out, state: MechanismState):
-    """``mass_matrix!(M, state)`` / ``mass_matrix!(result, state)``: [nv*nv, B], entry (i, j) at row i + j*nv."""
+def mass_matrix_(result_or_out, state: MechanismState, uplo: str = "full"):
+    """``mass_matrix!(M, state)`` / ``mass_matrix!(result, state)``: [nv*nv, B], entry (i, j) at row i + j*nv.
+    ``uplo="L"``: only the lower triangle (row >= column) is written, like the reference's ``Symmetric(:L)`` storage."""
     state.check_modcount()
     lib = _cabi.load_library()
     out = result_or_out.massmatrix if isinstance(result_or_out, DynamicsResult) else result_or_out
     if out.dim() != 2 or out.shape[0] != state.nv * state.nv or out.shape[1] != state.batch:
         raise DimensionMismatch("mass matrix has wrong size")                 # mechanism_algorithms.jl:250
     _check(out, state.nv * state.nv, state, "mass matrix")
-    _call(lib.rbd_mass_matrix(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(out),
-                              _stream()))
+    if uplo not in ("full", "L"):
+        raise ValueError("uplo must be 'full' or 'L'")                      # mechanism_algorithms.jl:251 (uplo == 'L')
+    _call(lib.rbd_mass_matrix_uplo(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(out),
+                                   1 if uplo == "L" else 0, _stream()))
     return out
 
 

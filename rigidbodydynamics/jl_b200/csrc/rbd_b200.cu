@@ -384,6 +384,7 @@ template <class T> struct CrbaArgs {
   const T* q;
   T* M;
   int64_t ld, B;
+  bool lower;
 };
 
 template <class T, int NT, int KMAX>
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 4 ? (KMAX == 1 ? 28 : 20) : 1
     CrbaIO<T> io;
     io.q = {a.q + bl, a.ld};
     io.M = {a.M + bl, a.ld, active};
+    io.lower = a.lower;
     crba_sample<T, NT, KMAX>(M, io, st);
   }
 }
@@ -454,6 +456,33 @@ int configure_once(const void* kernel, const DeviceProps& p) {
   done.insert({kernel, p.dev});
   return RBD_OK;
 }
+template <class T> struct BodiesArgs {
+  const T* q; const T* v; const T* vd; const T* wext;
+  T* acc; T* jw;
+  int64_t ld, B;
+};
+template <class T, int NT>
+__global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 16 : 8) bodies_kernel(const __grid_constant__ ModelDev<T> M, const BodiesArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Stash<T, NT> st{reinterpret_cast<T*>(smem_raw) + threadIdx.x};
+  const int64_t ngroups = (a.B + NT - 1) / NT;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t b = g * NT + threadIdx.x;
+    const bool active = b < a.B;
+    const int64_t bl = active ? b : a.B - 1;
+    BodiesIO<T> io;
+    io.q = {a.q + bl, a.ld};
+    io.v = {a.v + bl, a.ld};
+    io.vd = {a.vd ? a.vd + bl : nullptr, a.ld};
+    io.wext = {a.wext ? a.wext + bl : nullptr, a.ld};
+    io.acc = a.acc ? a.acc + bl : nullptr;
+    io.jw = a.jw ? a.jw + bl : nullptr;
+    io.ld = a.ld;
+    io.active = active;
+    bodies_sample<T>(M, io, st);
+  }
+}
+
 template <class K> int configure(K kernel, int nt, size_t smem, const DeviceProps& p, int& blocks_per_sm) {
   if ((int)smem > p.max_smem_optin) return fail(RBD_EUNSUPPORTED, "model working set exceeds shared memory per block");
   if (int rc = configure_once((const void*)kernel, p)) return rc;
@@ -659,10 +688,10 @@ int inverse_dynamics_t(const rbd_model* model, int64_t B, int64_t ld, const void
 }
 
 template <class T>
-int mass_matrix_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, void* Mout, cudaStream_t stream) {
+int mass_matrix_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, void* Mout, cudaStream_t stream, bool lower = false) {
   const HostModel& hm = model->hm;
   const ModelDev<T>& M = dev_model<T>(hm);
-  CrbaArgs<T> a{(const T*)q, (T*)Mout, ld, B};
+  CrbaArgs<T> a{(const T*)q, (T*)Mout, ld, B, lower};
   const int rows = std::max(1, crba_rows(hm));
   bool multi = false;
   for (int i = 0; i < hm.nb; ++i) multi |= kind_nv(M.body[i].kind) > 1;
@@ -950,6 +979,27 @@ int dynamics_gather_t(const rbd_model* model, int64_t B, int64_t ld, const void*
   return rc;
 }
 
+template <class T>
+int bodies_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, const void* v, const void* vd, const void* wext, void* acc,
+             void* jw, cudaStream_t stream) {
+  const HostModel& hm = model->hm;
+  const ModelDev<T>& M = dev_model<T>(hm);
+  BodiesArgs<T> a{(const T*)q, (const T*)v, (const T*)vd, (const T*)wext, (T*)acc, (T*)jw, ld, B};
+  DeviceProps p;
+  if (int rc = get_props(p)) return rc;
+  auto kernel = bodies_kernel<T, kNT>;
+  const size_t smem = (size_t)std::max(1, kin_rows(hm)) * kNT * sizeof(T);
+  int bps = 0;
+  if (int rc = configure(kernel, kNT, smem, p, bps)) return rc;
+  const int64_t ngroups = (B + kNT - 1) / kNT;
+  const int grid = (int)std::min<int64_t>(ngroups, (int64_t)bps * p.sms);
+  kernel<<<grid, kNT, smem, stream>>>(M, a);
+  if (cudaGetLastError() != cudaSuccess) return fail(RBD_ECUDA, "bodies_kernel launch failed");
+  g_launch.kernels_launched += 1;
+  g_launch.grid = grid; g_launch.block = kNT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
+  return RBD_OK;
+}
+
 int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, bool allow_dual = false) {
   if (!model) return fail(RBD_EINVAL, "model handle is NULL");
   if (dtype != RBD_F32 && dtype != RBD_F64 && dtype != RBD_DUAL64X6)
@@ -1220,6 +1270,36 @@ int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, i
                           : inverse_dynamics_t<double>(model, B, ld, q, v, vd, wext, tau_out, s);
 }
 
+int32_t rbd_inverse_dynamics_bodies(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                                    const void* vd, const void* wext, void* accelerations_out, void* jointwrenches_out, void* stream) {
+  if (int rc = check_common(model, dtype, B, ld)) return rc;
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
+  if (B == 0 || (!accelerations_out && !jointwrenches_out)) return RBD_OK;
+  if (!q || !v) return fail(RBD_EINVAL, "rbd_inverse_dynamics_bodies: q and v must not be NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == RBD_F32 ? bodies_t<float>(model, B, ld, q, v, vd, wext, accelerations_out, jointwrenches_out, s)
+                          : bodies_t<double>(model, B, ld, q, v, vd, wext, accelerations_out, jointwrenches_out, s);
+}
+
+int32_t rbd_dynamics_result(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                            const void* tau, const void* wext, void* vd_out, void* qd_out, void* M_out, void* c_out,
+                            void* accelerations_out, void* jointwrenches_out, void* stream) {
+  int rc = rbd_dynamics(model, dtype, B, ld, q, v, tau, wext, vd_out, qd_out, stream);
+  if (rc != RBD_OK || B == 0) return rc;
+  if (dtype == RBD_DUAL64X6 && (M_out || c_out || accelerations_out || jointwrenches_out))
+    return fail(RBD_EUNSUPPORTED, "rbd_dynamics_result: by-products are fp32 / fp64 only");
+  rbd_launch_info acc = g_launch;
+  auto merge = [&]() { acc.kernels_launched += g_launch.kernels_launched; };
+  if (c_out) { if ((rc = rbd_dynamics_bias(model, dtype, B, ld, q, v, wext, c_out, stream)) != RBD_OK) return rc; merge(); }
+  if (M_out) { if ((rc = rbd_mass_matrix(model, dtype, B, ld, q, M_out, stream)) != RBD_OK) return rc; merge(); }
+  if (accelerations_out || jointwrenches_out) {
+    if ((rc = rbd_inverse_dynamics_bodies(model, dtype, B, ld, q, v, vd_out, wext, accelerations_out, jointwrenches_out, stream)) != RBD_OK) return rc;
+    merge();
+  }
+  g_launch = acc;
+  return RBD_OK;
+}
+
 int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,
                           const void* v, const void* wext, void* c_out, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
@@ -1231,14 +1311,21 @@ int32_t rbd_dynamics_bias(const rbd_model* model, int32_t dtype, int64_t B, int6
                           : inverse_dynamics_t<double>(model, B, ld, q, v, nullptr, wext, c_out, s);
 }
 
-int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
-                        void* stream) {
+int32_t rbd_mass_matrix_uplo(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
+                             int32_t uplo, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
   g_launch = {0, 0, 0, 0, 0, 0.f, 0};
+  if (uplo != RBD_UPLO_FULL && uplo != RBD_UPLO_LOWER) return fail(RBD_EINVAL, "rbd_mass_matrix: uplo must be RBD_UPLO_FULL or RBD_UPLO_LOWER");
   if (B == 0) return RBD_OK;      // empty batch: nothing to read or write, pointers may be NULL
   if (!q || !M_out) return fail(RBD_EINVAL, "rbd_mass_matrix: q and M_out must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  return dtype == RBD_F32 ? mass_matrix_t<float>(model, B, ld, q, M_out, s) : mass_matrix_t<double>(model, B, ld, q, M_out, s);
+  const bool lower = uplo == RBD_UPLO_LOWER;
+  return dtype == RBD_F32 ? mass_matrix_t<float>(model, B, ld, q, M_out, s, lower) : mass_matrix_t<double>(model, B, ld, q, M_out, s, lower);
+}
+
+int32_t rbd_mass_matrix(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, void* M_out,
+                        void* stream) {
+  return rbd_mass_matrix_uplo(model, dtype, B, ld, q, M_out, RBD_UPLO_FULL, stream);
 }
 
 // ---- host-pointer variants: chunked H2D -> kernel -> D2H pipeline over three internal streams -----------------------

@@ -290,4 +290,126 @@ RBD_HD void kin_sample(const ModelDev<T>& M, const KinDev<T>& K, const KinIO<T>&
   }
 }
 
+// ==================================================================================================================
+// Per-body outputs of inverse_dynamics!: the `accelerations` and `jointwrenchesout` arguments of
+//   inverse_dynamics!(torquesout, jointwrenchesout, accelerations, state, v̇, externalwrenches)   mechanism_algorithms.jl:542-553
+// in the reference's own terms -- ROOT-frame quantities per body:
+//   spatial_accelerations!        :387-417   a_i = a_parent + v_parent x (S v)_i + S_i v̇_i ,  a_root = -g
+//   newton_euler!                 :428-439   w_i = I_i a_i + v_i x* (I_i v_i) - w_ext,i      (net wrench)
+//   joint_wrenches_and_torques!   :442-459   w_parent += w_i in reverse tree order            (joint wrench = subtree sum)
+// Outward sweep exactly like kin_sample (pose, twist, acceleration in registers; branch nodes park theirs in a pending slot);
+// net wrenches go straight into the output column and the inward accumulation is a read-modify-write on that column (a thread
+// owns its column; reverse preorder guarantees a body's sum is complete before it is added to its parent).
+// ==================================================================================================================
+template <class T> struct BodiesIO {
+  Col<T> q, v, vd, wext;       // vd / wext may be invalid (zero accelerations / no external wrenches)
+  T* acc; T* jw;               // output columns (already offset by the sample), rows 6 * refidx + c; either may be NULL
+  int64_t ld;
+  bool active;
+};
+
+template <class T, class ST>
+RBD_HD void bodies_sample(const ModelDev<T>& M, const BodiesIO<T>& io, const ST& st) {
+  const int nb = M.nb;
+  Pose<T> cur;
+  pose_identity(cur);
+  Mot<T> twc, ac;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) twc.w[k] = twc.l[k] = ac.w[k] = ac.l[k] = T(0);
+  for (int i = 0; i < nb; ++i) {
+    const BodyDev<T>& bd = M.body[i];
+    Pose<T> pp;
+    Mot<T> twp, ap;
+    if (bd.flags & F_ROOT_CHILD) {
+      pose_identity(pp);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { twp.w[k] = twp.l[k] = ap.w[k] = T(0); ap.l[k] = -M.g[k]; }
+    } else if (bd.flags & F_FIRST_CHILD) {
+      pp = cur; twp = twc; ap = ac;
+    } else {
+      const int row = bd.pslot * kSlotRowsKin;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) pp.R[k] = st.ld(row + k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        pp.p[k] = st.ld(row + 9 + k);
+        twp.w[k] = st.ld(row + 12 + k); twp.l[k] = st.ld(row + 15 + k);
+        ap.w[k] = st.ld(row + 18 + k); ap.l[k] = st.ld(row + 21 + k);
+      }
+    }
+    T R[9], r[3], t[3];
+    frame_any(bd, io.q, R, r);
+    Pose<T> w;
+    mat_mul3(pp.R, R, w.R);
+    mat_vec(pp.R, r, t);
+    w.p[0] = pp.p[0] + t[0]; w.p[1] = pp.p[1] + t[1]; w.p[2] = pp.p[2] + t[2];
+    Mot<T> jt, ja;                     // S v and S v̇ in the root frame
+#pragma unroll
+    for (int k = 0; k < 3; ++k) jt.w[k] = jt.l[k] = ja.w[k] = ja.l[k] = T(0);
+    const int nvj = kind_nv_dev(bd.kind);
+    for (int k = 0; k < nvj; ++k) {
+      Mot<T> S;
+      world_subspace(w, sub_comp(bd.kind, k), S);
+      const T x = io.v(bd.vrow + k);
+      const T xd = io.vd.valid() ? io.vd(bd.vrow + k) : T(0);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { jt.w[c] += x * S.w[c]; jt.l[c] += x * S.l[c]; ja.w[c] += xd * S.w[c]; ja.l[c] += xd * S.l[c]; }
+    }
+    Mot<T> tw, a, cm;
+    motion_cross(twp, jt, cm);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      tw.w[k] = twp.w[k] + jt.w[k]; tw.l[k] = twp.l[k] + jt.l[k];
+      a.w[k] = ap.w[k] + cm.w[k] + ja.w[k]; a.l[k] = ap.l[k] + cm.l[k] + ja.l[k];
+    }
+    const int64_t orow = (int64_t)6 * bd.refidx;
+    if (io.acc && io.active) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { io.acc[(orow + k) * io.ld] = a.w[k]; io.acc[(orow + 3 + k) * io.ld] = a.l[k]; }
+    }
+    if (io.jw) {                       // net wrench of this body, root frame
+      Rbi<T> Ib, Iw;
+      body_rbi(bd, Ib);
+      rbi_to_parent(w.R, w.p, Ib, Iw);
+      T n[3], f[3], hn[3], hf[3], c1[3], c2[3], c3[3];
+      rbi_mul(Iw, a, n, f);
+      rbi_mul(Iw, tw, hn, hf);
+      cross3(tw.w, hn, c1);
+      cross3(tw.l, hf, c2);
+      cross3(tw.w, hf, c3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { n[k] += c1[k] + c2[k]; f[k] += c3[k]; }
+      if (io.wext.valid()) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { n[k] -= io.wext((int)orow + k); f[k] -= io.wext((int)orow + 3 + k); }
+      }
+      if (io.active) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { io.jw[(orow + k) * io.ld] = n[k]; io.jw[(orow + 3 + k) * io.ld] = f[k]; }
+      }
+    }
+    if (bd.flags & F_HAS_PENDING) {
+      const int row = bd.oslot * kSlotRowsKin;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) st.st(row + k, w.R[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        st.st(row + 9 + k, w.p[k]);
+        st.st(row + 12 + k, tw.w[k]); st.st(row + 15 + k, tw.l[k]);
+        st.st(row + 18 + k, a.w[k]); st.st(row + 21 + k, a.l[k]);
+      }
+    }
+    cur = w; twc = tw; ac = a;
+  }
+  if (!io.jw || !io.active) return;
+  // inward accumulation on the output column
+  for (int i = nb - 1; i >= 0; --i) {
+    const BodyDev<T>& bd = M.body[i];
+    if (bd.flags & F_ROOT_CHILD) continue;
+    const int64_t crow = (int64_t)6 * bd.refidx, prow = (int64_t)6 * M.body[bd.parent].refidx;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) io.jw[(prow + k) * io.ld] += io.jw[(crow + k) * io.ld];
+  }
+}
+
 }  // namespace rbd

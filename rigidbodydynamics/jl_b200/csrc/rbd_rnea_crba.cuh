@@ -309,6 +309,9 @@ RBD_HD void rnea_sample(const ModelDev<T>& M, const RneaIO<T>& io, const ST& st)
 template <class T> struct CrbaIO {
   Col<T> q;
   ColOut<T> M;
+  bool lower;        // write only entries with row >= column (the triangle mass_matrix! fills, mechanism_algorithms.jl:248-272)
+  // entry (r, c) of the column-major matrix; indices are warp-uniform, so the triangle test costs a uniform predicate
+  RBD_HD void put(int r, int c, int nv, T val) const { if (!lower || r >= c) M.st(r + c * nv, val); }
 };
 
 // rigid-body inertia (m, h = m*com, J about the origin: xx xy xz yy yz zz)
@@ -450,7 +453,7 @@ RBD_HD void crba_sample(const ModelDev<T>& M, const CrbaIO<T>& io, const Stash<T
 #pragma unroll
         for (int l = 0; l < KMAX; ++l)
           if (k < K && l < K) {
-            io.M.st((bd.vrow + l) + (bd.vrow + k) * nv, comp6(Fn[k], Ff[k], sub_comp(kind, l)));
+            io.put(bd.vrow + l, bd.vrow + k, nv, comp6(Fn[k], Ff[k], sub_comp(kind, l)));
           }
       // ancestors (decreasing preorder index) and unrelated earlier bodies (zeros)
       int anc = bd.parent;
@@ -492,8 +495,8 @@ RBD_HD void crba_sample(const ModelDev<T>& M, const CrbaIO<T>& io, const Stash<T
             for (int k = 0; k < KMAX; ++k)
               if (k < K) {
                 const T val = comp6(Fn[k], Ff[k], cl);
-                io.M.st((bj.vrow + l) + (bd.vrow + k) * nv, val);
-                io.M.st((bd.vrow + k) + (bj.vrow + l) * nv, val);
+                io.put(bj.vrow + l, bd.vrow + k, nv, val);
+                io.put(bd.vrow + k, bj.vrow + l, nv, val);
               }
           }
         } else {
@@ -501,8 +504,8 @@ RBD_HD void crba_sample(const ModelDev<T>& M, const CrbaIO<T>& io, const Stash<T
 #pragma unroll
             for (int k = 0; k < KMAX; ++k)
               if (k < K) {
-                io.M.st((bj.vrow + l) + (bd.vrow + k) * nv, T(0));
-                io.M.st((bd.vrow + k) + (bj.vrow + l) * nv, T(0));
+                io.put(bj.vrow + l, bd.vrow + k, nv, T(0));
+                io.put(bd.vrow + k, bj.vrow + l, nv, T(0));
               }
         }
       }

@@ -3,6 +3,7 @@
 // The kernels come as a pair, exactly like the generic ones in rbd_b200.cu: single-warp shared-memory blocks on the caller's
 // stream and one Tensor-Memory CTA per SM on the handle's side stream, both claiming groups of 32 samples from one counter.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -161,7 +162,10 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
       if (!jit_get_cubin(m->hm, key, probe, false, &cached, nullptr, e2)) return RBD_OK;
     }
     std::string e2;
-    if (spec_prepare(m, key, true, e2) != RBD_OK) return RBD_OK;      // generic kernels take over; the reason is kept in the entry
+    if (spec_prepare(m, key, true, e2) != RBD_OK) {      // generic kernels take over; the reason is kept in the entry
+      if (getenv("RBD_JIT_VERBOSE")) fprintf(stderr, "[rbd_b200] specialised kernels unavailable: %s\n", e2.c_str());
+      return RBD_OK;
+    }
   }
   const int64_t ngroups = (a.B + 31) / 32;
   const int tm_warps = key.f64 ? 4 : 8;

@@ -163,6 +163,24 @@ class DynamicsResult:
         self.dynamicsbias = torch.empty((nv, batch), dtype=dtype, device=device)
         self._mm = torch.empty((nv * nv, batch), dtype=dtype, device=device) if with_massmatrix else None
         self._mm_args = (nv, batch, dtype, device)
+        self._nb6 = 6 * len(mechanism.joints)
+        self._acc = self._jw = None
+
+    @property
+    def accelerations(self) -> torch.Tensor:
+        """result.accelerations (dynamics_result.jl): [6*nb, B], root frame, allocated on first use."""
+        if self._acc is None:
+            _, batch, dtype, device = self._mm_args
+            self._acc = torch.empty((self._nb6, batch), dtype=dtype, device=device)
+        return self._acc
+
+    @property
+    def jointwrenches(self) -> torch.Tensor:
+        """result.jointwrenches: [6*nb, B], root frame, allocated on first use."""
+        if self._jw is None:
+            _, batch, dtype, device = self._mm_args
+            self._jw = torch.empty((self._nb6, batch), dtype=dtype, device=device)
+        return self._jw
 
     @property
     def massmatrix(self) -> torch.Tensor:

@@ -87,6 +87,7 @@ template <class T> void run_crba(const HostModel& hm, int64_t B, const T* q, T* 
     CrbaIO<T> io;
     io.q = {q + b, B};
     io.M = {Mout + b, B, true};
+    io.lower = false;
     if (multi) crba_sample<T, 1, 6>(M, io, Stash<T, 1>{stash.data()});
     else crba_sample<T, 1, 1>(M, io, Stash<T, 1>{stash.data()});
   }

@@ -563,3 +563,134 @@ def test_axis_aligned_trees_fast_classes_gpu(built, seed):
         st = _gpu_state(mech, q, v, dtype)
         out = rbd.inverse_dynamics(st, torch.from_numpy(vd).to(dtype).cuda(), torch.from_numpy(w).to(dtype).cuda())
         assert rel_err(out.double().cpu().numpy(), ref_id) < (1e-9 if dtype == torch.float64 else 2e-4)
+
+
+# ---- the reference's remaining identity tests through the GPU path (restated against the oracle in tests/test_oracle.py) ----
+def test_external_wrench_momentum_balance_gpu(built):
+    """test/test_mechanism_algorithms.jl:707-727 with tau from the GPU's inverse_dynamics! and the GPU's own kinematics by-products."""
+    from tests.test_oracle import momentum_balance_residual
+    rng = np.random.default_rng(39)
+    mech = rbd.rand_floating_tree_mechanism(rng, [rbd.Revolute] * 10 + [rbd.Planar] * 10 + [rbd.SinCosRevolute] * 5)
+    B = 40
+    q, v, _, vd, w = rand_inputs(mech, B, 39, wext=True)
+    st = _state(mech, q, v, torch.float64)
+    tau = torch.empty((st.nv, B), dtype=torch.float64, device="cuda")
+    rbd.inverse_dynamics_(tau, st, _cu(vd, torch.float64), _cu(w, torch.float64))
+    outs = {"transforms_to_root": torch.empty((12 * len(mech.joints), B), dtype=torch.float64, device="cuda"),
+            "center_of_mass": torch.empty((3, B), dtype=torch.float64, device="cuda"),
+            "momentum_rate_bias": torch.empty((6, B), dtype=torch.float64, device="cuda"),
+            "momentum_matrix": torch.empty((6 * st.nv, B), dtype=torch.float64, device="cuda")}
+    rbd.kinematics_(st, None, **outs)
+    torch.cuda.synchronize()
+    kin = {"transforms": outs["transforms_to_root"].cpu().numpy(), "com": outs["center_of_mass"].cpu().numpy(),
+           "mrb": outs["momentum_rate_bias"].cpu().numpy(), "A": outs["momentum_matrix"].cpu().numpy()}
+    taun = tau.cpu().numpy()
+    for b in range(B):
+        r = momentum_balance_residual(mech, q[:, b], v[:, b], vd[:, b], w[:, b], taun[:, b], {k: a[:, b] for k, a in kin.items()})
+        assert np.abs(r).max() < 1e-9
+
+
+def test_power_flow_gpu(built):
+    """:773-798 with v̇, q̇ and the energies from the GPU path: tau . v + sum_b w_b . twist_b == dE/dt."""
+    from tests.test_oracle import body_twists
+    mech = randmech(43)
+    o = Oracle(mech.flatten())
+    B = 6
+    q, v, tau, _, w = rand_inputs(mech, B, 43, wext=True)
+    vd, qd = gpu_dynamics(mech, q, v, tau, torch.float64, wext=w)
+    tw = body_twists(o, mech, q, v)
+    power = np.einsum("ib,ib->b", tau, v) + np.einsum("ncb,ncb->b", w.reshape(-1, 6, B), tw)
+
+    def energy(qq, vv):
+        st = _state(mech, qq, vv, torch.float64)
+        ke = torch.empty((1, B), dtype=torch.float64, device="cuda"); pe = torch.empty_like(ke)
+        rbd.kinematics_(st, None, kinetic_energy=ke, gravitational_potential_energy=pe)
+        return (ke + pe).cpu().numpy().ravel()
+    h = 1e-6
+    dE = (energy(q + h * qd, v + h * vd) - energy(q - h * qd, v - h * vd)) / (2 * h)
+    assert np.allclose(power, dE, rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_free_rigid_body_closed_form_gpu(built, dtype):
+    """Euler / Newton-Euler closed form of a single QuaternionFloating body (tests/test_oracle.py) through the GPU path."""
+    from tests.test_oracle import free_body_closed_form, free_body_mechanism
+    mech, J, c, m = free_body_mechanism(np.random.default_rng(7), True)
+    q, v, _, _, _ = rand_inputs(mech, 70, 8)
+    got, _ = gpu_dynamics(mech, q, v, None, dtype)
+    ref = np.stack([free_body_closed_form(J, c, m, mech.gravitational_acceleration, q[:4, b], v[:, b]) for b in range(70)], 1)
+    assert rel_err(got, ref) < (1e-11 if dtype == torch.float64 else 2e-5)
+
+
+def test_config3_at_full_batch_gpu(built):
+    """BASELINE config 3 at its stated size: 7-DoF arm, fp32, batch 2^20 -- inverse_dynamics! AND mass_matrix! against the oracle
+    on a strided sub-sample (the oracle takes seconds for ~2000 samples), every entry finite, M symmetric to the last bit."""
+    mech = rbd.load_model("iiwa14")
+    B = 1 << 20
+    st = rbd.MechanismState(mech, B, torch.float32)
+    rbd.rand_(st, np.random.default_rng(3))
+    vd = torch.rand((7, B), dtype=torch.float32, device="cuda")
+    tau = torch.empty_like(vd)
+    rbd.inverse_dynamics_(tau, st, vd)
+    M = torch.empty((49, B), dtype=torch.float32, device="cuda")
+    rbd.mass_matrix_(M, st)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(tau).all()) and bool(torch.isfinite(M).all())
+    M3 = M.view(7, 7, B)
+    assert torch.equal(M3, M3.transpose(0, 1))
+    idx = torch.arange(0, B, 509, device="cuda")
+    o = Oracle(mech.flatten())
+    qn, vn, vdn = (t[:, idx].double().cpu().numpy() for t in (st.q, st.v, vd))
+    assert rel_err(tau[:, idx].double().cpu().numpy(), o.inverse_dynamics(qn, vn, vdn)) < 2e-5
+    assert rel_err(M[:, idx].double().cpu().numpy(), o.mass_matrix(qn)) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_per_body_outputs_and_dynamics_byproducts_gpu(built, dtype):
+    """The reference's per-body arguments of inverse_dynamics! (jointwrenchesout, accelerations) and the by-products dynamics!
+    leaves in the DynamicsResult (massmatrix, dynamicsbias, accelerations, jointwrenches) against the oracle's caches."""
+    tol = TOL[dtype] * (1 if dtype == torch.float64 else 5)
+    for mech in (rbd.load_model("atlas", floating=True), randmech(3, shuffle=True)):
+        o = Oracle(mech.flatten())
+        B = 70
+        q, v, tau, vd, w = rand_inputs(mech, B, 12, wext=True)
+        st = _state(mech, q, v, dtype)
+        nb6 = 6 * len(mech.joints)
+        for wext in (None, w):
+            out = torch.empty((st.nv, B), dtype=dtype, device="cuda")
+            jw = torch.full((nb6, B), float("nan"), dtype=dtype, device="cuda"); acc = torch.full_like(jw, float("nan"))
+            rbd.inverse_dynamics_(out, st, _cu(vd, dtype), _cu(wext, dtype), jointwrenchesout=jw, accelerations=acc)
+            ra, rw = o.inverse_dynamics_bodies(q, v, vd, wext)
+            assert rel_err(acc.double().cpu().numpy(), ra) < tol and rel_err(jw.double().cpu().numpy(), rw) < tol
+        res = rbd.DynamicsResult(mech, B, dtype)
+        rbd.dynamics_(res, st, _cu(tau, dtype), _cu(w, dtype), byproducts="all")
+        vdn = res.vd.double().cpu().numpy()
+        assert rel_err(vdn, o.dynamics(q, v, tau, w)) < tol
+        assert rel_err(res.dynamicsbias.double().cpu().numpy(), o.dynamics_bias(q, v, w)) < tol
+        assert rel_err(res.massmatrix.double().cpu().numpy(), o.mass_matrix(q)) < tol
+        ra, rw = o.inverse_dynamics_bodies(q, v, vdn, w)               # at the v̇ the GPU returned
+        assert rel_err(res.accelerations.double().cpu().numpy(), ra) < tol
+        assert rel_err(res.jointwrenches.double().cpu().numpy(), rw) < tol
+        # M v̇ + c = tau with the by-products themselves (what the reference's dynamics! solves)
+        M = res.massmatrix.double().view(st.nv, st.nv, B)
+        lhs = torch.einsum("jib,jb->ib", M, res.vd.double()) + res.dynamicsbias.double()
+        assert rel_err(lhs.cpu().numpy(), tau) < (1e-8 if dtype == torch.float64 else 2e-3)
+
+
+@pytest.mark.parametrize("name,floating", [("atlas", True), ("iiwa14", False)])
+def test_mass_matrix_lower_triangle_only_gpu(built, name, floating):
+    """rbd_mass_matrix_uplo(RBD_UPLO_LOWER): exactly the lower triangle the reference's mass_matrix! fills, bit-identical to the
+    full result there, everything above the diagonal left untouched."""
+    mech = rbd.load_model(name, floating=floating)
+    B = 300
+    st = rbd.MechanismState(mech, B, torch.float64)
+    rbd.rand_(st, np.random.default_rng(4))
+    nv = st.nv
+    full = rbd.mass_matrix(st).view(nv, nv, B)                   # [j, i, b] = entry (i, j)
+    low = torch.full((nv * nv, B), float("nan"), dtype=torch.float64, device="cuda")
+    rbd.mass_matrix_(low, st, uplo="L")
+    low = low.view(nv, nv, B)
+    jj, ii = torch.meshgrid(torch.arange(nv), torch.arange(nv), indexing="ij")
+    lower = (ii >= jj).cuda()                                    # row i >= column j
+    assert torch.equal(low[lower], full[lower])
+    assert bool(torch.isnan(low[~lower]).all())

@@ -119,3 +119,132 @@ def test_float32_oracle_runs():
     a64 = o.dynamics(q, v, tau)
     a32 = o.dynamics(q, v, tau, dtype=np.float32)
     assert a32.dtype == np.float32 and rel_err(a32, a64) < 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# Further identities of the reference's test-suite restated against the oracle (they involve no stored numbers, so they pin the
+# oracle on mechanisms of any size).  tests/test_gpu_parity.py repeats (a), (b) and the closed form through the GPU path.
+# ----------------------------------------------------------------------------------------------------------------------------
+def _hat(a):
+    return np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+
+
+def momentum_balance_residual(mech, q, v, vd, wext, tau, kin):
+    """test/test_mechanism_algorithms.jl:707-727 for one sample: floating-joint wrench (moved to the root frame) + gravity wrench
+    + sum of external wrenches - (A v̇ + momentum_rate_bias).  `kin` = oracle-style kinematics dict of that sample."""
+    nv = v.shape[0]
+    T = kin["transforms"][:12]                                  # body of tree joint 0 = the floating base
+    R, p = T[:9].reshape(3, 3), T[9:12]
+    n_b, f_b = tau[:3], tau[3:6]                                # QuaternionFloating: tau = body-frame wrench [torque; force]
+    f_w = R @ f_b
+    n_w = R @ n_b + np.cross(p, f_w)
+    mg = mech.mass() * mech.gravitational_acceleration
+    grav = np.concatenate([np.cross(kin["com"], mg), mg])
+    ext = wext.reshape(-1, 6).sum(0)                            # already in the root frame
+    hdot = kin["A"].reshape(nv, 6).T @ vd + kin["mrb"]
+    return np.concatenate([n_w, f_w]) + grav + ext - hdot
+
+
+@pytest.mark.parametrize("seed", [39, 52])
+def test_external_wrench_momentum_balance(seed):
+    rng = np.random.default_rng(seed)
+    mech = rbd.rand_floating_tree_mechanism(rng, [rbd.Revolute] * 10 + [rbd.Planar] * 10 + [rbd.SinCosRevolute] * 5)
+    o = Oracle(mech.flatten())
+    B = 5
+    q, v, _, vd, w = rand_inputs(mech, B, seed, wext=True)
+    tau = o.inverse_dynamics(q, v, vd, w)
+    kin = o.kinematics(q, v, None, want=("transforms", "com", "mrb", "A"))
+    for b in range(B):
+        r = momentum_balance_residual(mech, q[:, b], v[:, b], vd[:, b], w[:, b], tau[:, b], {k: a[:, b] for k, a in kin.items()})
+        assert np.abs(r).max() < 1e-9
+
+
+def body_twists(o, mech, q, v):
+    """twist_wrt_world of every non-root body = geometric Jacobian of the path root -> body times v; [nb, 6, B]."""
+    out = []
+    for body in (j.successor for j in mech.joints):
+        sign = rbd.path(mech, mech.root_body, body).sign
+        J = o.kinematics(q, v, sign, want=("J",))["J"].reshape(o.nv, 6, -1)
+        out.append(np.einsum("kcb,kb->cb", J, v))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("seed", [43, 44])
+def test_power_flow(seed):
+    """:773-798: tau . v + sum_b w_ext,b . twist_b == d/dt (kinetic + gravitational potential energy) along the solution."""
+    mech = randmech(seed)
+    o = Oracle(mech.flatten())
+    B = 4
+    q, v, tau, _, w = rand_inputs(mech, B, seed, wext=True)
+    vd, qd = o.dynamics(q, v, tau, w, want_qd=True)
+    tw = body_twists(o, mech, q, v)
+    power = np.einsum("ib,ib->b", tau, v) + np.einsum("ncb,ncb->b", w.reshape(-1, 6, B), tw)
+    h = 1e-6
+
+    def energy(qq, vv):
+        k = o.kinematics(qq, vv, None, want=("ke", "pe"))
+        return (k["ke"] + k["pe"]).ravel()
+    dE = (energy(q + h * qd, v + h * vd) - energy(q - h * qd, v - h * vd)) / (2 * h)
+    assert np.allclose(power, dE, rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("seed", [45, 46])
+def test_mass_matrix_rate_minus_two_coriolis_is_skew_on_random_trees(seed):
+    """:616-652 on the 25-joint trees with every joint type: v'(Ṁ - 2C)v = 0, i.e. v . c = 1/2 v' Ṁ v without gravity, with
+    Ṁ the derivative of M along q̇ = N(q) v."""
+    mech = randmech(seed, shuffle=True)
+    mech.gravitational_acceleration[:] = 0
+    o = Oracle(mech.flatten())
+    q, v, tau, _, _ = rand_inputs(mech, 3, seed)
+    _, qd = o.dynamics(q, v, tau, want_qd=True)
+    M = lambda qq: o.mass_matrix(qq).reshape(o.nv, o.nv, -1).transpose(1, 0, 2)
+    h = 1e-6
+    Mdot = (M(q + h * qd) - M(q - h * qd)) / (2 * h)
+    lhs = np.einsum("ib,ib->b", v, o.dynamics_bias(q, v))
+    rhs = 0.5 * np.einsum("ib,ijb,jb->b", v, Mdot, v)
+    assert np.allclose(lhs, rhs, rtol=1e-6, atol=1e-5)
+
+
+def free_body_closed_form(J, c, m, g, quat, v):
+    """Newton-Euler equations of ONE free rigid body written out with 3-vectors (textbook form, independent of the oracle's
+    spatial algebra): body-frame twist v = [w; u] of the body origin, inertia J about the origin, centre of mass c.
+        m (u̇ + w x u + ẇ x c + w x (w x c)) = m R' g
+        J ẇ + w x J w + m c x (u̇ + w x u) = m c x R' g
+    Returns v̇ = [ẇ; u̇] -- what dynamics! must give for a QuaternionFloating joint with zero torque."""
+    w_, x, y, z = quat
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w_ * z), 2 * (x * z + w_ * y)],
+                  [2 * (x * y + w_ * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w_ * x)],
+                  [2 * (x * z - w_ * y), 2 * (y * z + w_ * x), 1 - 2 * (x * x + y * y)]])
+    w, u = v[:3], v[3:]
+    gb = R.T @ g
+    # unknowns [ẇ; u̇]:  [[J, m ĉ], [-m ĉ, m 1]] [ẇ; u̇] = rhs
+    A = np.block([[J, m * _hat(c)], [-m * _hat(c), m * np.eye(3)]])
+    rhs = np.concatenate([m * np.cross(c, gb) - np.cross(w, J @ w) - m * np.cross(c, np.cross(w, u)),
+                          m * gb - m * np.cross(w, u) - m * np.cross(w, np.cross(w, c))])
+    return np.linalg.solve(A, rhs)
+
+
+def free_body_mechanism(rng, com_offset=True):
+    mech = rbd.Mechanism(rbd.RigidBody("world"), gravity=(0.3, -0.2, -9.81))
+    Jc = rng.random((3, 3)); Jc = Jc @ Jc.T + np.eye(3)            # inertia about the centre of mass
+    c = rng.standard_normal(3) * (0.3 if com_offset else 0.0)
+    m = 2.5
+    J = Jc + m * (c @ c * np.eye(3) - np.outer(c, c))              # parallel axes: about the frame origin
+    mech.attach(mech.root_body, rbd.RigidBody("body", rbd.SpatialInertia(J, m * c, m)), rbd.Joint("free", rbd.QuaternionFloating()))
+    return mech, J, c, m
+
+
+@pytest.mark.parametrize("com_offset", [False, True])
+def test_free_rigid_body_closed_form(com_offset):
+    """Euler's equations (com at the origin) / the general Newton-Euler form (com offset) for a single QuaternionFloating body:
+    pins the floating-joint conventions (body-frame twist, world-frame gravity) that the planar pendulum cannot."""
+    rng = np.random.default_rng(7)
+    mech, J, c, m = free_body_mechanism(rng, com_offset)
+    o = Oracle(mech.flatten())
+    q, v, _, _, _ = rand_inputs(mech, 6, 8)
+    got = o.dynamics(q, v, None)
+    for b in range(6):
+        ref = free_body_closed_form(J, c, m, mech.gravitational_acceleration, q[:4, b], v[:, b])
+        assert np.allclose(got[:, b], ref, rtol=0, atol=1e-11)
+        if not com_offset:                                           # Euler's equations proper
+            assert np.allclose(J @ got[:3, b] + np.cross(v[:3, b], J @ v[:3, b]), 0, atol=1e-11)

