@@ -201,36 +201,6 @@ aba_kernel_tmem_q(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
   tmem_free_cta<COLS>(tm_base);
 }
 
-#if defined(RBD_EXPERIMENTS)
-// Experimental variant: the stash lives in global memory (L2-resident scratch), occupancy is register-limited.
-template <class T, int NT, bool GENERAL>
-__global__ void __launch_bounds__(NT) aba_kernel_gstash(const __grid_constant__ ModelDev<T> M, const AbaArgs<T> a) {
-  const Stash<T, 0> st{a.scratch + (int64_t)blockIdx.x * NT + threadIdx.x, (int64_t)gridDim.x * NT};
-  const int64_t ngroups = (a.B + NT - 1) / NT;
-  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    const int64_t gn = g + gridDim.x;
-    if (gn < ngroups) {
-      const int64_t bn = gn * NT + (threadIdx.x & ~31);
-      prefetch_rows(a.q, M.nq, a.ld, bn);
-      prefetch_rows(a.v, M.nv, a.ld, bn);
-      prefetch_rows(a.tau, M.nv, a.ld, bn);
-    }
-    const int64_t b = g * NT + threadIdx.x;
-    const bool active = b < a.B;
-    const int64_t bl = active ? b : a.B - 1;
-    AbaIO<T, false> io;
-    io.q = {a.q + bl, a.ld};
-    io.v = {a.v + bl, a.ld};
-    io.tau = {a.tau ? a.tau + bl : nullptr, a.ld};
-    io.wext = {nullptr, a.ld};
-    io.vd = {a.vd + bl, a.ld, active};
-    io.qd = {a.qd ? a.qd + bl : nullptr, a.ld, active};
-    io.ext = {nullptr, 0};
-    aba_sample<T, Stash<T, 0>, GENERAL>(M, io, st);
-  }
-}
-
-#endif  // RBD_EXPERIMENTS
 
 // dynamics! on Dual{Float64,6} arrays: thread t of the launch owns (sample t / 6, partial direction t % 6).
 struct DualArgs {
@@ -757,9 +727,7 @@ int dynamics_dual(const rbd_model* model, int64_t B, int64_t ld, const void* q, 
     d.qoff = Dual64(s.qoff);
     d.kind = s.kind; d.parent = s.parent; d.qrow = s.qrow; d.vrow = s.vrow; d.row0 = s.row0;
     d.oslot = s.oslot; d.pslot = s.pslot; d.flags = s.flags; d.refidx = s.refidx;
-    d.pair = s.pair; d.next_fwd = s.next_fwd; d.next_rev = s.next_rev;
   }
-  Mp->last_head = S.last_head; Mp->npairs = S.npairs;
   const DualArgs a{(const double*)q, (const double*)v, (const double*)tau, (double*)vd, ld, B};
   DeviceProps p;
   if (int rc = get_props(p)) return rc;

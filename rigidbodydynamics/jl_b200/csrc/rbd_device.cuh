@@ -53,49 +53,6 @@ template <class T, int STRIDE> struct Stash {
   RBD_HD void fence_st() const {}                          // stores are visible to later loads of the same thread
   RBD_HD const Stash& slots() const { return *this; }     // pending slots live in the same array
 };
-// STRIDE == 0: runtime stride (the stash lives in a global-memory scratch, one column per resident thread)
-template <class T> struct Stash<T, 0> {
-  T* p;
-  int64_t stride;
-  RBD_HD T ld(int row) const { return p[(int64_t)row * stride]; }
-  RBD_HD void st(int row, T v) const { p[(int64_t)row * stride] = v; }
-  RBD_HD void add(int row, T v) const { p[(int64_t)row * stride] += v; }
-  template <int N> RBD_HD void ldv(int row, T* out) const {
-#pragma unroll
-    for (int k = 0; k < N; ++k) out[k] = p[(int64_t)(row + k) * stride];
-  }
-  RBD_HD void fence_st() const {}
-  RBD_HD const Stash& slots() const { return *this; }
-};
-// Body rows in shared memory ([row][lane]); the pending slots -- touched only a handful of times per sample -- in a
-// global scratch column that stays L2-resident.  Frees 2 x 27 rows of shared memory per sample on Atlas (7 -> 9 warps/SM).
-template <class T, int STRIDE> struct StashGS {
-  T* p;
-  T* g;               // slot row r of this thread at g[(r - slot_base) * gstride]
-  int64_t gstride;
-  int slot_base;
-  RBD_HD T ld(int row) const { return p[row * STRIDE]; }
-  RBD_HD void st(int row, T v) const { p[row * STRIDE] = v; }
-  RBD_HD void add(int row, T v) const { p[row * STRIDE] += v; }
-  template <int N> RBD_HD void ldv(int row, T* out) const {
-#pragma unroll
-    for (int k = 0; k < N; ++k) out[k] = p[(row + k) * STRIDE];
-  }
-  RBD_HD void fence_st() const {}
-  struct Slots {
-    T* g; int64_t gstride; int base;
-    RBD_HD T ld(int row) const { return g[(int64_t)(row - base) * gstride]; }
-    RBD_HD void st(int row, T v) const { g[(int64_t)(row - base) * gstride] = v; }
-    RBD_HD void add(int row, T v) const { g[(int64_t)(row - base) * gstride] += v; }
-    template <int N> RBD_HD void ldv(int row, T* out) const {
-#pragma unroll
-      for (int k = 0; k < N; ++k) out[k] = g[(int64_t)(row + k - base) * gstride];
-    }
-    RBD_HD void fence_st() const {}
-  };
-  RBD_HD Slots slots() const { return Slots{g, gstride, slot_base}; }
-};
-
 // Read-only view of one sample's column in a rows x batch array (element (k, b) at base[k * ld + b]).
 template <class T> struct Col {
   const T* p;      // already offset by the sample index
@@ -1181,183 +1138,44 @@ RBD_HD void aba_pass3_multi(const ModelDev<T>& M, int i, const IO& io, const ST&
   save_own_va(M, bd, st, v, a);
 }
 
-// ---- paired steps: two sibling revolute chains walked in lock-step -----------------------------------------------
-// Both bodies of a pair are K_REV / K_SINCOS, have a real parent, sit at the same depth of equal-length chains (so they are
-// leaves together) and carry the serial flags of rbd_model.cpp; lane 0 (`i0`) shares the chain registers of the single
-// steps, lane 1 (`i1`, later in preorder, never a first child at its top) has its own.  The arithmetic of the two lanes is
-// written as straight-line code in ONE block so the scheduler interleaves the two independent dependency chains.
-template <class T, class ST, class IO>
-RBD_HD void aba_pass1_pair(const ModelDev<T>& M, int i0, int i1, const IO& io, const ST& st, Mot<T>& v0, Mot<T>& v1,
-                           const Pre<T>& p0, const Pre<T>& p1) {
-  const BodyDev<T>& b0 = M.body[i0];
-  const BodyDev<T>& b1 = M.body[i1];
-  Mot<T> vp0, vp1;
-  if (b0.flags & F_FIRST_CHILD) vp0 = v0;
-  else {
-    const int pr = M.body[b0.parent].row0;
-    st.fence_st();
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { vp0.w[k] = st.ld(pr + k); vp0.l[k] = st.ld(pr + 3 + k); }
-  }
-  if (b1.flags & F_FIRST_CHILD) vp1 = v1;
-  else {
-    const int pr = M.body[b1.parent].row0;
-    st.fence_st();
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { vp1.w[k] = st.ld(pr + k); vp1.l[k] = st.ld(pr + 3 + k); }
-  }
-  T s0, c0, d0, s1, c1, d1, R0[9], r0[3], R1[9], r1[3];
-  joint_scd(b0.kind, p0, s0, c0, d0);
-  joint_scd(b1.kind, p1, s1, c1, d1);
-  frame_1dof(b0, s0, c0, T(0), R0, r0);
-  frame_1dof(b1, s1, c1, T(0), R1, r1);
-  Mot<T> a, b;
-  motion_to_child(R0, r0, vp0, a);
-  motion_to_child(R1, r1, vp1, b);
-  a.w[2] += p0.qd;
-  b.w[2] += p1.qd;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    st.st(b0.row0 + k, a.w[k]); st.st(b0.row0 + 3 + k, a.l[k]);
-    st.st(b1.row0 + k, b.w[k]); st.st(b1.row0 + 3 + k, b.l[k]);
-  }
-  v0 = a; v1 = b;
-  if (io.qd.valid()) { qdot_joint(b0, io.q, io.v, io.qd); qdot_joint(b1, io.q, io.v, io.qd); }
-}
-
-template <class T, class ST, class IO>
-RBD_HD void aba_pass2_pair(const ModelDev<T>& M, int i0, int i1, const IO& io, const ST& st, Art<T>& c0, Art<T>& c1,
-                           const Pre<T>& p0, const Pre<T>& p1) {
-  const BodyDev<T>& b0 = M.body[i0];
-  const BodyDev<T>& b1 = M.body[i1];
-  Mot<T> v0, v1;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    v0.w[k] = st.ld(b0.row0 + k); v0.l[k] = st.ld(b0.row0 + 3 + k);
-    v1.w[k] = st.ld(b1.row0 + k); v1.l[k] = st.ld(b1.row0 + 3 + k);
-  }
-  Art<T> a0, a1;
-  art_set_body(b0, a0);
-  art_set_body(b1, a1);
-  bias_force(b0, v0, a0.n, a0.f);
-  bias_force(b1, v1, a1.n, a1.f);
-  if (!(b0.flags & F_LEAF)) { art_add(a0, c0); art_add(a1, c1); }      // equal-length chains: leaves together
-  T tU0[5], tu0, tU1[5], tu1;
-  Art<T> e0, e1;
-  rev_eliminate(a0, v0, p0.qd, p0.tau, tU0, tu0, e0);
-  rev_eliminate(a1, v1, p1.qd, p1.tau, tU1, tu1, e1);
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { st.st(b0.row0 + k, tU0[k]); st.st(b1.row0 + k, tU1[k]); }
-  st.st(b0.row0 + 5, tu0);
-  st.st(b1.row0 + 5, tu1);
-  T s0, cc0, d0, s1, cc1, d1, R0[9], r0[3], R1[9], r1[3];
-  joint_scd(b0.kind, p0, s0, cc0, d0);
-  joint_scd(b1.kind, p1, s1, cc1, d1);
-  frame_1dof(b0, s0, cc0, T(0), R0, r0);
-  frame_1dof(b1, s1, cc1, T(0), R1, r1);
-  art_to_parent<T, true>(R0, r0, e0, c0);
-  art_to_parent<T, true>(R1, r1, e1, c1);
-  hand_over(M, b1, st, c1);     // serial order: the later chain reaches the parent's slot first
-  hand_over(M, b0, st, c0);
-}
-
-// outward step of a revolute-z body from (vp, ap) of its parent: v, a, and the joint acceleration (stored)
-template <class T, class ST, class IO>
-RBD_HD void rev_pass3_core(const BodyDev<T>& bd, const IO& io, const ST& st, const Pre<T>& pre, const Mot<T>& vp,
-                           const Mot<T>& ap, Mot<T>& v, Mot<T>& a) {
-  T sn, c, dd, R[9], r[3];
-  joint_scd(bd.kind, pre, sn, c, dd);
-  const T qd = pre.qd;
-  const T t0 = st.ld(bd.row0 + 0), t1 = st.ld(bd.row0 + 1), t2 = st.ld(bd.row0 + 2), t3 = st.ld(bd.row0 + 3),
-          t4 = st.ld(bd.row0 + 4), tu = st.ld(bd.row0 + 5);
-  Mot<T> xa;
-  frame_1dof(bd, sn, c, T(0), R, r);
-  motion_to_child(R, r, vp, v);
-  motion_to_child(R, r, ap, xa);
-  v.w[2] += qd;
-  const T vd = tu - (t0 * xa.w[0] + t1 * xa.w[1] + xa.w[2] + t2 * xa.l[0] + t3 * xa.l[1] + t4 * xa.l[2]);
-  io.vd.st(bd.vrow, vd);
-  a.w[0] = xa.w[0] + qd * v.w[1]; a.w[1] = xa.w[1] - qd * v.w[0]; a.w[2] = xa.w[2] + vd;
-  a.l[0] = xa.l[0] + qd * v.l[1]; a.l[1] = xa.l[1] - qd * v.l[0]; a.l[2] = xa.l[2];
-}
-
-template <class T, class ST, class IO>
-RBD_HD void aba_pass3_pair(const ModelDev<T>& M, int i0, int i1, const IO& io, const ST& st, Mot<T>& v0, Mot<T>& a0,
-                           Mot<T>& v1, Mot<T>& a1, const Pre<T>& p0, const Pre<T>& p1) {
-  const BodyDev<T>& b0 = M.body[i0];
-  const BodyDev<T>& b1 = M.body[i1];
-  Mot<T> vp0, ap0, vp1, ap1, nv0, na0, nv1, na1;
-  load_parent_va(M, b0, st, v0, a0, vp0, ap0);
-  load_parent_va(M, b1, st, v1, a1, vp1, ap1);
-  rev_pass3_core(b0, io, st, p0, vp0, ap0, nv0, na0);
-  rev_pass3_core(b1, io, st, p1, vp1, ap1, nv1, na1);
-  v0 = nv0; a0 = na0; v1 = nv1; a1 = na1;
-}
-
 // ---- whole algorithm for one sample -------------------------------------------------------------------------------
-// GENERAL = false: bodies 1..nb-1 are 1-DoF or fixed (multi-DoF joint allowed only at position 0 under the world); in that
-// case paired steps (see above) are honoured.  GENERAL = true walks every body singly.
+// GENERAL = false: bodies 1..nb-1 are 1-DoF or fixed (a multi-DoF joint is allowed only at position 0 under the world), so the
+// loops carry 1-DoF code only.  GENERAL = true dispatches every body on its kind.
+// (Tried and removed: walking two sibling revolute chains in lock-step for 2x instruction-level parallelism -- 601 M vs 666 M
+// evals/s on Atlas, the second copy of the inlined step bodies overflowed the instruction cache.  DESIGN.md section 7.)
 template <class T, class ST, bool GENERAL, class IO>
 RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
-  // Paired steps are implemented and pass every parity test, but measured SLOWER on B200 (601 M vs 666 M evals/s on Atlas):
-  // the second copy of the inlined step bodies pushes the hot code past the instruction cache (no_instruction stalls
-  // 0.17 -> 0.43 per issue) and the gain in ILP does not make up for it.  Compiled out unless RBD_ENABLE_PAIRS is defined.
-#if defined(RBD_ENABLE_PAIRS)
-  constexpr bool PAIRS = !GENERAL && !IO::kExt;
-#else
-  constexpr bool PAIRS = false;
-#endif
   const int nb = M.nb;
-  Mot<T> vcur, acur, vB, aB;
+  Mot<T> vcur, acur;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    vcur.w[k] = vcur.l[k] = acur.w[k] = acur.l[k] = T(0);
-    vB.w[k] = vB.l[k] = aB.w[k] = aB.l[k] = T(0);
-  }
-  // ---- pass 1 (loads for the next step are in flight while this step is processed) ----
-  Pre<T> cur, nxt, curB, nxtB;
+  for (int k = 0; k < 3; ++k) vcur.w[k] = vcur.l[k] = acur.w[k] = acur.l[k] = T(0);
+  // ---- pass 1 (loads for the next body are in flight while this body is processed) ----
+  Pre<T> cur, nxt;
   prefetch_body<T, 1>(M, 0, io, cur);
-  prefetch_body<T, 1>(M, PAIRS ? M.body[0].pair : -1, io, curB);
-  int i1 = 0;
-  if (!PAIRS) {     // body 0 may be multi-DoF in any model; peeled so the loop of a non-GENERAL model carries 1-DoF code only
-    prefetch_body<T, 1>(M, 1, io, nxt);
-    aba_pass1_body<T, ST, true>(M, 0, io, st, vcur, cur);
+  prefetch_body<T, 1>(M, 1, io, nxt);
+  aba_pass1_body<T, ST, true>(M, 0, io, st, vcur, cur);      // body 0 may be multi-DoF in any model: peeled
+  cur = nxt;
+  for (int i = 1; i < nb; ++i) {
+    prefetch_body<T, 1>(M, i + 1, io, nxt);
+    aba_pass1_body<T, ST, GENERAL>(M, i, io, st, vcur, cur);
     cur = nxt;
-    i1 = 1;
-  }
-  for (int i = i1; i < nb;) {
-    const int j = PAIRS ? M.body[i].pair : -1;
-    const int in = PAIRS ? M.body[i].next_fwd : i + 1;
-    prefetch_body<T, 1>(M, in, io, nxt);
-    if (PAIRS) prefetch_body<T, 1>(M, in < nb ? M.body[in].pair : -1, io, nxtB);
-    if (PAIRS && j >= 0) aba_pass1_pair(M, i, j, io, st, vcur, vB, cur, curB);
-    else aba_pass1_body<T, ST, GENERAL || PAIRS>(M, i, io, st, vcur, cur);
-    cur = nxt; curB = nxtB;
-    i = in;
   }
   // ---- pass 2 ----
   st.fence_st();
-  Art<T> carry, carryB;
+  Art<T> carry;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { carry.A[k] = T(0); carry.C[k] = T(0); carryB.A[k] = T(0); carryB.C[k] = T(0); }
+  for (int k = 0; k < 6; ++k) { carry.A[k] = T(0); carry.C[k] = T(0); }
 #pragma unroll
-  for (int k = 0; k < 9; ++k) { carry.B[k] = T(0); carryB.B[k] = T(0); }
+  for (int k = 0; k < 9; ++k) carry.B[k] = T(0);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { carry.n[k] = T(0); carry.f[k] = T(0); carryB.n[k] = T(0); carryB.f[k] = T(0); }
-  const int last = PAIRS ? M.last_head : nb - 1;
-  prefetch_body<T, 2>(M, last, io, cur);
-  prefetch_body<T, 2>(M, PAIRS ? M.body[last].pair : -1, io, curB);
-  for (int i = last; i >= 1;) {
+  for (int k = 0; k < 3; ++k) { carry.n[k] = T(0); carry.f[k] = T(0); }
+  prefetch_body<T, 2>(M, nb - 1, io, cur);
+  for (int i = nb - 1; i >= 1; --i) {
     const int kind = M.body[i].kind;
-    const int j = PAIRS ? M.body[i].pair : -1;
-    const int ip = PAIRS ? M.body[i].next_rev : i - 1;
-    prefetch_body<T, 2>(M, ip, io, nxt);
-    if (PAIRS) prefetch_body<T, 2>(M, ip >= 0 ? M.body[ip].pair : -1, io, nxtB);
-    const Pre<T> now = cur, nowB = curB;
-    cur = nxt; curB = nxtB;
-    if (PAIRS && j >= 0) {
-      aba_pass2_pair(M, i, j, io, st, carry, carryB, now, nowB);
-    } else if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
+    prefetch_body<T, 2>(M, i - 1, io, nxt);
+    const Pre<T> now = cur;
+    cur = nxt;
+    if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass2_1dof(M, i, io, st, carry, now);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
       aba_pass2_multi<T, ST, 6, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
@@ -1366,15 +1184,12 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
     } else {
       aba_pass2_multi<T, ST, 3, K_QFLOAT, false>(M, i, io, st, carry, vcur, acur);
     }
-    i = ip;
   }
   // body 0: inward step, then the outward pass starts here
-  const int first = PAIRS ? M.body[0].next_fwd : 1;
   {
     const BodyDev<T>& b0 = M.body[0];
     const int kind = b0.kind;
-    prefetch_body<T, 3>(M, first, io, nxt);
-    if (PAIRS) prefetch_body<T, 3>(M, first < nb ? M.body[first].pair : -1, io, nxtB);
+    prefetch_body<T, 3>(M, 1, io, nxt);
     if (kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass2_1dof(M, 0, io, st, carry, cur);
       st.fence_st();
@@ -1392,18 +1207,13 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
   }
   // ---- pass 3 ----
   st.fence_st();
-  cur = nxt; curB = nxtB;
-  for (int i = first; i < nb;) {
+  cur = nxt;
+  for (int i = 1; i < nb; ++i) {
     const int kind = M.body[i].kind;
-    const int j = PAIRS ? M.body[i].pair : -1;
-    const int in = PAIRS ? M.body[i].next_fwd : i + 1;
-    prefetch_body<T, 3>(M, in, io, nxt);
-    if (PAIRS) prefetch_body<T, 3>(M, in < nb ? M.body[in].pair : -1, io, nxtB);
-    const Pre<T> now = cur, nowB = curB;
-    cur = nxt; curB = nxtB;
-    if (PAIRS && j >= 0) {
-      aba_pass3_pair(M, i, j, io, st, vcur, acur, vB, aB, now, nowB);
-    } else if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
+    prefetch_body<T, 3>(M, i + 1, io, nxt);
+    const Pre<T> now = cur;
+    cur = nxt;
+    if (!GENERAL || kind == K_REV || kind == K_PRIS || kind == K_SINCOS || kind == K_FIXED) {
       aba_pass3_1dof(M, i, io, st, vcur, acur, now);
     } else if (kind == K_QFLOAT || kind == K_SPQFLOAT) {
       aba_pass3_multi<T, ST, 6, K_QFLOAT>(M, i, io, st, vcur, acur);
@@ -1412,7 +1222,6 @@ RBD_HD void aba_sample(const ModelDev<T>& M, const IO& io, const ST& st) {
     } else {
       aba_pass3_multi<T, ST, 3, K_QFLOAT>(M, i, io, st, vcur, acur);
     }
-    i = in;
   }
 }
 

@@ -86,9 +86,7 @@ template <class T> void fill_dev(const HostModel& hm, const ModelDev<double>& sr
     d.qoff = (T)s.qoff;
     d.kind = s.kind; d.parent = s.parent; d.qrow = s.qrow; d.vrow = s.vrow; d.row0 = s.row0;
     d.oslot = s.oslot; d.pslot = s.pslot; d.flags = s.flags; d.refidx = s.refidx;
-    d.pair = s.pair; d.next_fwd = s.next_fwd; d.next_rev = s.next_rev;
   }
-  dst.last_head = src.last_head; dst.npairs = src.npairs;
   (void)hm;
 }
 
@@ -145,8 +143,9 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
   std::vector<std::vector<int>> children(nb);
   std::vector<int> roots;
   for (int i = 0; i < nb; ++i) (desc->parent[i] < 0 ? roots : children[desc->parent[i]]).push_back(i);
-  // Limb pairing: sibling subtrees that are pure revolute chains of equal length (the legs / arms of a humanoid) are walked
-  // in lock-step by the ABA kernel.  Paired children are placed first and adjacent (L then R).
+  // Ordering heuristic: sibling subtrees that are pure revolute chains of equal length (the legs / arms of a humanoid) are
+  // placed first and adjacent (L then R).  (It once fed a lock-step walk of such pairs, measured slower and removed; the order
+  // is kept because the slot colouring below and every measurement in DESIGN.md were made with it.)
   struct PairRec { int L, R, len; };
   std::vector<PairRec> pairs;
   {
@@ -338,25 +337,6 @@ int build_host_model(const rbd_model_desc* desc, HostModel& out, std::string& er
     else row += 7 * k;                                    // U~ (6k) + u~ (k), also holds v (6) between passes 1 and 2
   }
   // (a non-first child implies >= 2 children, so its parent always owns a slot)
-  // paired steps and the step-head links
-  for (int p = 0; p < nb; ++p) M.body[p].pair = -1;
-  for (const PairRec& pr : pairs) {
-    const int lp = out.pos[pr.L], rp = out.pos[pr.R];
-    if (rp != lp + pr.len) continue;     // not adjacent after ordering: leave both chains as single steps
-    for (int k = 0; k < pr.len; ++k) { M.body[lp + k].pair = rp + k; M.body[rp + k].pair = -2; }
-    M.npairs += pr.len;
-  }
-  {
-    int prev = -1;
-    for (int p = 0; p < nb; ++p) {
-      if (M.body[p].pair == -2) { M.body[p].next_fwd = nb; M.body[p].next_rev = -1; continue; }
-      M.body[p].next_rev = prev;
-      if (prev >= 0) M.body[prev].next_fwd = p;
-      prev = p;
-    }
-    if (prev >= 0) M.body[prev].next_fwd = nb;
-    M.last_head = prev;
-  }
   M.slot_base = row;
   M.nslots = nslots;
   M.nrows = row + nslots * kSlotRowsAba;

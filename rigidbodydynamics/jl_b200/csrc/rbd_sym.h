@@ -221,7 +221,6 @@ struct SymStash {
 // Model constants as literals of the trace.
 template <class F> inline void sym_model(const ModelDev<F>& S, ModelDev<Sym>& D) {
   D.nb = S.nb; D.nq = S.nq; D.nv = S.nv; D.nrows = S.nrows; D.slot_base = S.slot_base; D.nslots = S.nslots;
-  D.last_head = S.last_head; D.npairs = S.npairs;
   for (int k = 0; k < 3; ++k) D.g[k] = Sym((double)S.g[k]);
   D.pad_ = Sym(0.0);
   for (int i = 0; i < S.nb; ++i) {
@@ -234,7 +233,6 @@ template <class F> inline void sym_model(const ModelDev<F>& S, ModelDev<Sym>& D)
     d.qoff = Sym((double)s.qoff);
     d.kind = s.kind; d.parent = s.parent; d.qrow = s.qrow; d.vrow = s.vrow; d.row0 = s.row0;
     d.oslot = s.oslot; d.pslot = s.pslot; d.flags = s.flags; d.refidx = s.refidx;
-    d.pair = s.pair; d.next_fwd = s.next_fwd; d.next_rev = s.next_rev;
   }
 }
 

@@ -55,11 +55,6 @@ template <class T> struct BodyDev {
   int32_t pslot;      // index of the parent's pending slot (valid if !F_FIRST_CHILD && !F_ROOT_CHILD), else -1
   int32_t flags;
   int32_t refidx;     // joint index in the reference order (row 6*refidx of wext)
-  // Limb pairing (ABA fast path): two sibling revolute chains of equal length are walked in lock-step by one thread so
-  // their independent dependency chains interleave (instruction-level parallelism x2 on the critical path).
-  int32_t pair;       // >= 0: this body heads a paired step, `pair` is its partner (lane 1); -1: single step; -2: lane 1
-  int32_t next_fwd;   // next step head in forward order (nb = end)
-  int32_t next_rev;   // previous step head (-1 = end)
 };
 
 template <class T> struct ModelDev {
@@ -67,8 +62,6 @@ template <class T> struct ModelDev {
   int32_t nrows;      // total ABA stash rows per sample (body rows + pending slots)
   int32_t slot_base;  // first ABA stash row of pending slot 0 (slot s starts at slot_base + s * kSlotRowsAba)
   int32_t nslots;
-  int32_t last_head;  // last step head (start of the inward pass)
-  int32_t npairs;
   T g[3];             // gravitational acceleration, root frame
   T pad_;
   BodyDev<T> body[kMaxBodies];

@@ -206,9 +206,7 @@ int hostsim_dynamics_dual(const rbd_model_desc* d, int64_t B, const double* q, c
     b.qoff = Dual64(s.qoff);
     b.kind = s.kind; b.parent = s.parent; b.qrow = s.qrow; b.vrow = s.vrow; b.row0 = s.row0;
     b.oslot = s.oslot; b.pslot = s.pslot; b.flags = s.flags; b.refidx = s.refidx;
-    b.pair = s.pair; b.next_fwd = s.next_fwd; b.next_rev = s.next_rev;
   }
-  M.last_head = S.last_head; M.npairs = S.npairs;
   std::vector<Dual64> stash(M.nrows + 64);
   for (int64_t b = 0; b < B; ++b)
     for (int dir = 0; dir < 6; ++dir) {
