@@ -14,7 +14,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 12;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 14;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -346,23 +346,29 @@ uint64_t spec_hash(const HostModel& hm, const SpecKey& key) {
 }
 
 bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, std::string& out, SpecStats* stats, std::string& err) {
-  char buf[640];
+  // the three per-sample functions first (their size decides a code-shape switch in the header)
+  std::string fn_smem, fn_tmem, fn_uni;
+  SpecStats st;
+  if (!spec_emit_function(hm, key, FLAVOR_SMEM, "rbd_spec_smem", fn_smem, &st, err)) return false;
+  if (!spec_emit_function(hm, key, FLAVOR_TMEM, "rbd_spec_tmem", fn_tmem, nullptr, err)) return false;
+  if (!spec_emit_function(hm, key, FLAVOR_UNI, "rbd_spec_uni", fn_uni, nullptr, err)) return false;
+  if (stats) *stats = st;
+  char buf[768];
   const int rows = spec_stash_rows(hm, key);
   snprintf(buf, sizeof buf,
+           "// generated by librbd_b200.so (rbd_codegen.cpp) for one mechanism: %d live nodes (%d add/sub, %d mul, %d div, %d sincos, "
+           "%d global loads, %d stash loads, %d stash stores)\n"
            "#define RBD_SPEC_F64 %d\n#define RBD_SPEC_NQ %d\n#define RBD_SPEC_NV %d\n#define RBD_SPEC_ROWS %d\n"
            "#define RBD_SPEC_HAS_IN2 %d\n#define RBD_SPEC_HAS_OUT1 %d\n#define RBD_SPEC_OUT0_ROWS %d\n#define RBD_SPEC_OUT1_ROWS %d\n"
            "#define RBD_UNI_SW %d\n#include \"rbd_jit_prelude.cuh\"\n",
+           st.nodes_live, st.n_add, st.n_mul, st.n_div, st.n_sincos, st.n_load, st.n_sld, st.n_sst,
            key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, hm.nv, hm.nq,
            std::max(4, spec_uni_smem_warps(hm, key)));
   out += buf;
-  out += "#define RBD_FLAVOR_SMEM 1\n#include \"rbd_jit_flavor.cuh\"\n";
-  if (!spec_emit_function(hm, key, FLAVOR_SMEM, "rbd_spec_smem", out, stats, err)) return false;
-  out += "#undef RBD_FLAVOR_SMEM\n#define RBD_FLAVOR_TMEM 1\n#include \"rbd_jit_flavor.cuh\"\n";
-  if (!spec_emit_function(hm, key, FLAVOR_TMEM, "rbd_spec_tmem", out, nullptr, err)) return false;
-  out += "#undef RBD_FLAVOR_TMEM\n#define RBD_FLAVOR_UNI 1\n#include \"rbd_jit_flavor.cuh\"\n";
-  if (!spec_emit_function(hm, key, FLAVOR_UNI, "rbd_spec_uni", out, nullptr, err)) return false;
-  out += "#undef RBD_FLAVOR_UNI\n";
-  out += "#include \"rbd_jit_kernels.cuh\"\n";
+  out += "#define RBD_FLAVOR_SMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_smem;
+  out += "#undef RBD_FLAVOR_SMEM\n#define RBD_FLAVOR_TMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_tmem;
+  out += "#undef RBD_FLAVOR_TMEM\n#define RBD_FLAVOR_UNI 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_uni;
+  out += "#undef RBD_FLAVOR_UNI\n#include \"rbd_jit_kernels.cuh\"\n";
   return true;
 }
 

@@ -18,6 +18,7 @@ struct Env {
   int64_t min_batch = 1 << 15;      // below this a missing cubin is not compiled on the fly (generic kernels serve the call)
   int smem_blocks = 0;
   int variant = 0;                  // RBD_JIT_VARIANT=1 (pair) / 2 (unified): skip the tuning
+  const char* only = nullptr;       // RBD_ONLY=smem|tmem: launch one kernel of the pair (ncu captures: the profiler serialises them)
   Env() {
     if (const char* e = getenv("RBD_JIT")) jit = e[0] != '0';
     no_tmem = getenv("RBD_NO_TMEM") != nullptr;
@@ -26,6 +27,7 @@ struct Env {
     if (const char* e = getenv("RBD_JIT_MIN_BATCH")) min_batch = atoll(e);
     if (const char* e = getenv("RBD_SMEM_BLOCKS")) smem_blocks = atoi(e);
     if (const char* e = getenv("RBD_JIT_VARIANT")) variant = atoi(e);
+    only = getenv("RBD_ONLY");
   }
 };
 const Env& env() { static const Env e; return e; }
@@ -206,8 +208,8 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
     } else if (variant == 1) {
       e = cudaEventRecord(ctx.fork, stream);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx.side, ctx.fork, 0);
-      if (e == cudaSuccess) { e = cudaLaunchKernel((const void*)se->k_smem, dim3(bps_pair * p.sms), dim3(32), params, smem, stream); ++launched; }
-      if (e == cudaSuccess) { e = cudaLaunchKernel((const void*)se->k_tmem, dim3(p.sms), dim3(32 * tm_warps), params, 0, ctx.side); ++launched; }
+      if (e == cudaSuccess && (!ev.only || ev.only[0] == 's')) { e = cudaLaunchKernel((const void*)se->k_smem, dim3(bps_pair * p.sms), dim3(32), params, smem, stream); ++launched; }
+      if (e == cudaSuccess && (!ev.only || ev.only[0] == 't')) { e = cudaLaunchKernel((const void*)se->k_tmem, dim3(p.sms), dim3(32 * tm_warps), params, 0, ctx.side); ++launched; }
       if (e == cudaSuccess) e = cudaEventRecord(ctx.join, ctx.side);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, ctx.join, 0);
       li.grid = bps_pair * p.sms; li.block = 32; li.blocks_per_sm = bps_pair; li.smem_bytes = (int)smem;

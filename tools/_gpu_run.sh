@@ -1,2 +1,5 @@
-set -x
-python -m pytest tests -m gpu -x -q 2>&1 | grep -v "^E    " | tail -12
+python tools/jit_check.py atlas dynamics f32 20
+python tools/jit_check.py atlas id f32 20
+python tools/jit_check.py iiwa14 dynamics f32 20
+python tools/jit_check.py valkyrie dynamics f32 20
+python tools/jit_sweep.py 10 18 31
