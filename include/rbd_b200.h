@@ -232,6 +232,14 @@ int32_t rbd_mass_matrix_uplo(const rbd_model* model, int32_t dtype, int64_t B, i
 int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,
                       double dt, int32_t nsteps, void* stream);
 
+/* The same with a TIME-VARYING open-loop control -- the batched form of the `control!(torques, t, state)` closure that simulate
+ * evaluates at every stage of every step (src/simulate.jl:36-55, ode_integrators.jl:262-281): the torques of stage i (0..3, at
+ * times t, t + dt/2, t + dt/2, t + dt) of step s are the [nv x B] block at  tau + s * tau_step_stride + i * tau_stage_stride
+ * (strides in ELEMENTS; 0 / 0 = one block held over the whole call = rbd_integrate; stage stride 0 = zero-order hold over each
+ * step).  No host round trip between steps.  State-feedback controllers still call rbd_integrate once per control interval. */
+int32_t rbd_integrate_schedule(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,
+                               int64_t tau_step_stride, int64_t tau_stage_stride, double dt, int32_t nsteps, void* stream);
+
 /* Next row of the scope table: kinematics by-products of the same outward sweep, all expressed in the
  * mechanism's root frame, 6-vectors as [angular; linear].  Every output pointer may be NULL (not computed).
  *   transforms_to_root  [12*nb x B]  rows 12 i .. 12 i + 11 = transform_to_root(state, successor of tree joint i):

@@ -118,11 +118,23 @@ def simulate_(state: MechanismState, final_time: float, torques: Optional[torch.
     a time-varying controller calls this once per control interval.  Returns the number of steps taken."""
     state.check_modcount()
     lib = _cabi.load_library()
-    _check(torques, state.nv, state, "torques")
     nsteps, t = 0, 0.0
     while t < final_time:            # the reference's `while t < final_time` loop (ode_integrators.jl:311)
         t += dt
         nsteps += 1
+    if torques is not None and torques.dim() in (3, 4):
+        # open-loop schedule: [nsteps, nv, B] (zero-order hold over each step) or [nsteps, 4, nv, B] (one block per RK4 stage, the
+        # batched form of control!(torques, t, state) evaluated at t, t + dt/2, t + dt/2, t + dt)
+        if torques.shape[0] < nsteps or torques.shape[-2:] != (state.nv, state.batch) or (torques.dim() == 4 and torques.shape[1] != 4):
+            raise DimensionMismatch("torque schedule must be [nsteps, nv, B] or [nsteps, 4, nv, B]")
+        if torques.dtype != state.dtype or torques.device != state.q.device or not torques.is_contiguous():
+            raise TypeError("torque schedule: dtype / device must match the state, and it must be contiguous")
+        blk = state.nv * state.batch
+        step, stage = (4 * blk, blk) if torques.dim() == 4 else (blk, 0)
+        _call(lib.rbd_integrate_schedule(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(state.v),
+                                         _ptr(torques), step, stage, float(dt), nsteps, _stream()))
+        return nsteps
+    _check(torques, state.nv, state, "torques")
     _call(lib.rbd_integrate(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(state.v),
                             _ptr(torques), float(dt), nsteps, _stream()))
     return nsteps

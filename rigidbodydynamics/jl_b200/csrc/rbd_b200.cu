@@ -812,6 +812,7 @@ template <class T> struct FinishArgs {
   T* q; T* v;                              // user arrays (leading dimension ld)
   T w[4]; T dt;
   int64_t B, ld;
+  bool refresh;                            // also write the new state into (q0, v0) for the next step (each thread owns its joint's rows)
 };
 template <class T>
 __global__ void __launch_bounds__(128) integrate_finish_kernel(const __grid_constant__ ModelDev<T> M, const FinishArgs<T> a) {
@@ -822,15 +823,21 @@ __global__ void __launch_bounds__(128) integrate_finish_kernel(const __grid_cons
     const Col<T> q0{a.q0 + b, a.B};
     const SumRow4<T> phi{nullptr, {a.phid[0] + b, a.phid[1] + b, a.phid[2] + b, a.phid[3] + b}, a.B, {a.w[0], a.w[1], a.w[2], a.w[3]}, a.dt};
     const SumRow4<T> vn{a.v0 + b, {a.vd[0] + b, a.vd[1] + b, a.vd[2] + b, a.vd[3] + b}, a.B, {a.w[0], a.w[1], a.w[2], a.w[3]}, a.dt};
-    for (int k = k0; k < k1; ++k) a.v[(int64_t)k * a.ld + b] = vn(k);
+    T vnew[6];
+    for (int k = k0; k < k1; ++k) { vnew[k - k0] = vn(k); a.v[(int64_t)k * a.ld + b] = vnew[k - k0]; }
     const ColOut<T> q{a.q + b, a.ld, true}, dump{nullptr, a.B, false};
     joint_stage(bd, q0, phi, vn, q, dump);
+    if (a.refresh) {                       // after every read of this joint's (q0, v0) rows above
+      const int nqj = kind_nq_dev(bd.kind);
+      for (int k = 0; k < nqj; ++k) const_cast<T*>(a.q0)[(int64_t)(bd.qrow + k) * a.B + b] = a.q[(int64_t)(bd.qrow + k) * a.ld + b];
+      for (int k = k0; k < k1; ++k) const_cast<T*>(a.v0)[(int64_t)k * a.B + b] = vnew[k - k0];
+    }
   }
 }
 
 template <class T>
-int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v, const void* tau, double dt, int nsteps,
-                cudaStream_t stream) {
+int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v, const void* tau, int64_t step_stride,
+                int64_t stage_stride, double dt, int nsteps, cudaStream_t stream) {
   const HostModel& hm = model->hm;
   const ModelDev<T>& M = dev_model<T>(hm);
   DeviceProps p;
@@ -843,18 +850,30 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
   T* phid[4]; T* vd[4];
   for (int i = 0; i < 4; ++i) { phid[i] = vs + (size_t)(1 + i) * nv * B; vd[i] = vs + (size_t)(5 + i) * nv * B; }
   T* taud = vs + (size_t)9 * nv * B;
+  // torques of (step s, stage i): tau + s * step_stride + i * stage_stride (both 0: one array held over the whole call); the
+  // dynamics kernels want leading dimension B, so arrays with ld != B are densified per use
+  const bool varying = step_stride != 0 || stage_stride != 0;
+  auto tau_at = [&](int s_, int i_) -> const T* { return tau ? (const T*)tau + (size_t)s_ * step_stride + (size_t)i_ * stage_stride : nullptr; };
   const T* tau_dense = (const T*)tau;
-  if (tau && ld != B) {
+  if (tau && ld != B && !varying) {
     CUDA_TRY(cudaMemcpy2DAsync(taud, B * sizeof(T), tau, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
     tau_dense = taud;
   }
   const int grid = (int)std::min<int64_t>((B + 127) / 128, (int64_t)p.sms * 8);
   const double a[4] = {0.0, 0.5, 0.5, 1.0}, bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};   // runge_kutta_4, ode_integrators.jl:48-55
   int rc = RBD_OK, launches = 0;
+  // (q0, v0): dense copies of the state at the start of the step; the finishing kernel of step s refreshes them for step s + 1
+  CUDA_TRY(cudaMemcpy2DAsync(q0, B * sizeof(T), q, ld * sizeof(T), B * sizeof(T), nq, cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaMemcpy2DAsync(v0, B * sizeof(T), v, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
   for (int s = 0; s < nsteps && rc == RBD_OK; ++s) {
-    CUDA_TRY(cudaMemcpy2DAsync(q0, B * sizeof(T), q, ld * sizeof(T), B * sizeof(T), nq, cudaMemcpyDeviceToDevice, stream));
-    CUDA_TRY(cudaMemcpy2DAsync(v0, B * sizeof(T), v, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
     for (int i = 0; i < 4 && rc == RBD_OK; ++i) {
+      if (varying) {
+        tau_dense = tau_at(s, i);
+        if (tau && ld != B) {
+          CUDA_TRY(cudaMemcpy2DAsync(taud, B * sizeof(T), tau_dense, ld * sizeof(T), B * sizeof(T), nv, cudaMemcpyDeviceToDevice, stream));
+          tau_dense = taud;
+        }
+      }
       StageArgs<T> sa{q0, v0, i ? phid[i - 1] : nullptr, i ? vd[i - 1] : nullptr, phid[i], qs, vs, (T)(dt * a[i]), B};
       integrate_stage_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, sa);
       CUDA_TRY(cudaGetLastError());
@@ -864,7 +883,7 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
     }
     if (rc != RBD_OK) break;
     FinishArgs<T> fa{q0, v0, {phid[0], phid[1], phid[2], phid[3]}, {vd[0], vd[1], vd[2], vd[3]}, (T*)q, (T*)v,
-                     {(T)bw[0], (T)bw[1], (T)bw[2], (T)bw[3]}, (T)dt, B, ld};
+                     {(T)bw[0], (T)bw[1], (T)bw[2], (T)bw[3]}, (T)dt, B, ld, s + 1 < nsteps};
     integrate_finish_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, fa);
     CUDA_TRY(cudaGetLastError());
     launches += 1;
@@ -1214,17 +1233,22 @@ int32_t rbd_dynamics_gather(const rbd_model* model, int32_t dtype, int64_t B, in
                           : dynamics_gather_t<double>(model, B, ld, q, v, tau, npeers, vd_peers, vd_multicast, peer_ld, col0, s);
 }
 
-int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,
-                      double dt, int32_t nsteps, void* stream) {
+int32_t rbd_integrate_schedule(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,
+                               int64_t tau_step_stride, int64_t tau_stage_stride, double dt, int32_t nsteps, void* stream) {
   if (int rc = check_common(model, dtype, B, ld)) return rc;
-  if (dtype == RBD_DUAL64X6) return fail(RBD_EUNSUPPORTED, "rbd_integrate: RBD_DUAL64X6 is not supported");
   if (nsteps < 0 || !(dt > 0)) return fail(RBD_EINVAL, "rbd_integrate: need dt > 0 and nsteps >= 0");
+  if (tau_step_stride < 0 || tau_stage_stride < 0) return fail(RBD_EINVAL, "rbd_integrate: torque strides must be >= 0");
   g_launch = {0, 0, 0, 0, 0, 0.f, 0};
   if (B == 0 || nsteps == 0) return RBD_OK;
   if (!q || !v) return fail(RBD_EINVAL, "rbd_integrate: q and v must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  return dtype == RBD_F32 ? integrate_t<float>(model, B, ld, q, v, tau, dt, nsteps, s)
-                          : integrate_t<double>(model, B, ld, q, v, tau, dt, nsteps, s);
+  return dtype == RBD_F32 ? integrate_t<float>(model, B, ld, q, v, tau, tau_step_stride, tau_stage_stride, dt, nsteps, s)
+                          : integrate_t<double>(model, B, ld, q, v, tau, tau_step_stride, tau_stage_stride, dt, nsteps, s);
+}
+
+int32_t rbd_integrate(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, void* q, void* v, const void* tau,
+                      double dt, int32_t nsteps, void* stream) {
+  return rbd_integrate_schedule(model, dtype, B, ld, q, v, tau, 0, 0, dt, nsteps, stream);
 }
 
 int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q,

@@ -354,6 +354,9 @@ template <class T> RBD_HD T comp6(const T* n, const T* f, int c) {
 RBD_HD int kind_nv_dev(int k) {
   return (k == K_REV || k == K_PRIS || k == K_SINCOS) ? 1 : (k == K_FIXED ? 0 : ((k == K_PLANAR || k == K_QSPH) ? 3 : 6));
 }
+RBD_HD int kind_nq_dev(int k) {
+  return (k == K_REV || k == K_PRIS) ? 1 : (k == K_FIXED ? 0 : (k == K_SINCOS ? 2 : (k == K_PLANAR ? 3 : (k == K_QSPH ? 4 : (k == K_QFLOAT ? 7 : 6)))));
+}
 // one-hot component driven by velocity coordinate k of a joint of the given kind
 RBD_HD int sub_comp(int kind, int k) {
   return (kind == K_REV || kind == K_SINCOS) ? 2 : (kind == K_PRIS ? 5 : sub_index(kind == K_PLANAR ? K_PLANAR : K_QFLOAT, k));
