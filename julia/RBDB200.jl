@@ -1,6 +1,7 @@
 # RBDB200.jl -- Julia shim over librbd_b200.so (C ABI in include/rbd_b200.h).
 #
-# NOT EXECUTED in the build image (no Julia there); it is the binding a RigidBodyDynamics.jl maintainer would add.
+# UNTESTED: never executed (the build image has no Julia); it is the binding a RigidBodyDynamics.jl maintainer would add and
+# must be run against the reference's test-suite before use.
 # It keeps the reference's user-facing types: a reference `Mechanism` is flattened ONCE into an `rbd_model_desc`, and batched
 # methods with the reference's names (`dynamics!`, `inverse_dynamics!`, `mass_matrix!`, `dynamics_bias!`) `ccall` the
 # library.  Everything the GPU path does not cover (mechanisms with loops or contact points, scalar types other than
@@ -10,7 +11,9 @@ module RBDB200
 using RigidBodyDynamics
 using RigidBodyDynamics: Mechanism, Joint, JointType, Revolute, Prismatic, Fixed, Planar, QuaternionFloating,
     SPQuatFloating, QuaternionSpherical, SinCosRevolute, tree_joints, non_tree_joints, predecessor, successor,
-    joint_to_predecessor, joint_type, spatial_inertia, root_body, num_positions, num_velocities, modcount
+    joint_to_predecessor, joint_type, spatial_inertia, root_body, num_positions, num_velocities, modcount,
+    frame_after, fixed_transform, rotation, translation, transform, MechanismState, DynamicsResult,
+    set_configuration!, set_velocity!
 using StaticArrays
 using CUDA   # CuArray provides device pointers; any device-pointer provider works
 
@@ -45,14 +48,36 @@ function last_error()
     unsafe_string(ccall((:rbd_last_error, librbd), Cstring, ()))
 end
 
-"Convert an rbd_status into the exception type the reference would have thrown."
+"Thrown for RBD_EUNSUPPORTED / RBD_ELOOP: the batched methods catch it and run the reference's own methods sample by sample."
+struct FallbackToReference <: Exception
+    status::Int32
+    msg::String
+end
+
+"Convert an rbd_status into the exception type the reference would have thrown (INTEGRATION.md, 'Errors')."
 function check(status::Int32)
     status == RBD_OK && return nothing
     msg = last_error()
     status == RBD_EDIM && throw(DimensionMismatch(msg))
     status == RBD_EINVAL && throw(ArgumentError(msg))
     status == RBD_ESTALE && throw(RigidBodyDynamics.ModificationCountMismatch(msg))
+    (status == RBD_EUNSUPPORTED || status == RBD_ELOOP) && throw(FallbackToReference(status, msg))
     error("rbd_b200 (status $status): $msg")
+end
+
+"""
+The documented fallback: evaluate `f!(result, state, b)` with the reference's own `MechanismState` / `DynamicsResult` for every
+sample b of the batch on the host (slow, but it keeps the shim a drop-in for mechanisms / scalar types the GPU path refuses).
+`pull(state, b)` sets the single-sample state from row b; `push(result, b)` stores the result into the batched output.
+"""
+function reference_fallback(f!, mechanism::Mechanism, B::Integer, pull, push)
+    state = MechanismState(mechanism)
+    result = DynamicsResult(mechanism)
+    for b in 1:B
+        pull(state, b)
+        f!(result, state, b)
+        push(result, b)
+    end
 end
 
 # ---- flatten-once model handle ---------------------------------------------------------------------------------
@@ -83,7 +108,14 @@ function Model(mechanism::Mechanism{Float64})
         X[1:9, i] = vec(permutedims(Matrix(R)))           # row-major rotation
         X[10:12, i] = p
         P[:, i] = joint_params(joint_type(j))
-        inertia = spatial_inertia(successor(j, mechanism))   # expressed in the frame after the joint (mechanism.jl:250-260)
+        # The library wants the inertia in frame_after(joint).  That is where spatial_inertia(body) lives after
+        # canonicalize_frame_definitions! / for URDF-parsed mechanisms, but a body attached with a `successor_pose` keeps its own
+        # frame (mechanism_modification.jl:21-46): transform explicitly instead of assuming.
+        body = successor(j, mechanism)
+        inertia = spatial_inertia(body)
+        if inertia.frame != frame_after(j)
+            inertia = transform(inertia, fixed_transform(body, inertia.frame, frame_after(j)))
+        end
         I[1:9, i] = vec(permutedims(Matrix(inertia.moment)))
         I[10:12, i] = inertia.cross_part
         I[13, i] = inertia.mass
@@ -123,16 +155,37 @@ function checkstate(s::BatchedState)
     check(ccall((:rbd_model_check_modcount, librbd), Int32, (Ptr{Cvoid}, Int64), s.model.handle, modcount(s.model.mechanism)))
 end
 
-"`dynamics!(result, state, torques, externalwrenches)` -- src/mechanism_algorithms.jl:845-864, batched."
+"""
+`dynamics!(result, state, torques, externalwrenches)` -- src/mechanism_algorithms.jl:845-864, batched.  `byproducts = true` also
+fills `result.massmatrix` and `result.dynamicsbias` like the reference does (`rbd_dynamics_result`); the Articulated-Body kernel
+does not need them, so they are opt-in.
+"""
 function RigidBodyDynamics.dynamics!(result::BatchedResult{T}, state::BatchedState{T}, torques = nothing,
-                                     externalwrenches = nothing) where {T <: Union{Float32, Float64}}
+                                     externalwrenches = nothing; byproducts::Bool = false) where {T <: Union{Float32, Float64}}
     checkstate(state)
     B = size(state.q, 1)
-    GC.@preserve result state torques externalwrenches begin
-        check(ccall((:rbd_dynamics, librbd), Int32,
-                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
-                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v), devptr(torques),
-                    devptr(externalwrenches), devptr(result.v̇), devptr(result.q̇), stream_ptr()))
+    try
+        GC.@preserve result state torques externalwrenches begin
+            check(ccall((:rbd_dynamics_result, librbd), Int32,
+                        (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                         Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                        state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v), devptr(torques),
+                        devptr(externalwrenches), devptr(result.v̇), devptr(result.q̇),
+                        byproducts ? devptr(result.massmatrix) : C_NULL, byproducts ? devptr(result.dynamicsbias) : C_NULL,
+                        C_NULL, C_NULL, stream_ptr()))
+        end
+    catch e
+        e isa FallbackToReference || rethrow()
+        # mechanisms / dtypes the GPU path refuses: the reference's own dynamics!, one sample at a time, on the host
+        q, v = Array(state.q), Array(state.v)
+        τ = torques === nothing ? nothing : Array(torques)
+        v̇ = similar(v); q̇ = similar(q)
+        reference_fallback(state.model.mechanism, B,
+            (s, b) -> (set_configuration!(s, view(q, b, :)); set_velocity!(s, view(v, b, :))),
+            (r, b) -> (v̇[b, :] .= r.v̇; q̇[b, :] .= r.q̇)) do r, s, b
+            τ === nothing ? RigidBodyDynamics.dynamics!(r, s) : RigidBodyDynamics.dynamics!(r, s, τ[b, :])
+        end
+        copyto!(result.v̇, v̇); copyto!(result.q̇, q̇)
     end
     result
 end
@@ -166,18 +219,39 @@ function RigidBodyDynamics.dynamics_bias!(result::BatchedResult{T}, state::Batch
     result.dynamicsbias
 end
 
-"`mass_matrix!(M, state)` -- src/mechanism_algorithms.jl:248-272, batched: `M` is B x nv^2, entry (i, j) in column i + (j-1) nv."
-function RigidBodyDynamics.mass_matrix!(M::AbstractMatrix{T}, state::BatchedState{T}) where {T <: Union{Float32, Float64}}
+"""
+`mass_matrix!(M, state)` -- src/mechanism_algorithms.jl:248-272, batched: `M` is B x nv^2, entry (i, j) in column i + (j-1) nv.
+`uplo = :L` writes only the lower triangle, which is all the reference's `Symmetric(:L)` storage holds (half the bytes).
+"""
+function RigidBodyDynamics.mass_matrix!(M::AbstractMatrix{T}, state::BatchedState{T}; uplo::Symbol = :full) where {T <: Union{Float32, Float64}}
     checkstate(state)
     B = size(state.q, 1)
     size(M) == (B, state.model.nv^2) || throw(DimensionMismatch("mass matrix has wrong size"))
+    uplo in (:full, :L) || throw(ArgumentError("uplo must be :full or :L"))     # mechanism_algorithms.jl:251
     GC.@preserve M state begin
-        check(ccall((:rbd_mass_matrix, librbd), Int32,
-                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
-                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(M), stream_ptr()))
+        check(ccall((:rbd_mass_matrix_uplo, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(M), Int32(uplo == :L ? 1 : 0), stream_ptr()))
     end
     M
 end
+
+"Per-body outputs of `inverse_dynamics!` (`jointwrenchesout`, `accelerations`), B x 6nb each, root frame (`rbd_inverse_dynamics_bodies`)."
+function inverse_dynamics_bodies!(jointwrenchesout, accelerations, state::BatchedState{T}, v̇, externalwrenches = nothing) where {T <: Union{Float32, Float64}}
+    checkstate(state)
+    B = size(state.q, 1)
+    GC.@preserve jointwrenchesout accelerations state v̇ externalwrenches begin
+        check(ccall((:rbd_inverse_dynamics_bodies, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v), devptr(v̇), devptr(externalwrenches),
+                    devptr(accelerations), devptr(jointwrenchesout), stream_ptr()))
+    end
+    nothing
+end
+
+"Generate + NVRTC-compile the model-specialised kernels ahead of the first large call (`rbd_model_precompile`; `what` = RBD_SPEC_* bits)."
+precompile_kernels(model::Model, ::Type{T} = Float32; what::Integer = 31, load::Bool = true) where {T} =
+    check(ccall((:rbd_model_precompile, librbd), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), model.handle, dtype_code(T), Int32(what), Int32(load)))
 
 
 # ---- SURVEY 8(f) rank 1 / rank 2: the callers and by-products either side of the path -----------------------------------

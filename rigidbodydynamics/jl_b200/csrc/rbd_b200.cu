@@ -846,6 +846,7 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
   const size_t rows = 2 * nq + 10 * nv + (tau && ld != B ? nv : 0);
   T* ws = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&ws, rows * (size_t)B * sizeof(T), stream));
+  struct Guard { void* p; cudaStream_t s; ~Guard() { if (p) cudaFreeAsync(p, s); } } guard{ws, stream};    // freed on every exit path
   T* q0 = ws; T* qs = q0 + nq * B; T* v0 = qs + nq * B; T* vs = v0 + nv * B;
   T* phid[4]; T* vd[4];
   for (int i = 0; i < 4; ++i) { phid[i] = vs + (size_t)(1 + i) * nv * B; vd[i] = vs + (size_t)(5 + i) * nv * B; }
@@ -888,7 +889,6 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   }
-  cudaFreeAsync(ws, stream);
   g_launch.kernels_launched = launches;
   return rc;
 }
@@ -1032,6 +1032,7 @@ int ensure_staging(rbd_model* m, size_t bytes_per_stream) {
     if (!m->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
   if (!m->ev0) { CUDA_TRY(cudaEventCreate(&m->ev0)); CUDA_TRY(cudaEventCreate(&m->ev1)); }
   if (m->stage_bytes >= bytes_per_stream) return RBD_OK;
+  m->stage_bytes = 0;               // a failed reallocation must not leave a stale size behind
   for (int i = 0; i < 3; ++i) {
     if (m->d_stage[i]) { cudaFree(m->d_stage[i]); m->d_stage[i] = nullptr; }
     CUDA_TRY(cudaMalloc(&m->d_stage[i], bytes_per_stream));
@@ -1054,9 +1055,20 @@ struct HostArr { const void* in; void* out; int rows; };
 // Chunked host pipeline: chunk c uses stream c % 3 and that stream's staging buffer; H2D copies, the kernel and the D2H
 // copies of one chunk are stream-ordered, chunks on different streams overlap (copy engines in both directions + SMs).
 template <class Launch>
+int host_pipeline_impl(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const HostArr* ins, int nin, const HostArr* outs,
+                       int nout, Launch launch_chunk);
+template <class Launch>
 int host_pipeline(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const HostArr* ins, int nin, const HostArr* outs,
                   int nout, Launch launch_chunk) {
   std::lock_guard<std::mutex> lk(model->host_mu);
+  const int rc = host_pipeline_impl(model, dtype, B, ld, ins, nin, outs, nout, launch_chunk);
+  if (rc != RBD_OK)                 // never return with copies into the caller's host buffers still in flight
+    for (int i = 0; i < 3; ++i) if (model->streams[i]) cudaStreamSynchronize(model->streams[i]);
+  return rc;
+}
+template <class Launch>
+int host_pipeline_impl(rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const HostArr* ins, int nin, const HostArr* outs,
+                       int nout, Launch launch_chunk) {
   const size_t es = dtype == RBD_F32 ? 4 : 8;
   int64_t chunk = kChunk;
   if (const char* e = getenv("RBD_HOST_CHUNK")) chunk = std::max<int64_t>(1024, atoll(e));     // tuning knob
