@@ -782,12 +782,14 @@ template <class T> struct StageArgs {
   T* phid; T* qs; T* vs;                  // outputs
   T wa;                                   // dt * a_i
   int64_t B;
+  bool skip_linear;                       // revolute / prismatic joints are done by the vectorised kernel below
 };
 template <class T>
 __global__ void __launch_bounds__(128) integrate_stage_kernel(const __grid_constant__ ModelDev<T> M, const StageArgs<T> a) {
   const BodyDev<T>& bd = M.body[blockIdx.y];
   const int k0 = bd.vrow, k1 = bd.vrow + kind_nv_dev(bd.kind);
   if (k1 == k0) return;                                    // fixed joint: no coordinates
+  if (a.skip_linear && (bd.kind == K_REV || bd.kind == K_PRIS)) return;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
     const Col<T> q0{a.q0 + b, a.B};
     const ScaledRow<T> phi{a.phid_prev ? a.phid_prev + b : nullptr, a.B, a.wa};
@@ -795,6 +797,58 @@ __global__ void __launch_bounds__(128) integrate_stage_kernel(const __grid_const
     for (int k = k0; k < k1; ++k) a.vs[(int64_t)k * a.B + b] = vs(k);
     const ColOut<T> qs{a.qs + b, a.B, true}, phid{a.phid + b, a.B, true};
     joint_stage(bd, q0, phi, vs, qs, phid);
+  }
+}
+// Revolute / prismatic joints (the bulk of a robot): q_s = q0 + wa phid_prev, v_s = v0 + wa vd_prev, phid = v_s -- plain row
+// arithmetic, done VEC samples per thread with 16-byte accesses so that enough loads are in flight to approach the HBM rate (the
+// per-(sample, joint) kernel above sits at 15 % of it, long_scoreboard 13 warps per issue: profiles/r2_gen_rk4_stage_summary.txt).
+template <class T> struct VecOf { using type = float4; static constexpr int N = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+template <class T> __device__ __forceinline__ void vec_axpy(const typename VecOf<T>::type& a, T w, const typename VecOf<T>::type& x,
+                                                            typename VecOf<T>::type& o);
+template <> __device__ __forceinline__ void vec_axpy<float>(const float4& a, float w, const float4& x, float4& o) {
+  o.x = a.x + w * x.x; o.y = a.y + w * x.y; o.z = a.z + w * x.z; o.w = a.w + w * x.w;
+}
+template <> __device__ __forceinline__ void vec_axpy<double>(const double2& a, double w, const double2& x, double2& o) {
+  o.x = a.x + w * x.x; o.y = a.y + w * x.y;
+}
+template <class T> __device__ __forceinline__ typename VecOf<T>::type vec_comb4(const typename VecOf<T>::type& base, T dt, const T* w,
+                                                                                const typename VecOf<T>::type* x);
+template <> __device__ __forceinline__ float4 vec_comb4<float>(const float4& b, float dt, const float* w, const float4* x) {
+  float4 o;
+  o.x = b.x + dt * (w[0] * x[0].x + w[1] * x[1].x + w[2] * x[2].x + w[3] * x[3].x);
+  o.y = b.y + dt * (w[0] * x[0].y + w[1] * x[1].y + w[2] * x[2].y + w[3] * x[3].y);
+  o.z = b.z + dt * (w[0] * x[0].z + w[1] * x[1].z + w[2] * x[2].z + w[3] * x[3].z);
+  o.w = b.w + dt * (w[0] * x[0].w + w[1] * x[1].w + w[2] * x[2].w + w[3] * x[3].w);
+  return o;
+}
+template <> __device__ __forceinline__ double2 vec_comb4<double>(const double2& b, double dt, const double* w, const double2* x) {
+  double2 o;
+  o.x = b.x + dt * (w[0] * x[0].x + w[1] * x[1].x + w[2] * x[2].x + w[3] * x[3].x);
+  o.y = b.y + dt * (w[0] * x[0].y + w[1] * x[1].y + w[2] * x[2].y + w[3] * x[3].y);
+  return o;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) integrate_stage_linear_kernel(const __grid_constant__ ModelDev<T> M, const StageArgs<T> a) {
+  using V = typename VecOf<T>::type;
+  constexpr int N = VecOf<T>::N;
+  const BodyDev<T>& bd = M.body[blockIdx.y];
+  if (bd.kind != K_REV && bd.kind != K_PRIS) return;
+  const int64_t qo = (int64_t)bd.qrow * a.B, vo = (int64_t)bd.vrow * a.B, nvec = a.B / N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const V q0 = reinterpret_cast<const V*>(a.q0 + qo)[i];
+    const V v0 = reinterpret_cast<const V*>(a.v0 + vo)[i];
+    V qs = q0, vs = v0;
+    if (a.phid_prev) {
+      const V pp = reinterpret_cast<const V*>(a.phid_prev + vo)[i];
+      const V vp = reinterpret_cast<const V*>(a.vd_prev + vo)[i];
+      vec_axpy<T>(q0, a.wa, pp, qs);
+      vec_axpy<T>(v0, a.wa, vp, vs);
+    }
+    reinterpret_cast<V*>(a.qs + qo)[i] = qs;
+    reinterpret_cast<V*>(a.vs + vo)[i] = vs;
+    reinterpret_cast<V*>(a.phid + vo)[i] = vs;
   }
 }
 // v = v0 + dt sum_i b_i vd_i ,  q = global(q0, dt sum_i b_i phid_i)        (ode_integrators.jl:283-296)
@@ -813,12 +867,37 @@ template <class T> struct FinishArgs {
   T w[4]; T dt;
   int64_t B, ld;
   bool refresh;                            // also write the new state into (q0, v0) for the next step (each thread owns its joint's rows)
+  bool skip_linear;                        // revolute / prismatic joints are done by integrate_finish_linear_kernel
 };
+// finishing step of the revolute / prismatic rows, vectorised like integrate_stage_linear_kernel
+template <class T>
+__global__ void __launch_bounds__(256) integrate_finish_linear_kernel(const __grid_constant__ ModelDev<T> M, const FinishArgs<T> a) {
+  using V = typename VecOf<T>::type;
+  constexpr int N = VecOf<T>::N;
+  const BodyDev<T>& bd = M.body[blockIdx.y];
+  if (bd.kind != K_REV && bd.kind != K_PRIS) return;
+  const int64_t qo = (int64_t)bd.qrow * a.B, vo = (int64_t)bd.vrow * a.B, nvec = a.B / N;
+  V* qu = reinterpret_cast<V*>(a.q + (int64_t)bd.qrow * a.ld);
+  V* vu = reinterpret_cast<V*>(a.v + (int64_t)bd.vrow * a.ld);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    V ph[4], vd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ph[k] = reinterpret_cast<const V*>(a.phid[k] + vo)[i]; vd[k] = reinterpret_cast<const V*>(a.vd[k] + vo)[i]; }
+    const V qn = vec_comb4<T>(reinterpret_cast<const V*>(a.q0 + qo)[i], a.dt, a.w, ph);
+    const V vn = vec_comb4<T>(reinterpret_cast<const V*>(a.v0 + vo)[i], a.dt, a.w, vd);
+    qu[i] = qn; vu[i] = vn;
+    if (a.refresh) {
+      reinterpret_cast<V*>(const_cast<T*>(a.q0) + qo)[i] = qn;
+      reinterpret_cast<V*>(const_cast<T*>(a.v0) + vo)[i] = vn;
+    }
+  }
+}
 template <class T>
 __global__ void __launch_bounds__(128) integrate_finish_kernel(const __grid_constant__ ModelDev<T> M, const FinishArgs<T> a) {
   const BodyDev<T>& bd = M.body[blockIdx.y];
   const int k0 = bd.vrow, k1 = bd.vrow + kind_nv_dev(bd.kind);
   if (k1 == k0) return;
+  if (a.skip_linear && (bd.kind == K_REV || bd.kind == K_PRIS)) return;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * blockDim.x) {
     const Col<T> q0{a.q0 + b, a.B};
     const SumRow4<T> phi{nullptr, {a.phid[0] + b, a.phid[1] + b, a.phid[2] + b, a.phid[3] + b}, a.B, {a.w[0], a.w[1], a.w[2], a.w[3]}, a.dt};
@@ -861,6 +940,14 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
     tau_dense = taud;
   }
   const int grid = (int)std::min<int64_t>((B + 127) / 128, (int64_t)p.sms * 8);
+  // the vectorised kernel needs whole vectors per row (workspace rows are B long and 256-byte aligned)
+  const bool vec_ok = B % VecOf<T>::N == 0 && B >= 1024;
+  const int grid_lin = (int)std::min<int64_t>((B / VecOf<T>::N + 255) / 256, (int64_t)p.sms * 4);
+  // ... and, for the finishing kernel, vector-aligned rows of the caller's arrays too
+  const bool vec_user = vec_ok && ld % VecOf<T>::N == 0 && ((uintptr_t)q % sizeof(typename VecOf<T>::type)) == 0 &&
+                        ((uintptr_t)v % sizeof(typename VecOf<T>::type)) == 0;
+  bool has_other = false;
+  for (int i = 0; i < hm.nb; ++i) has_other |= (M.body[i].kind != K_REV && M.body[i].kind != K_PRIS && M.body[i].kind != K_FIXED);
   const double a[4] = {0.0, 0.5, 0.5, 1.0}, bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};   // runge_kutta_4, ode_integrators.jl:48-55
   int rc = RBD_OK, launches = 0;
   // (q0, v0): dense copies of the state at the start of the step; the finishing kernel of step s refreshes them for step s + 1
@@ -875,19 +962,34 @@ int integrate_t(const rbd_model* model, int64_t B, int64_t ld, void* q, void* v,
           tau_dense = taud;
         }
       }
-      StageArgs<T> sa{q0, v0, i ? phid[i - 1] : nullptr, i ? vd[i - 1] : nullptr, phid[i], qs, vs, (T)(dt * a[i]), B};
-      integrate_stage_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, sa);
-      CUDA_TRY(cudaGetLastError());
+      StageArgs<T> sa{q0, v0, i ? phid[i - 1] : nullptr, i ? vd[i - 1] : nullptr, phid[i], qs, vs, (T)(dt * a[i]), B, vec_ok};
+      if (vec_ok) {        // revolute / prismatic rows, VEC samples per thread
+        integrate_stage_linear_kernel<T><<<dim3(grid_lin, hm.nb), 256, 0, stream>>>(M, sa);
+        CUDA_TRY(cudaGetLastError());
+        launches += 1;
+      }
+      if (!vec_ok || has_other) {
+        integrate_stage_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, sa);
+        CUDA_TRY(cudaGetLastError());
+        launches += 1;
+      }
       const int before = g_launch.kernels_launched;
       rc = dynamics_t<T>(model, B, B, qs, vs, tau_dense, nullptr, vd[i], nullptr, stream);
-      launches += 1 + (g_launch.kernels_launched - before);
+      launches += g_launch.kernels_launched - before;
     }
     if (rc != RBD_OK) break;
     FinishArgs<T> fa{q0, v0, {phid[0], phid[1], phid[2], phid[3]}, {vd[0], vd[1], vd[2], vd[3]}, (T*)q, (T*)v,
-                     {(T)bw[0], (T)bw[1], (T)bw[2], (T)bw[3]}, (T)dt, B, ld, s + 1 < nsteps};
-    integrate_finish_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, fa);
-    CUDA_TRY(cudaGetLastError());
-    launches += 1;
+                     {(T)bw[0], (T)bw[1], (T)bw[2], (T)bw[3]}, (T)dt, B, ld, s + 1 < nsteps, vec_user};
+    if (vec_user) {
+      integrate_finish_linear_kernel<T><<<dim3(grid_lin, hm.nb), 256, 0, stream>>>(M, fa);
+      CUDA_TRY(cudaGetLastError());
+      launches += 1;
+    }
+    if (!vec_user || has_other) {
+      integrate_finish_kernel<T><<<dim3(grid, hm.nb), 128, 0, stream>>>(M, fa);
+      CUDA_TRY(cudaGetLastError());
+      launches += 1;
+    }
   }
   g_launch.kernels_launched = launches;
   return rc;
