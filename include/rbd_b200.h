@@ -193,6 +193,33 @@ int32_t rbd_inverse_dynamics(const rbd_model* model, int32_t dtype, int64_t B, i
 int32_t rbd_inverse_dynamics_bodies(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                                     const void* vd, const void* wext, void* accelerations_out, void* jointwrenches_out, void* stream);
 
+/* Next row of the scope table: soft point contact with half-spaces -- the batched contact_dynamics!
+ *                                                             src/mechanism_algorithms.jl:680-723, src/contact.jl
+ * with the reference's default SoftContactModel{HuntCrossleyModel, ViscoelasticCoulombModel} (contact.jl:104-118, :130-206; HalfSpace3D :219-239):
+ *   normal force  f_n = max(lambda z^n zdot + k z^n, 0),   z = penetration, zdot = penetration velocity
+ *   friction      f_stick = -k x - b v_t clipped to mu f_n;  xdot = (-k x - f_t) / b   (x: tangential displacement, the
+ *                 3 "additional state" entries the reference keeps per (contact point, half-space) pair)
+ * The descriptor is read on the host at call time (plain host arrays). */
+typedef struct rbd_contact_desc {
+  int32_t npoints;              /* <= 32 */
+  const int32_t* body;          /* [npoints] tree-joint index whose successor carries the point (contact_points(body))      */
+  const double* location;       /* [npoints][3] point in the frame after that joint (the frame of rbd_model_desc.inertia)    */
+  const double* normal_model;   /* [npoints][3] HuntCrossleyModel k, lambda, n       (hunt_crossley_hertz: 50e3, 15e3, 1.5) */
+  const double* friction_model; /* [npoints][3] ViscoelasticCoulombModel mu, k, b                                           */
+  int32_t nhalfspaces;          /* <= 4 */
+  const double* halfspace;      /* [nhalfspaces][6] HalfSpace3D: point (3), outward normal (3, normalised here), root frame */
+} rbd_contact_desc;
+
+/*   state           [3*npoints*nhalfspaces x B] or NULL (= all zero): tangential displacement of pair (p, h) at rows
+ *                   3*(p*nhalfspaces + h) .. +2.  IN/OUT: pairs that are not in contact are reset to zero, as the reference does
+ *                   inside contact_dynamics! (Contact.reset!).
+ *   state_deriv_out same shape or NULL: xdot (zero for pairs not in contact) -- result.contact_state_derivatives
+ *   wrenches_out    [6*nb x B]: rows 6 i .. 6 i + 5 = total contact wrench [torque; force] on the successor of tree joint i in the
+ *                   ROOT frame -- result.contactwrenches; add the caller's externalwrenches and pass the sum as `wext` to
+ *                   rbd_dynamics, which is exactly what dynamics! does (mechanism_algorithms.jl:850-856). */
+int32_t rbd_contact_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                             const rbd_contact_desc* contact, void* state, void* state_deriv_out, void* wrenches_out, void* stream);
+
 /* dynamics!(result, ...) INCLUDING the by-products the reference leaves in the DynamicsResult (src/dynamics_result.jl:11-85,
  * mechanism_algorithms.jl:849-863): besides v̇ / q̇, any of  result.massmatrix (M_out [nv*nv x B], see rbd_mass_matrix),
  * result.dynamicsbias (c_out [nv x B]), result.accelerations and result.jointwrenches (see rbd_inverse_dynamics_bodies, evaluated

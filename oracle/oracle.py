@@ -34,6 +34,7 @@ def _load():
     lib.rbdo_integrate.argtypes = [vp, i64, vp, vp, vp, ctypes.c_double, i32, i32]
     lib.rbdo_inverse_dynamics.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32]
     lib.rbdo_inverse_dynamics_bodies.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
+    lib.rbdo_contact_dynamics.argtypes = [vp, i32, i64, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.rbdo_mass_matrix.argtypes = [vp, i32, i64, vp, vp, i32]
     lib.rbdo_kinematics.argtypes = [vp, i32, i64] + [vp] * 11 + [i32]
     return lib
@@ -137,6 +138,23 @@ class Oracle:
         acc = np.empty((6 * self.nb, B), dt); jw = np.empty((6 * self.nb, B), dt)
         _lib.rbdo_inverse_dynamics_bodies(self._h, self._code(dt), B, _ptr(q), _ptr(v), _ptr(vd), _ptr(wext), _ptr(acc), _ptr(jw))
         return acc, jw
+
+    def contact_dynamics(self, q, v, contact, s=None, *, dtype=None):
+        """contact_dynamics! (mechanism_algorithms.jl:680-723) for a ``ContactDesc``-like object (body, location, normal_model,
+        friction_model, halfspace).  Returns (contactwrenches [6*nb, B], state_derivatives [ns, B], state after the resets [ns, B])."""
+        dt = np.dtype(dtype or np.asarray(q).dtype)
+        q = self._prep(q, self.nq, dt); v = self._prep(v, self.nv, dt)
+        B = q.shape[1]
+        body = np.ascontiguousarray(contact.body, np.int32)
+        loc = np.ascontiguousarray(contact.location, np.float64); hc = np.ascontiguousarray(contact.normal_model, np.float64)
+        fr = np.ascontiguousarray(contact.friction_model, np.float64); hs = np.ascontiguousarray(contact.halfspace, np.float64)
+        npnt, nh = len(body), len(hs)
+        ns = 3 * npnt * nh
+        s = np.zeros((ns, B), dt) if s is None else np.array(self._prep(s, ns, dt), copy=True)
+        sd = np.zeros((ns, B), dt); wr = np.empty((6 * self.nb, B), dt)
+        _lib.rbdo_contact_dynamics(self._h, self._code(dt), B, _ptr(q), _ptr(v), npnt, _ptr(body), _ptr(loc), _ptr(hc), _ptr(fr), nh,
+                                   _ptr(hs), _ptr(s), _ptr(sd), _ptr(wr))
+        return wr, sd, s
 
     def dynamics_bias(self, q, v, wext=None, *, nthreads=1, dtype=None):
         return self.inverse_dynamics(q, v, None, wext, nthreads=nthreads, dtype=dtype)

@@ -124,6 +124,63 @@ int inverse_dynamics_bodies_t(const Model& m, int64_t B, const T* q, const T* v,
   return 0;
 }
 
+// contact_dynamics!(result, state)                                       mechanism_algorithms.jl:680-723
+// with SoftContactModel{HuntCrossleyModel, ViscoelasticCoulombModel}    contact.jl:104-118, :130-146, :152-206
+// and HalfSpace3D environment primitives                                 contact.jl:219-239
+//   body[p]: tree joint whose successor carries point p;  loc [np][3] in that body's frame;  hc [np][3] = k, lambda, n;
+//   fr [np][3] = mu, k, b;  hs [nh][6] = point, outward normal;  state s / derivative sd [3*np*nh x B] (pair (p, h) at rows
+//   3 (p nh + h) ..), s is reset where the pair is not in contact (:716 reset!);  wr [6 nb x B] = result.contactwrenches.
+template <class T>
+int contact_dynamics_t(const Model& m, int64_t B, const T* q, const T* v, int np, const int* body, const double* loc,
+                       const double* hc, const double* fr, int nh, const double* hs, T* s, T* sd, T* wr) {
+  Workspace<T> w(m);
+  std::vector<T> ql(m.nq), vl(m.nv);
+  std::vector<S6<T>> cw(m.nb);
+  for (int64_t b = 0; b < B; ++b) {
+    for (int k = 0; k < m.nq; ++k) ql[k] = q[(size_t)k * B + b];
+    for (int k = 0; k < m.nv; ++k) vl[k] = v[(size_t)k * B + b];
+    update_transforms(w, ql.data());
+    update_twists(w, vl.data());
+    for (int i = 0; i < m.nb; ++i) cw[i] = S6<T>();                                        // :688 zero(Wrench)
+    for (int p = 0; p < np; ++p) {
+      const int i = body[p];
+      const S6<T>& tw = w.twist[i];                                                      // :693 twist_wrt_world
+      const V3<T> lp(T(loc[3 * p]), T(loc[3 * p + 1]), T(loc[3 * p + 2]));
+      const V3<T> pt = w.T_root[i].R * lp + w.T_root[i].p;                                // :698 body_to_root * location
+      const V3<T> vel = cross(tw.ang, pt) + tw.lin;                                       // :699 point_velocity
+      for (int h = 0; h < nh; ++h) {
+        const V3<T> hp(T(hs[6 * h]), T(hs[6 * h + 1]), T(hs[6 * h + 2]));
+        V3<T> n(T(hs[6 * h + 3]), T(hs[6 * h + 4]), T(hs[6 * h + 5]));
+        n = n * (T(1) / T(std::sqrt(dot(n, n))));                                          // contact.jl:225 normalize
+        const size_t row = (size_t)3 * (p * nh + h);
+        const T sep = dot(pt - hp, n);                                                    // contact.jl:237 separation
+        V3<T> xd;
+        if (sep <= T(0)) {                                                                // :710, contact.jl:238 point_inside
+          const T z = -sep, zd = -dot(vel, n);                                            // contact.jl:108-109
+          const T zn = T(std::pow(z, T(hc[3 * p + 2])));
+          T fn = T(hc[3 * p + 1]) * zn * zd + T(hc[3 * p]) * zn;                          // contact.jl:143-146
+          if (fn < T(0)) fn = T(0);                                                       // contact.jl:110 max(., 0)
+          const V3<T> vt = vel + zd * n;                                                  // contact.jl:113 tangential velocity
+          const T mu = T(fr[3 * p]), kf = T(fr[3 * p + 1]), bf = T(fr[3 * p + 2]);
+          const V3<T> x = s ? V3<T>(s[(row + 0) * B + b], s[(row + 1) * B + b], s[(row + 2) * B + b]) : V3<T>();
+          V3<T> ft = -(kf * x) - bf * vt;                                                 // contact.jl:188 fstick
+          const T n2 = dot(ft, ft), m2 = (mu * fn) * (mu * fn);
+          if (n2 > m2) ft = ft * T(std::sqrt(m2 / n2));                                   // contact.jl:191-197 Coulomb cone
+          xd = (-(kf * x) - ft) * (T(1) / bf);                                            // contact.jl:205 state derivative
+          const V3<T> f = fn * n + ft;                                                    // contact.jl:117
+          cw[i] = cw[i] + S6<T>{cross(pt, f), f};                                         // :714 Wrench(point, force)
+        } else if (s) {
+          for (int k = 0; k < 3; ++k) s[(row + k) * B + b] = T(0);                        // :716 reset!
+        }
+        if (sd) { sd[(row + 0) * B + b] = xd.x; sd[(row + 1) * B + b] = xd.y; sd[(row + 2) * B + b] = xd.z; }   // :717 zero!
+      }
+    }
+    for (int i = 0; i < m.nb; ++i)
+      for (int k = 0; k < 3; ++k) { wr[(size_t)(6 * i + k) * B + b] = cw[i].ang[k]; wr[(size_t)(6 * i + 3 + k) * B + b] = cw[i].lin[k]; }
+  }
+  return 0;
+}
+
 template <class T> int mass_matrix_t(const Model& m, int64_t B, const T* q, T* M, int nthreads) {
   parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
     Workspace<T> w(m);
@@ -272,6 +329,12 @@ int rbdo_inverse_dynamics_bodies(void* mp, int dtype, int64_t B, const void* q, 
   const Model& m = *static_cast<Model*>(mp);
   if (dtype == 0) return inverse_dynamics_bodies_t<float>(m, B, (const float*)q, (const float*)v, (const float*)vd, (const float*)wext, (float*)acc, (float*)jw);
   return inverse_dynamics_bodies_t<double>(m, B, (const double*)q, (const double*)v, (const double*)vd, (const double*)wext, (double*)acc, (double*)jw);
+}
+int rbdo_contact_dynamics(void* mp, int dtype, int64_t B, const void* q, const void* v, int np, const int* body, const double* loc,
+                          const double* hc, const double* fr, int nh, const double* hs, void* s, void* sd, void* wr) {
+  const Model& m = *static_cast<Model*>(mp);
+  if (dtype == 0) return contact_dynamics_t<float>(m, B, (const float*)q, (const float*)v, np, body, loc, hc, fr, nh, hs, (float*)s, (float*)sd, (float*)wr);
+  return contact_dynamics_t<double>(m, B, (const double*)q, (const double*)v, np, body, loc, hc, fr, nh, hs, (double*)s, (double*)sd, (double*)wr);
 }
 int rbdo_mass_matrix(void* mp, int dtype, int64_t B, const void* q, void* M, int nthreads) {
   const Model& m = *static_cast<Model*>(mp);

@@ -453,6 +453,34 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 16 : 8) bodies_kernel(con
   }
 }
 
+// Soft contact (contact_sample, rbd_kin.cuh): one thread per sample, stash = pending poses + twists.
+template <class T> struct ContactArgs {
+  const T *q, *v;
+  T *s, *sd, *wr;
+  int64_t ld, B;
+};
+template <class T, int NT>
+__global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 16 : 8)
+contact_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ ContactDev<T> C, const ContactArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Stash<T, NT> st{reinterpret_cast<T*>(smem_raw) + threadIdx.x};
+  const int64_t ngroups = (a.B + NT - 1) / NT;
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t b = g * NT + threadIdx.x;
+    const bool active = b < a.B;
+    const int64_t bl = active ? b : a.B - 1;
+    ContactIO<T> io;
+    io.q = {a.q + bl, a.ld};
+    io.v = {a.v + bl, a.ld};
+    io.s = a.s ? a.s + bl : nullptr;
+    io.sd = a.sd ? a.sd + bl : nullptr;
+    io.wr = a.wr + bl;
+    io.ld = a.ld;
+    io.active = active;
+    contact_sample<T>(M, C, io, st);
+  }
+}
+
 template <class K> int configure(K kernel, int nt, size_t smem, const DeviceProps& p, int& blocks_per_sm) {
   if ((int)smem > p.max_smem_optin) return fail(RBD_EUNSUPPORTED, "model working set exceeds shared memory per block");
   if (int rc = configure_once((const void*)kernel, p)) return rc;
@@ -1089,6 +1117,29 @@ int bodies_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, const
   return RBD_OK;
 }
 
+template <class T>
+int contact_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, const void* v, const rbd_contact_desc& cd, void* sx,
+              void* sd, void* wr, cudaStream_t stream) {
+  const HostModel& hm = model->hm;
+  const ModelDev<T>& M = dev_model<T>(hm);
+  ContactDev<T> C;
+  build_contact_dev<T>(hm.nb, hm.pos.data(), hm.alignT.data(), cd, C);
+  ContactArgs<T> a{(const T*)q, (const T*)v, (T*)sx, (T*)sd, (T*)wr, ld, B};
+  DeviceProps p;
+  if (int rc = get_props(p)) return rc;
+  auto kernel = contact_kernel<T, kNT>;
+  const size_t smem = (size_t)std::max(1, kin_rows(hm)) * kNT * sizeof(T);
+  int bps = 0;
+  if (int rc = configure(kernel, kNT, smem, p, bps)) return rc;
+  const int64_t ngroups = (B + kNT - 1) / kNT;
+  const int grid = (int)std::min<int64_t>(ngroups, (int64_t)bps * p.sms);
+  kernel<<<grid, kNT, smem, stream>>>(M, C, a);
+  if (cudaGetLastError() != cudaSuccess) return fail(RBD_ECUDA, "contact_kernel launch failed");
+  g_launch.kernels_launched += 1;
+  g_launch.grid = grid; g_launch.block = kNT; g_launch.smem_bytes = (int)smem; g_launch.blocks_per_sm = bps;
+  return RBD_OK;
+}
+
 int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, bool allow_dual = false) {
   if (!model) return fail(RBD_EINVAL, "model handle is NULL");
   if (dtype != RBD_F32 && dtype != RBD_F64 && dtype != RBD_DUAL64X6)
@@ -1385,6 +1436,32 @@ int32_t rbd_inverse_dynamics_bodies(const rbd_model* model, int32_t dtype, int64
   cudaStream_t s = (cudaStream_t)stream;
   return dtype == RBD_F32 ? bodies_t<float>(model, B, ld, q, v, vd, wext, accelerations_out, jointwrenches_out, s)
                           : bodies_t<double>(model, B, ld, q, v, vd, wext, accelerations_out, jointwrenches_out, s);
+}
+
+int32_t rbd_contact_dynamics(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                             const rbd_contact_desc* contact, void* state, void* state_deriv_out, void* wrenches_out, void* stream) {
+  if (int rc = check_common(model, dtype, B, ld)) return rc;
+  g_launch = {0, 0, 0, 0, 0, 0.f, 0};
+  if (!contact) return fail(RBD_EINVAL, "rbd_contact_dynamics: contact must not be NULL");
+  if (contact->npoints < 0 || contact->nhalfspaces < 0) return fail(RBD_EINVAL, "rbd_contact_dynamics: negative counts");
+  if (contact->npoints > kMaxContactPoints || contact->nhalfspaces > kMaxHalfSpaces)
+    return fail(RBD_EUNSUPPORTED, "rbd_contact_dynamics: at most 32 contact points and 4 half-spaces");
+  if (contact->npoints && (!contact->body || !contact->location || !contact->normal_model || !contact->friction_model))
+    return fail(RBD_EINVAL, "rbd_contact_dynamics: point arrays must not be NULL");
+  if (contact->nhalfspaces && !contact->halfspace) return fail(RBD_EINVAL, "rbd_contact_dynamics: halfspace must not be NULL");
+  for (int p = 0; p < contact->npoints; ++p) {
+    if (contact->body[p] < 0 || contact->body[p] >= model->hm.nb) return fail(RBD_EINVAL, "rbd_contact_dynamics: body index out of range");
+    if (!(contact->friction_model[3 * p + 2] > 0)) return fail(RBD_EINVAL, "rbd_contact_dynamics: friction damping b must be > 0");
+  }
+  for (int h = 0; h < contact->nhalfspaces; ++h) {
+    const double* n = contact->halfspace + 6 * h + 3;
+    if (!(n[0] * n[0] + n[1] * n[1] + n[2] * n[2] > 0)) return fail(RBD_EINVAL, "rbd_contact_dynamics: zero half-space normal");
+  }
+  if (B == 0) return RBD_OK;
+  if (!q || !v || !wrenches_out) return fail(RBD_EINVAL, "rbd_contact_dynamics: q, v and wrenches_out must not be NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == RBD_F32 ? contact_t<float>(model, B, ld, q, v, *contact, state, state_deriv_out, wrenches_out, s)
+                          : contact_t<double>(model, B, ld, q, v, *contact, state, state_deriv_out, wrenches_out, s);
 }
 
 int32_t rbd_dynamics_result(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,

@@ -11,6 +11,10 @@
 // which does not depend on that choice, except transform_to_root itself, which is mapped back to the caller's body frames
 // with the per-body alignment rotation kept in KinDev.
 #pragma once
+#include <cmath>
+#include <cstring>
+
+#include "../../../include/rbd_b200.h"
 #include "rbd_rnea_crba.cuh"
 
 namespace rbd {
@@ -409,6 +413,195 @@ RBD_HD void bodies_sample(const ModelDev<T>& M, const BodiesIO<T>& io, const ST&
     const int64_t crow = (int64_t)6 * bd.refidx, prow = (int64_t)6 * M.body[bd.parent].refidx;
 #pragma unroll
     for (int k = 0; k < 6; ++k) io.jw[(prow + k) * io.ld] += io.jw[(crow + k) * io.ld];
+  }
+}
+
+// ==================================================================================================================
+// Soft point contact with half-spaces: the batched contact_dynamics!   mechanism_algorithms.jl:680-723
+// with the reference's default models (src/contact.jl):
+//   normal force   HuntCrossleyModel          f_n = max(lambda z^n zdot + k z^n, 0)                  contact.jl:130-146
+//   friction       ViscoelasticCoulombModel   f_stick = -k x - b v_t, clipped to the cone mu f_n;    :152-206
+//                                             state x = tangential displacement, xdot = (-k x - f_t) / b
+// One thread per sample; outward sweep with root-frame pose and twist per body (as bodies_sample); for every contact point
+// p of the body and every half-space h:  point = T_body p,  velocity = omega x point + v_lin  (point_velocity),
+// separation = (point - h.point) . h.normal;  inside (<= 0): force as above, wrench += (point x force, force), xdot written;
+// outside: the state is RESET to zero and its derivative zeroed, exactly like the reference does inside contact_dynamics!.
+// ==================================================================================================================
+constexpr int kMaxContactPoints = 32, kMaxHalfSpaces = 4;
+template <class T> struct ContactDev {
+  int32_t npoints, nhalf;
+  int32_t first[kMaxBodies + 1];        // preorder body i owns points first[i] .. first[i + 1] - 1 (sorted by body)
+  int32_t orig[kMaxContactPoints];      // sorted position -> caller's point index (rows of the state arrays)
+  T loc[kMaxContactPoints][3];          // location in the CANONICAL body frame
+  T hc[kMaxContactPoints][3];           // Hunt-Crossley k, lambda, n
+  T fr[kMaxContactPoints][3];           // viscoelastic Coulomb mu, k, b
+  T hp[kMaxHalfSpaces][3], hn[kMaxHalfSpaces][3];   // half-space point and unit outward normal, root frame
+};
+template <class T> struct ContactIO {
+  Col<T> q, v;
+  T* s;            // [3 * npoints * nhalf] rows of this sample's column: tangential displacements (in / out: reset when outside)
+  T* sd;           // same shape, derivative out; may be NULL
+  T* wr;           // [6 nb] contact wrench per body (root frame, rows 6 * refidx + c)
+  int64_t ld;
+  bool active;
+};
+RBD_HD float contact_pow(float z, float n) {
+#if defined(__CUDA_ARCH__)
+  return n == 1.5f ? z * sqrtf(z) : powf(z, n);
+#else
+  return n == 1.5f ? z * std::sqrt(z) : std::pow(z, n);
+#endif
+}
+RBD_HD double contact_pow(double z, double n) {
+#if defined(__CUDA_ARCH__)
+  return n == 1.5 ? z * sqrt(z) : pow(z, n);
+#else
+  return n == 1.5 ? z * std::sqrt(z) : std::pow(z, n);
+#endif
+}
+RBD_HD float contact_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  return sqrtf(x);
+#else
+  return std::sqrt(x);
+#endif
+}
+RBD_HD double contact_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return sqrt(x);
+#else
+  return std::sqrt(x);
+#endif
+}
+
+// Host side: rbd_contact_desc -> ContactDev (points sorted by the preorder position of their body, stable; locations rotated into
+// the canonical body frame; normals normalised like the HalfSpace3D constructor, contact.jl:225).  pos: reference joint index ->
+// preorder position, alignT: preorder position -> A^T (HostModel).
+template <class T>
+inline void build_contact_dev(int nb, const int* pos, const double* alignT, const rbd_contact_desc& cd, ContactDev<T>& C) {
+  std::memset(&C, 0, sizeof(C));
+  C.npoints = cd.npoints; C.nhalf = cd.nhalfspaces;
+  int cnt[kMaxBodies + 1] = {0};
+  for (int p = 0; p < cd.npoints; ++p) cnt[pos[cd.body[p]] + 1] += 1;
+  for (int i = 0; i < nb; ++i) cnt[i + 1] += cnt[i];
+  for (int i = 0; i <= kMaxBodies; ++i) C.first[i] = cnt[i < nb ? i : nb];
+  int fill[kMaxBodies] = {0};
+  for (int p = 0; p < cd.npoints; ++p) {
+    const int i = pos[cd.body[p]];
+    const int k = C.first[i] + fill[i]++;
+    C.orig[k] = p;
+    const double* At = alignT + 9 * i;
+    const double* l = cd.location + 3 * p;
+    for (int r = 0; r < 3; ++r) C.loc[k][r] = (T)(At[3 * r] * l[0] + At[3 * r + 1] * l[1] + At[3 * r + 2] * l[2]);
+    for (int r = 0; r < 3; ++r) { C.hc[k][r] = (T)cd.normal_model[3 * p + r]; C.fr[k][r] = (T)cd.friction_model[3 * p + r]; }
+  }
+  for (int h = 0; h < cd.nhalfspaces; ++h) {
+    const double* hs = cd.halfspace + 6 * h;
+    const double nn = std::sqrt(hs[3] * hs[3] + hs[4] * hs[4] + hs[5] * hs[5]);
+    for (int r = 0; r < 3; ++r) { C.hp[h][r] = (T)hs[r]; C.hn[h][r] = (T)(hs[3 + r] / nn); }
+  }
+}
+
+template <class T, class ST>
+RBD_HD void contact_sample(const ModelDev<T>& M, const ContactDev<T>& C, const ContactIO<T>& io, const ST& st) {
+  const int nb = M.nb;
+  Pose<T> cur;
+  pose_identity(cur);
+  Mot<T> twc;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) twc.w[k] = twc.l[k] = T(0);
+  for (int i = 0; i < nb; ++i) {
+    const BodyDev<T>& bd = M.body[i];
+    Pose<T> pp;
+    Mot<T> twp;
+    if (bd.flags & F_ROOT_CHILD) {
+      pose_identity(pp);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) twp.w[k] = twp.l[k] = T(0);
+    } else if (bd.flags & F_FIRST_CHILD) {
+      pp = cur; twp = twc;
+    } else {
+      const int row = bd.pslot * kSlotRowsKin;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) pp.R[k] = st.ld(row + k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { pp.p[k] = st.ld(row + 9 + k); twp.w[k] = st.ld(row + 12 + k); twp.l[k] = st.ld(row + 15 + k); }
+    }
+    T R[9], r[3], t[3];
+    frame_any(bd, io.q, R, r);
+    Pose<T> w;
+    mat_mul3(pp.R, R, w.R);
+    mat_vec(pp.R, r, t);
+    w.p[0] = pp.p[0] + t[0]; w.p[1] = pp.p[1] + t[1]; w.p[2] = pp.p[2] + t[2];
+    Mot<T> tw = twp;
+    const int nvj = kind_nv_dev(bd.kind);
+    for (int k = 0; k < nvj; ++k) {
+      Mot<T> S;
+      world_subspace(w, sub_comp(bd.kind, k), S);
+      const T x = io.v(bd.vrow + k);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { tw.w[c] += x * S.w[c]; tw.l[c] += x * S.l[c]; }
+    }
+    T wn[3] = {T(0), T(0), T(0)}, wf[3] = {T(0), T(0), T(0)};
+    for (int pi = C.first[i]; pi < C.first[i + 1]; ++pi) {
+      T pt[3], vel[3], tmp[3];
+      mat_vec(w.R, C.loc[pi], tmp);
+      pt[0] = w.p[0] + tmp[0]; pt[1] = w.p[1] + tmp[1]; pt[2] = w.p[2] + tmp[2];
+      cross3(tw.w, pt, vel);                                   // point_velocity(twist, point), spatialmotion.jl
+      vel[0] += tw.l[0]; vel[1] += tw.l[1]; vel[2] += tw.l[2];
+      for (int h = 0; h < C.nhalf; ++h) {
+        const int64_t srow = (int64_t)3 * (C.orig[pi] * C.nhalf + h);
+        const T* n = C.hn[h];
+        const T sep = (pt[0] - C.hp[h][0]) * n[0] + (pt[1] - C.hp[h][1]) * n[1] + (pt[2] - C.hp[h][2]) * n[2];
+        T xd[3] = {T(0), T(0), T(0)};
+        if (sep <= T(0)) {
+          const T z = -sep;
+          const T zd = -(vel[0] * n[0] + vel[1] * n[1] + vel[2] * n[2]);
+          const T zn = contact_pow(z, C.hc[pi][2]);
+          T fn = C.hc[pi][1] * zn * zd + C.hc[pi][0] * zn;
+          fn = fn > T(0) ? fn : T(0);
+          const T mu = C.fr[pi][0], kf = C.fr[pi][1], bf = C.fr[pi][2];
+          T x[3], ft[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            x[k] = io.s ? io.s[(srow + k) * io.ld] : T(0);
+            ft[k] = -kf * x[k] - bf * (vel[k] + zd * n[k]);          // f_stick; tangential velocity = velocity + zdot * normal
+          }
+          const T n2 = ft[0] * ft[0] + ft[1] * ft[1] + ft[2] * ft[2], m2 = (mu * fn) * (mu * fn);
+          if (n2 > m2) {
+            const T sc = contact_sqrt(m2 / n2);
+            ft[0] *= sc; ft[1] *= sc; ft[2] *= sc;
+          }
+          T f[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { f[k] = fn * n[k] + ft[k]; xd[k] = (-kf * x[k] - ft[k]) / bf; }
+          T m[3];
+          cross3(pt, f, m);                                   // Wrench(point, force)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { wn[k] += m[k]; wf[k] += f[k]; }
+        } else if (io.s && io.active) {                       // Contact.reset!(contact_state)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) io.s[(srow + k) * io.ld] = T(0);
+        }
+        if (io.sd && io.active) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) io.sd[(srow + k) * io.ld] = xd[k];
+        }
+      }
+    }
+    if (io.active) {
+      const int64_t orow = (int64_t)6 * bd.refidx;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { io.wr[(orow + k) * io.ld] = wn[k]; io.wr[(orow + 3 + k) * io.ld] = wf[k]; }
+    }
+    if (bd.flags & F_HAS_PENDING) {
+      const int row = bd.oslot * kSlotRowsKin;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) st.st(row + k, w.R[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { st.st(row + 9 + k, w.p[k]); st.st(row + 12 + k, tw.w[k]); st.st(row + 15 + k, tw.l[k]); }
+    }
+    cur = w; twc = tw;
   }
 }
 

@@ -200,3 +200,19 @@ class SpecProgram:
             self.fn(q.ctypes.data + b * es, v.ctypes.data + b * es, None if in2 is None else in2.ctypes.data + b * es,
                     o0.ctypes.data + b * es, None if o1 is None else o1.ctypes.data + b * es, B, sh.ctypes.data)
         return (o0, o1) if self.has_out1 else o0
+
+
+def contact(desc, q, v, cd, s=None):
+    """contact_sample (csrc/rbd_kin.cuh) on the CPU for a ``ContactDesc``; returns (wrenches, state_derivatives, state)."""
+    d, keep = make_desc(desc)
+    st, keep2 = cd.c_struct()
+    q = np.ascontiguousarray(q); v = np.ascontiguousarray(v, q.dtype)
+    dt, B = q.dtype, q.shape[1]
+    ns = cd.nstates
+    s = np.zeros((ns, B), dt) if s is None else np.array(s, dt, copy=True, order="C")
+    sd = np.full((ns, B), np.nan, dt); wr = np.full((6 * desc.nb, B), np.nan, dt)
+    fn = lib().hostsim_contact
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc), ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
+    rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(v), ctypes.byref(st), _p(s), _p(sd), _p(wr))
+    assert rc == 0, rc
+    return wr, sd, s

@@ -78,6 +78,21 @@ void run_kin(const HostModel& hm, int64_t B, const T* q, const T* v, const int8_
   }
 }
 
+template <class T>
+void run_contact(const HostModel& hm, int64_t B, const T* q, const T* v, const rbd_contact_desc& cd, T* s, T* sd, T* wr) {
+  const ModelDev<T>& M = dev<T>(hm);
+  ContactDev<T> C;
+  build_contact_dev<T>(hm.nb, hm.pos.data(), hm.alignT.data(), cd, C);
+  std::vector<T> stash(kin_rows(hm) + 64);
+  for (int64_t b = 0; b < B; ++b) {
+    ContactIO<T> io;
+    io.q = {q + b, B}; io.v = {v + b, B};
+    io.s = s ? s + b : nullptr; io.sd = sd ? sd + b : nullptr; io.wr = wr + b;
+    io.ld = B; io.active = true;
+    contact_sample<T>(M, C, io, Stash<T, 1>{stash.data()});
+  }
+}
+
 template <class T> void run_crba(const HostModel& hm, int64_t B, const T* q, T* Mout) {
   const ModelDev<T>& M = dev<T>(hm);
   std::vector<T> stash(crba_rows(hm) + 64);
@@ -248,6 +263,15 @@ int hostsim_kinematics(const rbd_model_desc* d, int dtype, int64_t B, const void
   if (rc) return rc;
   if (dtype == 0) run_kin<float>(hm, B, (const float*)q, (const float*)v, sign, (float* const*)outs);
   else run_kin<double>(hm, B, (const double*)q, (const double*)v, sign, (double* const*)outs);
+  return 0;
+}
+int hostsim_contact(const rbd_model_desc* d, int dtype, int64_t B, const void* q, const void* v, const rbd_contact_desc* cd, void* s,
+                    void* sd, void* wr) {
+  HostModel hm; std::string err;
+  int rc = build_host_model(d, hm, err);
+  if (rc) return rc;
+  if (dtype == 0) run_contact<float>(hm, B, (const float*)q, (const float*)v, *cd, (float*)s, (float*)sd, (float*)wr);
+  else run_contact<double>(hm, B, (const double*)q, (const double*)v, *cd, (double*)s, (double*)sd, (double*)wr);
   return 0;
 }
 int hostsim_flags(const rbd_model_desc* d, int* flags /* [nb], preorder */) {
