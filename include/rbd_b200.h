@@ -229,6 +229,22 @@ int32_t rbd_dynamics_result(const rbd_model* model, int32_t dtype, int64_t B, in
                             const void* tau, const void* wext, void* vd_out, void* qd_out, void* M_out, void* c_out,
                             void* accelerations_out, void* jointwrenches_out, void* stream);
 
+/* Next row of the scope table: first derivatives of forward dynamics, analytically -- what the reference's
+ * users obtain by pushing ForwardDiff.Dual numbers through dynamics! (examples/5. Derivatives and gradients using ForwardDiff,
+ * test/test_mechanism_algorithms.jl:600-675, src/caches.jl:46-64), here in ONE call for the whole Jacobian of every sample:
+ *   vd_out      [nv x B]     v̇ = dynamics!(...)                     (always written; it is the linearisation point)
+ *   dvd_dq_out  [nv*nv x B]  entry (i, j) at row i + j*nv:  d v̇_i / d q_j  along velocity coordinate j, i.e. the derivative of
+ *                            v̇ along q̇ = velocity_to_configuration_derivative(e_j) (mechanism_state.jl:905-910).  For joints with
+ *                            nq == nv whose q̇ = v (revolute, prismatic, planar in its own axes) this is d v̇ / d q itself; in general
+ *                            it equals  [d v̇ / d q] * velocity_to_configuration_derivative_jacobian(state)  -- the Jacobian in
+ *                            the tangent space, which is what the Munthe-Kaas integrator's local coordinates need and which does
+ *                            not depend on how the rotation is extended to non-unit quaternions.
+ *   dvd_dv_out  [nv*nv x B]  d v̇_i / d v_j, same layout.
+ * d v̇ / d tau is M^-1: mass_matrix! gives M.  tau may be NULL (zero torques).  fp32 / fp64; no external wrenches (RBD_EUNSUPPORTED
+ * is never returned for them: the argument does not exist -- use the reference's Dual path, rbd_dynamics with RBD_DUAL64X6). */
+int32_t rbd_dynamics_derivatives(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
+                                 const void* tau, void* vd_out, void* dvd_dq_out, void* dvd_dv_out, void* stream);
+
 /* dynamics_bias!(result, state) / dynamics_bias!(torques, biasaccelerations, wrenches, state, externalwrenches)
  *                                                             src/mechanism_algorithms.jl:484-498
  *   -> c_out [nv x B] = c(q, v, wext) = inverse_dynamics with v̇ = 0. */

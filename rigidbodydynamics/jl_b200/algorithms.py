@@ -18,7 +18,7 @@ import torch
 from . import _cabi
 from .state import DynamicsResult, MechanismState, _DT
 
-__all__ = ["dynamics_", "dynamics_dual_", "dynamics_ode_", "simulate_", "inverse_dynamics_", "inverse_dynamics", "mass_matrix_", "mass_matrix",
+__all__ = ["dynamics_", "dynamics_dual_", "dynamics_derivatives_", "dynamics_ode_", "simulate_", "inverse_dynamics_", "inverse_dynamics", "mass_matrix_", "mass_matrix",
            "dynamics_bias_", "dynamics_bias", "DimensionMismatch"]
 
 
@@ -98,6 +98,28 @@ def dynamics_dual_(vd_out: torch.Tensor, state: MechanismState, q: torch.Tensor,
     _call(lib.rbd_dynamics(state.handle.ptr, _cabi.RBD_DUAL64X6, B, B, _ptr(q), _ptr(v), _ptr(torques), None,
                            _ptr(vd_out), None, _stream()))
     return vd_out
+
+
+def dynamics_derivatives_(dvd_dq: torch.Tensor, dvd_dv: torch.Tensor, result: DynamicsResult, state: MechanismState,
+                          torques: Optional[torch.Tensor] = None):
+    """Jacobians of ``dynamics!`` with respect to the configuration (tangent space) and the velocity for every sample, in one call:
+    the batched, analytic counterpart of ``ForwardDiff.jacobian`` over the reference's generic ``dynamics!`` (examples/5,
+    test/test_mechanism_algorithms.jl:600-675).  ``dvd_dq`` / ``dvd_dv`` are [nv*nv, B], entry (i, j) at row i + j*nv (column-major
+    like ``M.data``); ``dvd_dq[:, j]`` is the derivative along ``velocity_to_configuration_derivative(e_j)``, i.e.
+    ``(d v̇/d q) * velocity_to_configuration_derivative_jacobian(state)``.  ``result.vd`` receives v̇."""
+    state.check_modcount()
+    lib = _cabi.load_library()
+    _check(torques, state.nv, state, "torques")
+    _check(result.vd, state.nv, state, "result.vd")
+    _check(dvd_dq, state.nv * state.nv, state, "dvd_dq")
+    _check(dvd_dv, state.nv * state.nv, state, "dvd_dv")
+    if dvd_dq is None or dvd_dv is None:
+        raise ValueError("dvd_dq and dvd_dv must be given")
+    with torch.cuda.device(state.q.device):
+        _call(lib.rbd_dynamics_derivatives(state.handle.ptr, _DT[state.dtype], state.batch, state.batch, _ptr(state.q), _ptr(state.v),
+                                           _ptr(torques), _ptr(result.vd), _ptr(dvd_dq), _ptr(dvd_dv),
+                                           torch.cuda.current_stream(state.q.device).cuda_stream))
+    return dvd_dq, dvd_dv
 
 
 def dynamics_ode_(xdot: torch.Tensor, result: DynamicsResult, state: MechanismState, x: torch.Tensor,

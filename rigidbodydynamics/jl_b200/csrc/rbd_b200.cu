@@ -1152,6 +1152,16 @@ int check_common(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, b
 
 }  // namespace
 
+// hooks for the other translation units of the library (rbd_deriv.cu): per-thread error text, argument checks, launch statistics
+namespace rbd {
+int api_fail(int status, const std::string& msg) { return fail(status, msg); }
+int api_check(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld) { return check_common(model, dtype, B, ld); }
+void api_note_launch(int grid, int block, int smem_bytes, int blocks_per_sm) {
+  g_launch.kernels_launched += 1;
+  g_launch.grid = grid; g_launch.block = block; g_launch.smem_bytes = smem_bytes; g_launch.blocks_per_sm = blocks_per_sm;
+}
+}  // namespace rbd
+
 // ------------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------------

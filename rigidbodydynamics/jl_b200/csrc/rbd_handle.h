@@ -87,4 +87,9 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
 int spec_prepare(rbd_model* m, const SpecKey& key, bool load_on_device, std::string& err);
 void spec_release(rbd_model* m);
 
+// rbd_b200.cu's per-thread error text / argument checks / launch statistics, for the library's other translation units
+int api_fail(int status, const std::string& msg);
+int api_check(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld);
+void api_note_launch(int grid, int block, int smem_bytes, int blocks_per_sm);
+
 }  // namespace rbd

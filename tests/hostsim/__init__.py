@@ -85,6 +85,22 @@ def mass_matrix(desc, q):
     return M
 
 
+def dynamics_derivatives(desc, q, v, tau=None):
+    """csrc/rbd_deriv.cuh on the CPU: (vd [nv, B], dvd_dq [nv*nv, B], dvd_dv [nv*nv, B]), entry (i, j) at row i + j*nv."""
+    dt = q.dtype
+    d, keep = make_desc(desc)
+    q = np.ascontiguousarray(q); v = np.ascontiguousarray(v, dt)
+    tau = None if tau is None else np.ascontiguousarray(tau, dt)
+    B, nv = q.shape[1], desc.nv
+    vd = np.empty((nv, B), dt)
+    dq = np.zeros((nv * nv, B), dt); dv = np.zeros((nv * nv, B), dt)
+    fn = lib().hostsim_derivatives
+    fn.argtypes = [ctypes.POINTER(RbdModelDesc), ctypes.c_int, ctypes.c_int64] + [ctypes.c_void_p] * 6
+    rc = fn(ctypes.byref(d), 0 if dt == np.float32 else 1, B, _p(q), _p(v), _p(tau), _p(vd), _p(dq), _p(dv))
+    assert rc == 0, rc
+    return vd, dq, dv
+
+
 def dynamics_dual(desc, q, v, tau=None):
     """Dual{Float64,6} arrays [rows, B, 7]."""
     d, keep = make_desc(desc)

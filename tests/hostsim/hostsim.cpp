@@ -8,6 +8,7 @@
 
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_rnea_crba.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_kin.cuh"
+#include "../../rigidbodydynamics/jl_b200/csrc/rbd_deriv.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_dual.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_integrate.cuh"
 #include "../../rigidbodydynamics/jl_b200/csrc/rbd_model.h"
@@ -106,6 +107,31 @@ template <class T> void run_crba(const HostModel& hm, int64_t B, const T* q, T* 
     if (multi) crba_sample<T, 1, 6>(M, io, Stash<T, 1>{stash.data()});
     else crba_sample<T, 1, 1>(M, io, Stash<T, 1>{stash.data()});
   }
+}
+// dv̇/dq, dv̇/dv (csrc/rbd_deriv.cuh): the five phases run one sample at a time with a scratch of one column
+template <class T>
+int run_derivatives(const HostModel& hm, int64_t B, const T* q, const T* v, const T* tau, T* vd, T* dq, T* dv) {
+  const ModelDev<T>& M = dev<T>(hm);
+  DerivDev D;
+  if (!build_deriv_dev(M, D)) return RBD_EUNSUPPORTED;
+  run_dynamics<T>(hm, B, q, v, tau, nullptr, vd, nullptr);
+  std::vector<T> stash(kin_rows(hm) + 64), scr(D.rows), x(D.nv);
+  for (int64_t b = 0; b < B; ++b) {
+    DerivIO<T> io;
+    io.q = {q + b, B}; io.v = {v + b, B}; io.vd = {vd + b, B};
+    io.s = scr.data(); io.sld = 1; io.active = true;
+    deriv_world_sample<T>(M, D, io, Stash<T, 1>{stash.data()});
+    for (int c = 0; c < kBodyRows; ++c) deriv_accumulate<T>(M, D, scr.data(), 1, c);
+    for (int K = 0; K < M.nb; ++K) deriv_pairs<T>(M, D, scr.data(), 1, dq + b, dv + b, B, K, true);
+    deriv_factor<T>(D, scr.data(), 1);
+    const T* H = scr.data() + D.h_base;
+    auto Hf = [H](int row) { return H[row]; };
+    for (int c = 0; c < 2 * D.nv; ++c) {
+      T* out = (c < D.nv ? dq : dv) + (int64_t)(c % D.nv) * D.nv * B + b;
+      deriv_solve_column<T>(D, Hf, x.data(), 1, out, B, c % D.nv, true);
+    }
+  }
+  return 0;
 }
 }  // namespace
 
@@ -273,6 +299,14 @@ int hostsim_contact(const rbd_model_desc* d, int dtype, int64_t B, const void* q
   if (dtype == 0) run_contact<float>(hm, B, (const float*)q, (const float*)v, *cd, (float*)s, (float*)sd, (float*)wr);
   else run_contact<double>(hm, B, (const double*)q, (const double*)v, *cd, (double*)s, (double*)sd, (double*)wr);
   return 0;
+}
+int hostsim_derivatives(const rbd_model_desc* d, int dtype, int64_t B, const void* q, const void* v, const void* tau, void* vd, void* dq,
+                        void* dv) {
+  HostModel hm; std::string err;
+  int rc = build_host_model(d, hm, err);
+  if (rc) return rc;
+  if (dtype == 0) return run_derivatives<float>(hm, B, (const float*)q, (const float*)v, (const float*)tau, (float*)vd, (float*)dq, (float*)dv);
+  return run_derivatives<double>(hm, B, (const double*)q, (const double*)v, (const double*)tau, (double*)vd, (double*)dq, (double*)dv);
 }
 int hostsim_flags(const rbd_model_desc* d, int* flags /* [nb], preorder */) {
   HostModel hm; std::string err;

@@ -126,3 +126,34 @@ def axis_aligned_tree(seed, n=24):
         mech.attach(parent, rbd.RigidBody(f"b{i}", rbd.SpatialInertia.rand(rng)), rbd.Joint(f"j{i}", jt),
                     joint_pose=rbd.Transform3D(R, trans))
     return mech
+
+
+def oracle_dynamics_derivatives(oracle, mech, q, v, tau):
+    """Tangent-space Jacobians of forward dynamics from the ORACLE's dual-number run of the reference's own algorithm, the way a
+    ForwardDiff user gets them (examples/5, test_mechanism_algorithms.jl:600-675): partial k of q is seeded with
+    q̇ = velocity_to_configuration_derivative(e_k) (mechanism_state.jl:905-910), partial k of v with e_k; six partials per sweep.
+    Returns (dvd_dq, dvd_dv), each [nv*nv, B] with entry (i, j) at row i + j*nv."""
+    q, v, tau = np.asarray(q, float), np.asarray(v, float), np.asarray(tau, float)
+    nq, B = q.shape
+    nv = v.shape[0]
+    N = np.zeros((nq, nv, B))                       # velocity_to_configuration_derivative_jacobian, column by column
+    for k in range(nv):
+        e = np.zeros((nv, B)); e[k] = 1.0
+        N[:, k] = oracle.dynamics(q, e, tau, want_qd=True)[1]
+    out = []
+    for which in range(2):
+        J = np.zeros((nv, nv, B))
+        for k0 in range(0, nv, 6):
+            Q = np.zeros((nq, B, 7)); V = np.zeros((nv, B, 7)); T = np.zeros((nv, B, 7))
+            Q[..., 0], V[..., 0], T[..., 0] = q, v, tau
+            ks = range(k0, min(k0 + 6, nv))
+            for s, k in enumerate(ks):
+                if which == 0:
+                    Q[:, :, 1 + s] = N[:, k]
+                else:
+                    V[k, :, 1 + s] = 1.0
+            r = oracle.dynamics_dual6(Q, V, T)
+            for s, k in enumerate(ks):
+                J[:, k] = r[:, :, 1 + s]
+        out.append(J.transpose(1, 0, 2).reshape(nv * nv, B))   # row i + j*nv  <->  [j, i]
+    return out[0], out[1]
