@@ -217,7 +217,25 @@ def other_configs(steps):
     odual = torch.empty((36, Bd, 7), dtype=torch.float64, device="cuda")
     ms = time_fn(lambda: rbd.dynamics_dual_(odual, std, qd_, vdual, tdual), max(3, steps // 2))
     out["atlas_dual64x6_dynamics_b8192"] = {"evals_per_s": Bd / (ms * 1e-3), "ms": ms, "algorithmic_GBps": Bd * 8120 / (ms * 1e-3) / 1e9}
+    dual_sweeps_per_s = Bd / (ms * 1e-3)
     del std, stq, qd_, vdual, tdual, odual
+    # the full Jacobians dv̇/dq, dv̇/dv analytically (rbd_dynamics_derivatives) -- what 2 nv / 6 = 12 of the Dual
+    # sweeps above produce for one Atlas sample.  Algorithmic bytes: q, v, tau in; v̇ and two nv x nv matrices out.
+    for tdt, key, Bj in ((torch.float64, "f64", 1 << 15), (torch.float32, "f32", 1 << 16)):
+        stj = rbd.MechanismState(atlas, Bj, tdt)
+        rbd.rand_(stj, rng)
+        tauj = torch.rand((36, Bj), dtype=tdt, device="cuda")
+        resj = rbd.DynamicsResult(atlas, Bj, tdt)
+        dq = torch.empty((36 * 36, Bj), dtype=tdt, device="cuda")
+        dv = torch.empty_like(dq)
+        ms = time_fn(lambda: rbd.dynamics_derivatives_(dq, dv, resj, stj, tauj), max(3, steps // 2))
+        es = dq.element_size()
+        out[f"atlas_{key}_dynamics_derivatives_b{Bj}"] = {
+            "jacobian_pairs_per_s": Bj / (ms * 1e-3), "ms": ms, "dual_sweep_equivalents_per_s": Bj / (ms * 1e-3) * 12,
+            "vs_own_dual_sweeps": Bj / (ms * 1e-3) * 12 / dual_sweeps_per_s,
+            "algorithmic_GBps": Bj * (37 + 36 + 36 + 36 + 2 * 1296) * es / (ms * 1e-3) / 1e9,
+            "kernel_launches": rbd.launch_info().kernels_launched}
+        del stj, tauj, resj, dq, dv
     iiwa = rbd.load_model("iiwa14")
     st = rbd.MechanismState(iiwa, B, torch.float32)
     rbd.rand_(st, rng)

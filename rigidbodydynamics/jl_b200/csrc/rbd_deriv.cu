@@ -1,13 +1,14 @@
 // rbd_dynamics_derivatives: batched analytic dv̇/dq, dv̇/dv (csrc/rbd_deriv.cuh has the mathematics and the work split).
 //
-// Five kernels per chunk of the batch, all with the sample index fastest (lane l of a warp = sample b0 + l, so every global
+// Four kernels (after the forward dynamics itself) per chunk of the batch, all with the sample index fastest (lane l of a warp = sample b0 + l, so every global
 // access of a warp is one fully used line) and warp-uniform control flow (the tree walk depends on the model only):
 //   deriv_world_kernel   one thread per sample            root-frame S, Psi_dot, Psi_ddot, Sdp per coordinate; I, G, f per body
 //   deriv_accum_kernel   one thread per (sample, 1 of 52) subtree sums of (I, G, f)
 //   deriv_pairs_kernel   one thread per (sample, body)    d tau/dq, d tau/dv (into the output arrays) and M (into the scratch)
-//   deriv_factor_kernel  one thread per sample            M = L^T D L with the tree's sparsity
-//   deriv_solve_kernel   one warp per (32 samples, column subset): the factor of the 32 samples is staged in shared memory once and
-//                        re-used by all 2 nv columns; each warp keeps its right-hand side in shared memory, [row][lane]
+//   deriv_solve_kernel   one CTA per 32 samples (lane = sample), W warps: M of the 32 samples is staged in shared memory, factored
+//                        there as L^T D L (tree sparsity) by the W warps together, then each warp solves its share of the 2 nv
+//                        columns in place with its right-hand side in shared memory, [row][lane]
+//   (deriv_factor_kernel one thread per sample, on the scratch: only when M does not fit into shared memory)
 // Intermediates: a global scratch of DerivDev::rows rows per sample, allocated from the stream-ordered pool per call and
 // bounded by RBD_DERIV_SCRATCH_MB (default 2048): larger batches are processed in chunks on the same stream.
 #include <cuda_runtime.h>
@@ -73,28 +74,33 @@ __global__ void __launch_bounds__(NT) deriv_accum_kernel(const __grid_constant__
 }
 
 template <class T, int NT>
-__global__ void __launch_bounds__(NT) deriv_pairs_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ DerivDev D,
+__global__ void __launch_bounds__(NT) deriv_pairs_kernel(const __grid_constant__ DerivDev D, const __grid_constant__ DerivAnc A,
                                                          const DerivArgs<T> a) {
   const int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x;
   if (b >= a.C) return;
-  deriv_pairs<T>(M, D, a.s + b, a.sld, a.dq + b, a.dv + b, a.ld, blockIdx.y, true);
+  deriv_pairs<T>(D, A, a.s + b, a.sld, a.dq + b, a.dv + b, a.ld, blockIdx.y, true);
 }
 
+// only for models whose factor does not fit into shared memory next to the right-hand sides (deriv_solve_kernel<T, false>)
 template <class T, int NT>
-__global__ void __launch_bounds__(NT) deriv_factor_kernel(const __grid_constant__ DerivDev D, const DerivArgs<T> a) {
+__global__ void __launch_bounds__(NT) deriv_factor_kernel(const __grid_constant__ DerivDev D, const __grid_constant__ DerivAnc A,
+                                                          const DerivArgs<T> a) {
   const int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x;
   if (b >= a.C) return;
-  deriv_factor<T>(D, a.s + b, a.sld);
+  deriv_factor<T>(D, A, a.s + (int64_t)D.h_base * a.sld + b, a.sld);
 }
 
-// blockDim = (32, W).  HS: the factor of the block's 32 samples is staged in shared memory; otherwise it is read from the scratch.
+// blockDim = (32, W): lane = sample, warp = column subset.  HS: M of the block's 32 samples is staged in shared memory, factored
+// there by all W warps together (row k's updates of its ancestors' rows are independent of each other: warp w takes the
+// ancestors at depth w, w + W, ...; two barriers per row) and then re-used by all 2 nv columns.  Otherwise the factor was made
+// by deriv_factor_kernel and is read from the scratch.
 template <class T, bool HS>
-__global__ void deriv_solve_kernel(const __grid_constant__ DerivDev D, const DerivArgs<T> a) {
+__global__ void deriv_solve_kernel(const __grid_constant__ DerivDev D, const __grid_constant__ DerivAnc A, const DerivArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm = reinterpret_cast<T*>(smem_raw);
   const int lane = threadIdx.x, w = threadIdx.y, W = blockDim.y;
   const int nv = D.nv, nnz = D.nnz;
-  T* Hs = sm;
+  T* Hs = sm + lane;
   T* xs = sm + (HS ? (size_t)nnz * 32 : 0) + (size_t)w * nv * 32 + lane;
   const int64_t ngroups = (a.C + 31) / 32;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
@@ -104,18 +110,31 @@ __global__ void deriv_solve_kernel(const __grid_constant__ DerivDev D, const Der
     const T* Hg = a.s + (int64_t)D.h_base * a.sld + bl;
     if (HS) {
       __syncthreads();      // the previous group's columns are done with Hs
-      for (int r = w; r < nnz; r += W) Hs[r * 32 + lane] = Hg[(int64_t)r * a.sld];
+      for (int r = w; r < nnz; r += W) Hs[r * 32] = Hg[(int64_t)r * a.sld];
+      for (int k = nv - 1; k >= 0; --k) {
+        const int rk = D.rowstart[k], dk = D.depth[k];
+        __syncthreads();    // row k has received the updates of all its descendants
+        const T inv = T(1) / Hs[(rk + dk) * 32];
+        for (int di = w; di < dk; di += W) {
+          const int ri = D.rowstart[A.anc[rk + di]];
+          const T f = Hs[(rk + di) * 32] * inv;
+          for (int d = di; d >= 0; --d) Hs[(ri + d) * 32] -= f * Hs[(rk + d) * 32];
+        }
+        __syncthreads();    // everybody has read row k
+        for (int di = w; di < dk; di += W) Hs[(rk + di) * 32] *= inv;
+        if (w == 0) Hs[(rk + dk) * 32] = inv;
+      }
       __syncthreads();
     }
     for (int c = w; c < 2 * nv; c += W) {
       const int vj = c < nv ? c : c - nv;
       T* col = (c < nv ? a.dq : a.dv) + (int64_t)vj * nv * a.ld + bl;
       if (HS) {
-        const T* Hl = Hs + lane;
-        deriv_solve_column<T>(D, [Hl](int row) { return Hl[row * 32]; }, xs, 32, col, a.ld, vj, active);
+        const T* Hl = Hs;
+        deriv_solve_column<T>(D, A, [Hl](int row) { return Hl[row * 32]; }, xs, 32, col, a.ld, vj, active);
       } else {
         const int64_t sld = a.sld;
-        deriv_solve_column<T>(D, [Hg, sld](int row) { return Hg[(int64_t)row * sld]; }, xs, 32, col, a.ld, vj, active);
+        deriv_solve_column<T>(D, A, [Hg, sld](int row) { return Hg[(int64_t)row * sld]; }, xs, 32, col, a.ld, vj, active);
       }
     }
   }
@@ -151,7 +170,9 @@ int derivatives_t(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, 
   const HostModel& hm = model->hm;
   const ModelDev<T>& M = dev_model<T>(hm);
   DerivDev D;
-  if (!build_deriv_dev(M, D)) return api_fail(RBD_EUNSUPPORTED, "rbd_dynamics_derivatives: more than 128 velocity coordinates");
+  DerivAnc A;
+  if (!build_deriv_dev(M, D, A))
+    return api_fail(RBD_EUNSUPPORTED, "rbd_dynamics_derivatives: more than 128 velocity coordinates or 4096 mass-matrix entries");
   Props p;
   if (int rc = get_props(p)) return rc;
   // chunk size from the scratch budget
@@ -176,6 +197,7 @@ int derivatives_t(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, 
     const int W = (int)std::min<int64_t>(std::min(16, 2 * D.nv), avail / (int64_t)xbytes);
     if (W * nb > bestW * bestNb) { bestW = W; bestNb = nb; }
   }
+  if (const char* e = std::getenv("RBD_DERIV_GLOBAL_FACTOR")) { if (e[0] == '1') bestW = 0; }   // tests: exercise the fallback
   if (bestW == 0) {       // factor too large for shared memory: read it from the scratch
     hs = false;
     bestW = (int)std::min<int64_t>(std::min(8, 2 * D.nv), p.max_smem_optin / (int64_t)xbytes);
@@ -202,15 +224,17 @@ int derivatives_t(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, 
     deriv_accum_kernel<T, kNT><<<dim3(gx, kBodyRows), kNT, 0, stream>>>(M, D, a);
     LAUNCH_CHECK("deriv_accum_kernel");
     api_note_launch(gx * kBodyRows, kNT, 0, 0);
-    deriv_pairs_kernel<T, kNT><<<dim3(gx, D.nb), kNT, 0, stream>>>(M, D, a);
+    deriv_pairs_kernel<T, kNT><<<dim3(gx, D.nb), kNT, 0, stream>>>(D, A, a);
     LAUNCH_CHECK("deriv_pairs_kernel");
     api_note_launch(gx * D.nb, kNT, 0, 0);
-    deriv_factor_kernel<T, kNT><<<gx, kNT, 0, stream>>>(D, a);
-    LAUNCH_CHECK("deriv_factor_kernel");
-    api_note_launch(gx, kNT, 0, 0);
+    if (!hs) {
+      deriv_factor_kernel<T, kNT><<<gx, kNT, 0, stream>>>(D, A, a);
+      LAUNCH_CHECK("deriv_factor_kernel");
+      api_note_launch(gx, kNT, 0, 0);
+    }
     const int sg = (int)std::min<int64_t>((c + 31) / 32, (int64_t)bestNb * p.sms);
-    if (hs) ksolve_s<<<sg, dim3(32, bestW), solve_smem, stream>>>(D, a);
-    else ksolve_g<<<sg, dim3(32, bestW), solve_smem, stream>>>(D, a);
+    if (hs) ksolve_s<<<sg, dim3(32, bestW), solve_smem, stream>>>(D, A, a);
+    else ksolve_g<<<sg, dim3(32, bestW), solve_smem, stream>>>(D, A, a);
     LAUNCH_CHECK("deriv_solve_kernel");
     api_note_launch(sg, 32 * bestW, (int)solve_smem, bestNb);
   }

@@ -32,6 +32,7 @@
 namespace rbd {
 
 constexpr int kMaxDofs = 128;
+constexpr int kMaxNnz = 4096;    // stored entries of M (sum of depth + 1): a 89-coordinate serial chain, or any humanoid
 constexpr int kDofRows = 24;     // S, Psi_dot, Psi_ddot, Sdp
 constexpr int kBodyRows = 52;    // Ic (m, h, J: 10), G (36, row-major), F (6)
 
@@ -47,10 +48,15 @@ struct DerivDev {
   int16_t dsub[kMaxDofs];        // size of the coordinate's subtree: descendants-or-self are [p, p + dsub[p])
   int16_t comp[kMaxDofs];        // one-hot component of [w; l] in the canonical body frame
 };
+// anc[rowstart[p] + d] = the ancestor-or-self of coordinate p at depth d (d = 0 .. depth[p]; the last one is p itself): the same
+// index as the entry (p, that ancestor) of M, so the walks up the tree are loops over consecutive table entries instead of
+// pointer chases through lambda[]
+struct DerivAnc { int16_t anc[kMaxNnz]; };
 
 // Host side: tables from the flattened model (preorder bodies).
-template <class T> inline bool build_deriv_dev(const ModelDev<T>& M, DerivDev& D) {
+template <class T> inline bool build_deriv_dev(const ModelDev<T>& M, DerivDev& D, DerivAnc& A) {
   std::memset(&D, 0, sizeof(D));
+  std::memset(&A, 0, sizeof(A));
   D.nb = M.nb; D.nv = M.nv;
   if (M.nv > kMaxDofs) return false;
   int p = 0;
@@ -74,7 +80,9 @@ template <class T> inline bool build_deriv_dev(const ModelDev<T>& M, DerivDev& D
   for (int i = M.nb + 1; i <= kMaxBodies; ++i) D.pdof0[i] = (int16_t)p;
   int nnz = 0;
   for (int k = 0; k < M.nv; ++k) { D.rowstart[k] = (int16_t)nnz; nnz += D.depth[k] + 1; D.dsub[k] = 1; }
-  if (nnz > 32000) return false;
+  if (nnz > kMaxNnz) return false;
+  for (int k = 0; k < M.nv; ++k)
+    for (int a = k; a >= 0; a = D.lambda[a]) A.anc[D.rowstart[k] + D.depth[a]] = (int16_t)a;
   for (int k = M.nv - 1; k >= 0; --k) if (D.lambda[k] >= 0) D.dsub[D.lambda[k]] += D.dsub[k];
   D.nnz = nnz;
   D.dof_base = 0;
@@ -269,7 +277,7 @@ template <class T> RBD_HD void apply_IG(const Rbi<T>& I, const T* G, const Mot<T
 }
 
 template <class T>
-RBD_HD void deriv_pairs(const ModelDev<T>& M, const DerivDev& D, T* s, int64_t sld, T* dq, T* dv, int64_t ld, int K, bool active) {
+RBD_HD void deriv_pairs(const DerivDev& D, const DerivAnc& A, T* s, int64_t sld, T* dq, T* dv, int64_t ld, int K, bool active) {
   const int nv = D.nv;
   const int pk0 = D.pdof0[K], nk = D.pdof0[K + 1] - pk0;
   if (nk == 0) return;
@@ -287,47 +295,44 @@ RBD_HD void deriv_pairs(const ModelDev<T>& M, const DerivDev& D, T* s, int64_t s
 #pragma unroll
     for (int k = 0; k < 3; ++k) { Fn[k] = s[(int64_t)(row + 46 + k) * sld]; Ff[k] = s[(int64_t)(row + 49 + k) * sld]; }
   }
-  for (int A = K; A >= 0; A = M.body[A].parent) {
-    const int pj0 = D.pdof0[A], nj = D.pdof0[A + 1] - pj0;
-    for (int jj = 0; jj < nj; ++jj) {
-      const int pj = pj0 + jj;
-      const int rj = D.dof_base + kDofRows * pj;
-      Mot<T> Sj, pd, pdd, sdp;
-      load_mot(s, sld, rj, Sj);
-      load_mot(s, sld, rj + 6, pd);
-      load_mot(s, sld, rj + 12, pdd);
-      load_mot(s, sld, rj + 18, sdp);
-      T yq[6], yv[6], ym[6];
-      apply_IG(Ic, G, pdd, pd, yq);
-      apply_IG(Ic, G, sdp, Sj, yv);
-      rbi_mul(Ic, Sj, ym, ym + 3);
-      const int64_t colj = (int64_t)nv * D.vrow[pj];
-      for (int kk = 0; kk < nk; ++kk) {
-        const int pk = pk0 + kk;
-        Mot<T> Sk;
-        load_mot(s, sld, D.dof_base + kDofRows * pk, Sk);
-        if (active) {
-          dq[(colj + D.vrow[pk]) * ld] = dot6(Sk, yq);
-          dv[(colj + D.vrow[pk]) * ld] = dot6(Sk, yv);
-          if (pj <= pk) s[(int64_t)(D.h_base + D.rowstart[pk] + D.depth[pj]) * sld] = dot6(Sk, ym);
-        }
+  // all coordinates at or above K, deepest first: the ancestor list of K's last coordinate
+  const int plast = pk0 + nk - 1, rl = D.rowstart[plast];
+  for (int dj = D.depth[plast]; dj >= 0; --dj) {
+    const int pj = A.anc[rl + dj];
+    const int rj = D.dof_base + kDofRows * pj;
+    Mot<T> Sj, pd, pdd, sdp;
+    load_mot(s, sld, rj, Sj);
+    load_mot(s, sld, rj + 6, pd);
+    load_mot(s, sld, rj + 12, pdd);
+    load_mot(s, sld, rj + 18, sdp);
+    T yq[6], yv[6], ym[6];
+    apply_IG(Ic, G, pdd, pd, yq);
+    apply_IG(Ic, G, sdp, Sj, yv);
+    rbi_mul(Ic, Sj, ym, ym + 3);
+    const int64_t colj = (int64_t)nv * D.vrow[pj];
+    for (int kk = 0; kk < nk; ++kk) {
+      const int pk = pk0 + kk;
+      Mot<T> Sk;
+      load_mot(s, sld, D.dof_base + kDofRows * pk, Sk);
+      if (active) {
+        dq[(colj + D.vrow[pk]) * ld] = dot6(Sk, yq);
+        dv[(colj + D.vrow[pk]) * ld] = dot6(Sk, yv);
+        if (pj <= pk) s[(int64_t)(D.h_base + D.rowstart[pk] + D.depth[pj]) * sld] = dot6(Sk, ym);
       }
-      if (A == K) {
-        // rows of the strict ancestors: S_k' . (S_j x* F_K + y)
-        T cn[3], cf[3];
-        force_cross(Sj, Fn, Ff, cn, cf);
+    }
+    if (pj >= pk0) {
+      // j belongs to K itself: rows of the strict ancestors,  S_k' . (S_j x* F_K + y)
+      T cn[3], cf[3];
+      force_cross(Sj, Fn, Ff, cn, cf);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { yq[c] += cn[c]; yq[3 + c] += cf[c]; }
-        for (int A2 = M.body[K].parent; A2 >= 0; A2 = M.body[A2].parent) {
-          const int p0 = D.pdof0[A2], n2 = D.pdof0[A2 + 1] - p0;
-          for (int k2 = 0; k2 < n2; ++k2) {
-            Mot<T> Sa;
-            load_mot(s, sld, D.dof_base + kDofRows * (p0 + k2), Sa);
-            if (active) {
-              dq[(colj + D.vrow[p0 + k2]) * ld] = dot6(Sa, yq);
-              dv[(colj + D.vrow[p0 + k2]) * ld] = dot6(Sa, yv);
-            }
-          }
+      for (int c = 0; c < 3; ++c) { yq[c] += cn[c]; yq[3 + c] += cf[c]; }
+      for (int d2 = D.depth[pk0] - 1; d2 >= 0; --d2) {
+        const int p2 = A.anc[D.rowstart[pk0] + d2];
+        Mot<T> Sa;
+        load_mot(s, sld, D.dof_base + kDofRows * p2, Sa);
+        if (active) {
+          dq[(colj + D.vrow[p2]) * ld] = dot6(Sa, yq);
+          dv[(colj + D.vrow[p2]) * ld] = dot6(Sa, yv);
         }
       }
     }
@@ -337,19 +342,17 @@ RBD_HD void deriv_pairs(const ModelDev<T>& M, const DerivDev& D, T* s, int64_t s
 // ------------------------------------------------------------------------------------------------------------------
 // 4. M = L^T D L in place on the scratch, one thread per sample; the diagonal is left INVERTED.
 // ------------------------------------------------------------------------------------------------------------------
-template <class T> RBD_HD void deriv_factor(const DerivDev& D, T* s, int64_t sld) {
-  T* H = s + (int64_t)D.h_base * sld;
+template <class T> RBD_HD void deriv_factor(const DerivDev& D, const DerivAnc& A, T* H, int64_t sld) {
   for (int k = D.nv - 1; k >= 0; --k) {
-    const int rk = D.rowstart[k];
-    const T inv = T(1) / H[(int64_t)(rk + D.depth[k]) * sld];
-    for (int i = D.lambda[k]; i >= 0; i = D.lambda[i]) {
-      const int ri = D.rowstart[i], di = D.depth[i];
-      const T hki = H[(int64_t)(rk + di) * sld];
-      const T a = hki * inv;
+    const int rk = D.rowstart[k], dk = D.depth[k];
+    const T inv = T(1) / H[(int64_t)(rk + dk) * sld];
+    for (int di = dk - 1; di >= 0; --di) {
+      const int ri = D.rowstart[A.anc[rk + di]];
+      const T a = H[(int64_t)(rk + di) * sld] * inv;
       for (int d = di; d >= 0; --d) H[(int64_t)(ri + d) * sld] -= a * H[(int64_t)(rk + d) * sld];
-      H[(int64_t)(rk + di) * sld] = a;
     }
-    H[(int64_t)(rk + D.depth[k]) * sld] = inv;
+    for (int di = 0; di < dk; ++di) H[(int64_t)(rk + di) * sld] *= inv;
+    H[(int64_t)(rk + dk) * sld] = inv;
   }
 }
 
@@ -358,7 +361,7 @@ template <class T> RBD_HD void deriv_factor(const DerivDev& D, T* s, int64_t sld
 //    H(row) reads the factor; col: this sample's column of the nv x nv array, rows x batch.
 // ------------------------------------------------------------------------------------------------------------------
 template <class T, class HF>
-RBD_HD void deriv_solve_column(const DerivDev& D, const HF& H, T* x, int xs, T* col, int64_t ld, int vj, bool active) {
+RBD_HD void deriv_solve_column(const DerivDev& D, const DerivAnc& A, const HF& H, T* x, int xs, T* col, int64_t ld, int vj, bool active) {
   const int nv = D.nv;
   const int pj = D.pdof[vj];
   const int lo = pj, hi = pj + D.dsub[pj];
@@ -367,20 +370,26 @@ RBD_HD void deriv_solve_column(const DerivDev& D, const HF& H, T* x, int xs, T* 
     const bool rel = (p >= lo && p < hi) || (pj >= p && pj < p + D.dsub[p]);
     x[p * xs] = rel ? col[(int64_t)D.vrow[p] * ld] : T(0);
   }
-  // L^-T: coordinates push to their ancestors; only the subtree and the ancestor chain of pj carry anything
+  // L^-T: coordinates push to their ancestors; only the subtree and the ancestor chain of pj carry anything.  The ancestors of
+  // one coordinate are distinct, so four read-modify-writes go out together (the compiler cannot know they do not alias).
   for (int i = hi - 1; i >= 0; i = (i > lo ? i - 1 : D.lambda[i])) {
     const T xi = x[i * xs];
     const int ri = D.rowstart[i];
     int d = D.depth[i] - 1;
-    for (int j = D.lambda[i]; j >= 0; j = D.lambda[j], --d) x[j * xs] -= H(ri + d) * xi;
+    for (; d >= 3; d -= 4) {
+      const int j0 = A.anc[ri + d], j1 = A.anc[ri + d - 1], j2 = A.anc[ri + d - 2], j3 = A.anc[ri + d - 3];
+      const T h0 = H(ri + d), h1 = H(ri + d - 1), h2 = H(ri + d - 2), h3 = H(ri + d - 3);
+      const T x0 = x[j0 * xs], x1 = x[j1 * xs], x2 = x[j2 * xs], x3 = x[j3 * xs];
+      x[j0 * xs] = x0 - h0 * xi; x[j1 * xs] = x1 - h1 * xi; x[j2 * xs] = x2 - h2 * xi; x[j3 * xs] = x3 - h3 * xi;
+    }
+    for (; d >= 0; --d) { const int j = A.anc[ri + d]; x[j * xs] -= H(ri + d) * xi; }
   }
   for (int p = 0; p < nv; ++p) x[p * xs] *= H(D.rowstart[p] + D.depth[p]);
   // L^-1: coordinates pull from their ancestors
   for (int i = 0; i < nv; ++i) {
     T acc = x[i * xs];
     const int ri = D.rowstart[i];
-    int d = D.depth[i] - 1;
-    for (int j = D.lambda[i]; j >= 0; j = D.lambda[j], --d) acc -= H(ri + d) * x[j * xs];
+    for (int d = D.depth[i] - 1; d >= 0; --d) acc -= H(ri + d) * x[A.anc[ri + d] * xs];
     x[i * xs] = acc;
     if (active) col[(int64_t)D.vrow[i] * ld] = -acc;
   }

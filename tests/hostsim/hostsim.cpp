@@ -112,8 +112,8 @@ template <class T> void run_crba(const HostModel& hm, int64_t B, const T* q, T* 
 template <class T>
 int run_derivatives(const HostModel& hm, int64_t B, const T* q, const T* v, const T* tau, T* vd, T* dq, T* dv) {
   const ModelDev<T>& M = dev<T>(hm);
-  DerivDev D;
-  if (!build_deriv_dev(M, D)) return RBD_EUNSUPPORTED;
+  DerivDev D; DerivAnc A;
+  if (!build_deriv_dev(M, D, A)) return RBD_EUNSUPPORTED;
   run_dynamics<T>(hm, B, q, v, tau, nullptr, vd, nullptr);
   std::vector<T> stash(kin_rows(hm) + 64), scr(D.rows), x(D.nv);
   for (int64_t b = 0; b < B; ++b) {
@@ -122,13 +122,13 @@ int run_derivatives(const HostModel& hm, int64_t B, const T* q, const T* v, cons
     io.s = scr.data(); io.sld = 1; io.active = true;
     deriv_world_sample<T>(M, D, io, Stash<T, 1>{stash.data()});
     for (int c = 0; c < kBodyRows; ++c) deriv_accumulate<T>(M, D, scr.data(), 1, c);
-    for (int K = 0; K < M.nb; ++K) deriv_pairs<T>(M, D, scr.data(), 1, dq + b, dv + b, B, K, true);
-    deriv_factor<T>(D, scr.data(), 1);
+    for (int K = 0; K < M.nb; ++K) deriv_pairs<T>(D, A, scr.data(), 1, dq + b, dv + b, B, K, true);
+    deriv_factor<T>(D, A, scr.data() + D.h_base, 1);
     const T* H = scr.data() + D.h_base;
     auto Hf = [H](int row) { return H[row]; };
     for (int c = 0; c < 2 * D.nv; ++c) {
       T* out = (c < D.nv ? dq : dv) + (int64_t)(c % D.nv) * D.nv * B + b;
-      deriv_solve_column<T>(D, Hf, x.data(), 1, out, B, c % D.nv, true);
+      deriv_solve_column<T>(D, A, Hf, x.data(), 1, out, B, c % D.nv, true);
     }
   }
   return 0;

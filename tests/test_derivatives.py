@@ -130,6 +130,21 @@ def test_derivatives_gpu_fp32_and_chunks(built, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_derivatives_gpu_factor_in_scratch_fallback(built, monkeypatch):
+    """Models whose mass matrix does not fit into shared memory next to the right-hand sides factor it on the scratch instead
+    (deriv_factor_kernel + deriv_solve_kernel<T, false>); forced here on a random tree with every joint type."""
+    torch = built
+    mech = randmech(4, shuffle=True)
+    o = Oracle(mech.flatten())
+    q, v, tau, _, _ = rand_inputs(mech, 70, 9)
+    idx = np.array([0, 31, 32, 69])
+    rq, rv = oracle_dynamics_derivatives(o, mech, q[:, idx], v[:, idx], tau[:, idx])
+    monkeypatch.setenv("RBD_DERIV_GLOBAL_FACTOR", "1")
+    _, gq, gv = _gpu_run(torch, mech, q, v, tau, torch.float64)
+    assert rel_err(gq[:, idx], rq) < TOL64 and rel_err(gv[:, idx], rv) < TOL64
+
+
+@pytest.mark.gpu
 def test_derivatives_gpu_consistent_with_dual_entry_point(built):
     """The analytic Jacobians contracted with six seed directions == the library's own Dual{Float64,6} sweep (config 4)."""
     torch = built
