@@ -245,6 +245,12 @@ int32_t rbd_dynamics_result(const rbd_model* model, int32_t dtype, int64_t B, in
 int32_t rbd_dynamics_derivatives(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const void* q, const void* v,
                                  const void* tau, void* vd_out, void* dvd_dq_out, void* dvd_dv_out, void* stream);
 
+/* The triangular solves of rbd_dynamics_derivatives also exist as a model-specialised kernel (every index a constant, right-hand
+ * sides in registers; generated and NVRTC-compiled like the kernels of rbd_model_precompile, same cubin cache).  It is used when
+ * its cubin is cached or the batch is at least RBD_JIT_MIN_BATCH (default 4096 for this entry point); RBD_DERIV_JIT=0 / RBD_JIT=0
+ * keep the generic table-driven kernel.  This call compiles it ahead of time (no GPU needed). */
+int32_t rbd_model_precompile_derivatives(rbd_model* model, int32_t dtype);
+
 /* dynamics_bias!(result, state) / dynamics_bias!(torques, biasaccelerations, wrenches, state, externalwrenches)
  *                                                             src/mechanism_algorithms.jl:484-498
  *   -> c_out [nv x B] = c(q, v, wext) = inverse_dynamics with v̇ = 0. */

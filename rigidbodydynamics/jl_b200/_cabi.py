@@ -112,6 +112,7 @@ SYMBOLS = {
     "rbd_contact_dynamics": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rbd_dynamics_result": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rbd_dynamics_derivatives": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rbd_model_precompile_derivatives": (c_int32, [_vp, _i32]),
     "rbd_dynamics_bias": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "rbd_mass_matrix": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "rbd_mass_matrix_uplo": (c_int32, [_vp, _i32, _i64, _i64, _vp, _vp, _i32, _vp]),
@@ -173,6 +174,10 @@ class ModelHandle:
         """rbd_model_precompile: generate + NVRTC-compile the model-specialised kernels into the cubin cache (no GPU needed
         unless ``load``)."""
         check(self._lib.rbd_model_precompile(self._h, int(dtype), int(what), 1 if load else 0))
+
+    def precompile_derivatives(self, dtype: int = RBD_F64):
+        """rbd_model_precompile_derivatives: the model-specialised solve kernel of rbd_dynamics_derivatives into the cubin cache."""
+        check(self._lib.rbd_model_precompile_derivatives(self._h, int(dtype)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -15,17 +15,23 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
 #include <mutex>
 #include <set>
 #include <string>
+#include <vector>
 
 #include "../../../include/rbd_b200.h"
 // rbd_sincos.cuh defines one out-of-line __device__ function with external linkage (its text is also compiled by NVRTC, where
 // `static` would be noise); this second translation unit of the library gets its own copy under another name
 #define sincos_slow sincos_slow_deriv_tu
 #include "rbd_deriv.cuh"
+#include "rbd_deriv_jit.h"
 #include "rbd_handle.h"
+#include "rbd_jit_text.h"
 
 using namespace rbd;
 
@@ -73,12 +79,14 @@ __global__ void __launch_bounds__(NT) deriv_accum_kernel(const __grid_constant__
   deriv_accumulate<T>(M, D, a.s + b, a.sld, blockIdx.y);
 }
 
+// grid = (bodies, sample groups), bodies fastest: the CTAs that are resident together work on the SAME samples, so the per-coordinate
+// rows a body shares with its relatives are served by L2 instead of being streamed from HBM once per body
 template <class T, int NT>
 __global__ void __launch_bounds__(NT) deriv_pairs_kernel(const __grid_constant__ DerivDev D, const __grid_constant__ DerivAnc A,
                                                          const DerivArgs<T> a) {
-  const int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x;
+  const int64_t b = (int64_t)blockIdx.y * NT + threadIdx.x;
   if (b >= a.C) return;
-  deriv_pairs<T>(D, A, a.s + b, a.sld, a.dq + b, a.dv + b, a.ld, blockIdx.y, true);
+  deriv_pairs<T>(D, A, a.s + b, a.sld, a.dq + b, a.dv + b, a.ld, blockIdx.x, true);
 }
 
 // only for models whose factor does not fit into shared memory next to the right-hand sides (deriv_solve_kernel<T, false>)
@@ -164,6 +172,78 @@ int big_smem_once(const void* kernel, const Props& p) {
 }
 #define LAUNCH_CHECK(name) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { rc = api_fail(RBD_ECUDA, std::string(name " launch failed: ") + cudaGetErrorString(e_)); goto done; } } while (0)
 
+// ---- model-specialised solve kernel (rbd_deriv_jit.cpp): compiled with NVRTC on the first large call (or ahead of time by
+// rbd_model_precompile_derivatives), cubin cached on disk, module cached per (tables, dtype, device) ----
+struct JitSolve {
+  int state = 0;                 // 1 = ready, -1 = unavailable (the generic kernel serves the call)
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kernel = nullptr;
+  DerivJitPlan plan;
+  size_t smem = 0;
+  int bps = 0;
+};
+std::mutex g_jit_mu;
+std::map<std::string, JitSolve> g_jit;
+
+bool jit_enabled() {
+  const char* e = std::getenv("RBD_JIT");
+  if (e && e[0] == '0') return false;
+  e = std::getenv("RBD_DERIV_JIT");
+  return !(e && e[0] == '0');
+}
+int64_t jit_min_batch() {
+  if (const char* e = std::getenv("RBD_JIT_MIN_BATCH")) return std::max<int64_t>(1, std::atoll(e));
+  return 4096;
+}
+// cubin for the model's solve kernel (from the cache, or compiled when `compile`); no GPU needed
+bool jit_solve_cubin(const DerivDev& D, const DerivAnc& A, bool f64, bool compile, DerivJitPlan& plan, std::vector<char>& cubin,
+                     std::string& err) {
+  if (D.nnz * 32 * (f64 ? 8 : 4) > 200 * 1024) { err = "factor does not fit into shared memory"; return false; }
+  if (!deriv_jit_plan(D, f64, plan)) { err = "too many velocity coordinates for a register-resident solve"; return false; }
+  std::string src;
+  deriv_jit_source(D, A, f64, plan, src);
+  if (const char* dump = std::getenv("RBD_DERIV_DUMP")) {           // inspection: nvcc -cubin -Xptxas -v on the dumped text
+    if (FILE* f = fopen((std::string(dump) + (f64 ? "_f64.cu" : "_f32.cu")).c_str(), "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+  }
+  bool from_cache = false;
+  return jit_compile_text(f64 ? "deriv_f64" : "deriv_f32", src, true, cubin, compile, &from_cache, err);
+}
+JitSolve* jit_solve_get(const DerivDev& D, const DerivAnc& A, bool f64, int64_t B, const Props& p) {
+  if (!jit_enabled()) return nullptr;
+  std::string key((const char*)&D, sizeof(D));
+  key.append((const char*)A.anc, sizeof(int16_t) * D.nnz);
+  key.push_back(f64 ? 'd' : 'f');
+  key.push_back((char)p.dev);
+  std::lock_guard<std::mutex> lk(g_jit_mu);
+  JitSolve& e = g_jit[key];
+  if (e.state == 1) return &e;
+  if (e.state == -1) return nullptr;
+  std::vector<char> cubin;
+  std::string err;
+  if (!jit_solve_cubin(D, A, f64, B >= jit_min_batch(), e.plan, cubin, err)) {
+    if (err != "no cached cubin") {
+      e.state = -1;
+      if (std::getenv("RBD_JIT_VERBOSE")) fprintf(stderr, "rbd_b200: derivative solve kernel not specialised: %s\n", err.c_str());
+    }
+    return nullptr;
+  }
+  e.smem = (size_t)D.nnz * 32 * (f64 ? 8 : 4);
+  cudaError_t ce = cudaLibraryLoadData(&e.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&e.kernel, e.lib, "rbd_deriv_solve");
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute((const void*)e.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute((const void*)e.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e.bps, (const void*)e.kernel, 32 * e.plan.warps, e.smem);
+  if (ce != cudaSuccess || e.bps < 1) {
+    cudaGetLastError();
+    if (std::getenv("RBD_JIT_VERBOSE")) fprintf(stderr, "rbd_b200: derivative solve kernel failed to load: %s\n", cudaGetErrorString(ce));
+    if (e.lib) { cudaLibraryUnload(e.lib); e.lib = nullptr; }
+    e.state = -1;
+    return nullptr;
+  }
+  e.state = 1;
+  return &e;
+}
+
 template <class T>
 int derivatives_t(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, const T* q, const T* v, const T* tau, T* vd_out, T* dq,
                   T* dv, cudaStream_t stream) {
@@ -203,6 +283,7 @@ int derivatives_t(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, 
     bestW = (int)std::min<int64_t>(std::min(8, 2 * D.nv), p.max_smem_optin / (int64_t)xbytes);
     bestNb = 1;
   }
+  JitSolve* js = hs ? jit_solve_get(D, A, sizeof(T) == 8, B, p) : nullptr;
   const size_t solve_smem = (hs ? hbytes : 0) + (size_t)bestW * xbytes;
   const size_t world_smem = (size_t)std::max(1, kin_rows(hm)) * kNT * sizeof(T);
   auto kworld = deriv_world_kernel<T, kNT>;
@@ -224,13 +305,26 @@ int derivatives_t(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, 
     deriv_accum_kernel<T, kNT><<<dim3(gx, kBodyRows), kNT, 0, stream>>>(M, D, a);
     LAUNCH_CHECK("deriv_accum_kernel");
     api_note_launch(gx * kBodyRows, kNT, 0, 0);
-    deriv_pairs_kernel<T, kNT><<<dim3(gx, D.nb), kNT, 0, stream>>>(D, A, a);
+    deriv_pairs_kernel<T, kNT><<<dim3(D.nb, gx), kNT, 0, stream>>>(D, A, a);
     LAUNCH_CHECK("deriv_pairs_kernel");
     api_note_launch(gx * D.nb, kNT, 0, 0);
     if (!hs) {
       deriv_factor_kernel<T, kNT><<<gx, kNT, 0, stream>>>(D, A, a);
       LAUNCH_CHECK("deriv_factor_kernel");
       api_note_launch(gx, kNT, 0, 0);
+    }
+    if (js) {
+      const T* Hg = scratch + (int64_t)D.h_base * sld;
+      long long sld_ = sld, ld_ = ld, c_ = c;
+      T* dq_ = dq + b0; T* dv_ = dv + b0;
+      void* params[] = {(void*)&Hg, (void*)&sld_, (void*)&dq_, (void*)&dv_, (void*)&ld_, (void*)&c_};
+      const int sgj = (int)std::min<int64_t>((c + 31) / 32, (int64_t)js->bps * p.sms);
+      if (cudaLaunchKernel((const void*)js->kernel, dim3(sgj), dim3(32 * js->plan.warps), params, js->smem, stream) != cudaSuccess) {
+        rc = api_fail(RBD_ECUDA, std::string("rbd_deriv_solve launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        goto done;
+      }
+      api_note_launch(sgj, 32 * js->plan.warps, (int)js->smem, js->bps);
+      continue;
     }
     const int sg = (int)std::min<int64_t>((c + 31) / 32, (int64_t)bestNb * p.sms);
     if (hs) ksolve_s<<<sg, dim3(32, bestW), solve_smem, stream>>>(D, A, a);
@@ -256,4 +350,19 @@ extern "C" int32_t rbd_dynamics_derivatives(const rbd_model* model, int32_t dtyp
                                                  (float*)dvd_dq_out, (float*)dvd_dv_out, s)
                           : derivatives_t<double>(model, dtype, B, ld, (const double*)q, (const double*)v, (const double*)tau,
                                                   (double*)vd_out, (double*)dvd_dq_out, (double*)dvd_dv_out, s);
+}
+
+// Ahead-of-time compilation of the model's solve kernel into the cubin cache (no GPU needed): the analogue of rbd_model_precompile
+// for this entry point.  RBD_EUNSUPPORTED if NVRTC is missing or the model does not qualify (the generic kernel then serves it).
+extern "C" int32_t rbd_model_precompile_derivatives(rbd_model* model, int32_t dtype) {
+  if (!model) return api_fail(RBD_EINVAL, "model handle is NULL");
+  if (dtype != RBD_F32 && dtype != RBD_F64) return api_fail(RBD_EINVAL, "rbd_model_precompile_derivatives: fp32 / fp64 only");
+  DerivDev D;
+  DerivAnc A;
+  if (!build_deriv_dev(model->hm.dev64, D, A)) return api_fail(RBD_EUNSUPPORTED, "model too large for rbd_dynamics_derivatives");
+  DerivJitPlan plan;
+  std::vector<char> cubin;
+  std::string err;
+  if (!jit_solve_cubin(D, A, dtype == RBD_F64, true, plan, cubin, err)) return api_fail(RBD_EUNSUPPORTED, err);
+  return RBD_OK;
 }

@@ -1,5 +1,6 @@
 // NVRTC front end + cubin cache for the model-specialised kernels (see rbd_jit.h).  Host-only C++.
 #include "rbd_jit.h"
+#include "rbd_jit_text.h"
 
 #include <dlfcn.h>
 #include <nvrtc.h>
@@ -107,19 +108,10 @@ std::string jit_cache_dir() {
   return "/tmp";
 }
 
-bool jit_get_cubin(const HostModel& hm, const SpecKey& key, std::vector<char>& cubin, bool compile_if_missing, bool* from_cache,
-                   SpecStats* stats, std::string& err) {
-  const std::string path = jit_cache_dir() + "/" + key_name(hm, key) + ".cubin";
-  if (from_cache) *from_cache = false;
-  if (!getenv("RBD_JIT_NO_CACHE") && read_file(path, cubin)) {
-    if (from_cache) *from_cache = true;
-    return true;
-  }
-  if (!compile_if_missing) { err = "no cached cubin"; return false; }
+// NVRTC for sm_100a on a complete source text; the embedded headers are offered to every program.
+static bool nvrtc_compile(const std::string& src, bool fmad, std::vector<char>& cubin, std::string& err) {
   Nvrtc& n = nvrtc();
   if (!n.h) { err = n.err; return false; }
-  std::string src;
-  if (!spec_emit_cuda_tu(hm, key, src, stats, err)) return false;
   const int nh = (int)(sizeof(kEmbeddedHeaders) / sizeof(kEmbeddedHeaders[0]));
   std::vector<const char*> hn, ht;
   for (int i = 0; i < nh; ++i) { hn.push_back(kEmbeddedHeaders[i].name); ht.push_back(kEmbeddedHeaders[i].text); }
@@ -127,7 +119,7 @@ bool jit_get_cubin(const HostModel& hm, const SpecKey& key, std::vector<char>& c
   nvrtcResult r = n.CreateProgram(&prog, src.c_str(), "rbd_spec.cu", nh, ht.data(), hn.data());
   if (r != NVRTC_SUCCESS) { err = std::string("nvrtcCreateProgram: ") + n.GetErrorString(r); return false; }
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=false"};
-  r = n.CompileProgram(prog, 4, opts);
+  r = n.CompileProgram(prog, fmad ? 3 : 4, opts);
   if (r != NVRTC_SUCCESS) {
     size_t ls = 0;
     n.GetProgramLogSize(prog, &ls);
@@ -143,6 +135,39 @@ bool jit_get_cubin(const HostModel& hm, const SpecKey& key, std::vector<char>& c
   if (r == NVRTC_SUCCESS && sz > 0) { cubin.resize(sz); r = n.GetCUBIN(prog, cubin.data()); }
   n.DestroyProgram(&prog);
   if (r != NVRTC_SUCCESS || sz == 0) { err = "nvrtcGetCUBIN failed"; return false; }
+  return true;
+}
+
+bool jit_get_cubin(const HostModel& hm, const SpecKey& key, std::vector<char>& cubin, bool compile_if_missing, bool* from_cache,
+                   SpecStats* stats, std::string& err) {
+  const std::string path = jit_cache_dir() + "/" + key_name(hm, key) + ".cubin";
+  if (from_cache) *from_cache = false;
+  if (!getenv("RBD_JIT_NO_CACHE") && read_file(path, cubin)) {
+    if (from_cache) *from_cache = true;
+    return true;
+  }
+  if (!compile_if_missing) { err = "no cached cubin"; return false; }
+  std::string src;
+  if (!spec_emit_cuda_tu(hm, key, src, stats, err)) return false;
+  if (!nvrtc_compile(src, false, cubin, err)) return false;
+  if (!getenv("RBD_JIT_NO_CACHE")) write_file_atomic(path, cubin.data(), cubin.size());
+  return true;
+}
+
+bool jit_compile_text(const std::string& tag, const std::string& src, bool fmad, std::vector<char>& cubin, bool compile_if_missing,
+                      bool* from_cache, std::string& err) {
+  unsigned long long h = 1469598103934665603ull;            // FNV-1a of the text: the cache key
+  for (unsigned char c : src) { h ^= c; h *= 1099511628211ull; }
+  char buf[64];
+  snprintf(buf, sizeof buf, "%016llx_%s", h, tag.c_str());
+  const std::string path = jit_cache_dir() + "/" + buf + ".cubin";
+  if (from_cache) *from_cache = false;
+  if (!getenv("RBD_JIT_NO_CACHE") && read_file(path, cubin)) {
+    if (from_cache) *from_cache = true;
+    return true;
+  }
+  if (!compile_if_missing) { err = "no cached cubin"; return false; }
+  if (!nvrtc_compile(src, fmad, cubin, err)) return false;
   if (!getenv("RBD_JIT_NO_CACHE")) write_file_atomic(path, cubin.data(), cubin.size());
   return true;
 }

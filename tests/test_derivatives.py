@@ -145,6 +145,28 @@ def test_derivatives_gpu_factor_in_scratch_fallback(built, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("jit", ["0", "1"])
+def test_derivatives_gpu_specialised_and_generic_solve_kernels(built, monkeypatch, jit):
+    """The triangular solves exist twice: the table-driven kernel and the model-specialised one (right-hand sides in registers,
+    NVRTC).  Both against the oracle, fp64 and fp32, on Atlas and on a random tree with every joint type (51 coordinates)."""
+    torch = built
+    from rigidbodydynamics.jl_b200 import _cabi
+    monkeypatch.setenv("RBD_DERIV_JIT", jit)
+    for mech in (rbd.load_model("atlas", floating=True), randmech(5, shuffle=True)):
+        o = Oracle(mech.flatten())
+        q, v, tau, _, _ = rand_inputs(mech, 97, 13)
+        idx = np.array([0, 31, 32, 96])
+        rq, rv = oracle_dynamics_derivatives(o, mech, q[:, idx], v[:, idx], tau[:, idx])
+        for dtype, code, tol in ((torch.float64, _cabi.RBD_F64, TOL64), (torch.float32, _cabi.RBD_F32, TOL32)):
+            if jit == "1":
+                st = rbd.MechanismState(mech, 1, dtype)
+                st.handle.precompile_derivatives(code)          # cached cubin => used at any batch size
+            _, gq, gv = _gpu_run(torch, mech, q, v, tau, dtype)
+            assert not np.isnan(gq).any() and not np.isnan(gv).any()
+            assert rel_err(gq[:, idx], rq) < tol and rel_err(gv[:, idx], rv) < tol, (jit, dtype, rel_err(gq[:, idx], rq), rel_err(gv[:, idx], rv))
+
+
+@pytest.mark.gpu
 def test_derivatives_gpu_consistent_with_dual_entry_point(built):
     """The analytic Jacobians contracted with six seed directions == the library's own Dual{Float64,6} sweep (config 4)."""
     torch = built
