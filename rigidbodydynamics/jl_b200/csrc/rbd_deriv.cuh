@@ -103,13 +103,20 @@ template <class T> RBD_HD void force_cross(const Mot<T>& v, const T* n, const T*
 template <class T> RBD_HD T dot6(const Mot<T>& S, const T* y) {
   return S.w[0] * y[0] + S.w[1] * y[1] + S.w[2] * y[2] + S.l[0] * y[3] + S.l[1] * y[4] + S.l[2] * y[5];
 }
+// rows row .. row + 5 of a scratch column; the address walks by ld (one 64-bit add per element instead of a multiply each)
 template <class T> RBD_HD void load_mot(const T* s, int64_t ld, int row, Mot<T>& m) {
+  const T* p = s + (int64_t)row * ld;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { m.w[k] = s[(int64_t)(row + k) * ld]; m.l[k] = s[(int64_t)(row + 3 + k) * ld]; }
+  for (int k = 0; k < 3; ++k) { m.w[k] = *p; p += ld; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { m.l[k] = *p; p += ld; }
 }
 template <class T> RBD_HD void store_mot(T* s, int64_t ld, int row, const Mot<T>& m) {
+  T* p = s + (int64_t)row * ld;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { s[(int64_t)(row + k) * ld] = m.w[k]; s[(int64_t)(row + 3 + k) * ld] = m.l[k]; }
+  for (int k = 0; k < 3; ++k) { *p = m.w[k]; p += ld; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { *p = m.l[k]; p += ld; }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -284,16 +291,18 @@ RBD_HD void deriv_pairs(const DerivDev& D, const DerivAnc& A, T* s, int64_t sld,
   Rbi<T> Ic;
   T G[36], Fn[3], Ff[3];
   {
-    const int row = D.body_base + kBodyRows * K;
-    Ic.m = s[(int64_t)row * sld];
+    const T* p = s + (int64_t)(D.body_base + kBodyRows * K) * sld;
+    Ic.m = *p; p += sld;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) Ic.h[k] = s[(int64_t)(row + 1 + k) * sld];
+    for (int k = 0; k < 3; ++k) { Ic.h[k] = *p; p += sld; }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) Ic.J[k] = s[(int64_t)(row + 4 + k) * sld];
+    for (int k = 0; k < 6; ++k) { Ic.J[k] = *p; p += sld; }
 #pragma unroll
-    for (int k = 0; k < 36; ++k) G[k] = s[(int64_t)(row + 10 + k) * sld];
+    for (int k = 0; k < 36; ++k) { G[k] = *p; p += sld; }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { Fn[k] = s[(int64_t)(row + 46 + k) * sld]; Ff[k] = s[(int64_t)(row + 49 + k) * sld]; }
+    for (int k = 0; k < 3; ++k) { Fn[k] = *p; p += sld; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Ff[k] = *p; p += sld; }
   }
   // all coordinates at or above K, deepest first: the ancestor list of K's last coordinate
   const int plast = pk0 + nk - 1, rl = D.rowstart[plast];
@@ -301,10 +310,17 @@ RBD_HD void deriv_pairs(const DerivDev& D, const DerivAnc& A, T* s, int64_t sld,
     const int pj = A.anc[rl + dj];
     const int rj = D.dof_base + kDofRows * pj;
     Mot<T> Sj, pd, pdd, sdp;
-    load_mot(s, sld, rj, Sj);
-    load_mot(s, sld, rj + 6, pd);
-    load_mot(s, sld, rj + 12, pdd);
-    load_mot(s, sld, rj + 18, sdp);
+    {
+      const T* p = s + (int64_t)rj * sld;
+      T t[24];
+#pragma unroll
+      for (int k = 0; k < 24; ++k) { t[k] = *p; p += sld; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        Sj.w[k] = t[k]; Sj.l[k] = t[3 + k]; pd.w[k] = t[6 + k]; pd.l[k] = t[9 + k];
+        pdd.w[k] = t[12 + k]; pdd.l[k] = t[15 + k]; sdp.w[k] = t[18 + k]; sdp.l[k] = t[21 + k];
+      }
+    }
     T yq[6], yv[6], ym[6];
     apply_IG(Ic, G, pdd, pd, yq);
     apply_IG(Ic, G, sdp, Sj, yv);
