@@ -321,4 +321,32 @@ RigidBodyDynamics.momentum_matrix!(A::AbstractMatrix, state::BatchedState) = (ki
 RigidBodyDynamics.geometric_jacobian!(J::AbstractMatrix, state::BatchedState, p::RigidBodyDynamics.TreePath) =
     (kinematics!(state; path = p, geometric_jacobian = J); J)
 
+# ---- SURVEY 8(f) rank 3: Jacobians of forward dynamics ----------------------------------------------------------------------
+
+"""
+    dynamics_derivatives!(dvd_dq, dvd_dv, result, state, torques = nothing)
+
+Analytic `∂v̇/∂q` (tangent space) and `∂v̇/∂v` of `dynamics!` for every sample in one call -- what
+`ForwardDiff.jacobian(x -> dynamics!(...), ...)` over the reference's generic path produces with 2 nv / 6 Dual sweeps per sample
+(examples/5. Derivatives and gradients using ForwardDiff, test/test_mechanism_algorithms.jl:600-675).  `dvd_dq`, `dvd_dv` are
+B x (nv*nv) device matrices, entry (i, j) of sample b at `[b, i + (j - 1) * nv]` (column-major like `M.data`);
+`dvd_dq[:, :, j]` is the derivative along `velocity_to_configuration_derivative(e_j)`, i.e. `(∂v̇/∂q) * velocity_to_configuration_derivative_jacobian(state)`.
+`result.v̇` receives v̇.  External wrenches: use the Dual path (`dynamics!` on `Dual` inputs).
+"""
+function dynamics_derivatives!(dvd_dq, dvd_dv, result::BatchedResult{T}, state::BatchedState{T}, torques = nothing) where {T <: Union{Float32, Float64}}
+    checkstate(state)
+    B = size(state.q, 1)
+    GC.@preserve state result torques dvd_dq dvd_dv begin
+        check(ccall((:rbd_dynamics_derivatives, librbd), Int32,
+                    (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                    state.model.handle, dtype_code(T), B, B, devptr(state.q), devptr(state.v),
+                    torques === nothing ? C_NULL : devptr(torques), devptr(result.v̇), devptr(dvd_dq), devptr(dvd_dv), stream_ptr()))
+    end
+    dvd_dq, dvd_dv
+end
+
+"Compile the model-specialised solve kernel of `dynamics_derivatives!` ahead of time (cubin cache; no GPU needed)."
+precompile_derivatives(model, ::Type{T}) where {T <: Union{Float32, Float64}} =
+    check(ccall((:rbd_model_precompile_derivatives, librbd), Int32, (Ptr{Cvoid}, Int32), model.handle, dtype_code(T)))
+
 end # module
