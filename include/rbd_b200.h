@@ -134,7 +134,7 @@ int32_t rbd_get_launch_info(rbd_launch_info* info);
 
 /*
  * Model-specialised kernels.  For a given handle the library can generate straight-line CUDA code for dynamics! /
- * inverse_dynamics! / dynamics_bias! of THAT mechanism (tree walk unrolled, joint classes resolved, model constants folded,
+ * inverse_dynamics! / dynamics_bias! / mass_matrix! of THAT mechanism (tree walk unrolled, joint classes resolved, model constants folded,
  * structural zeros removed), compile it with NVRTC for sm_100a and keep the cubin in a disk cache
  * ($RBD_JIT_CACHE, else <library dir>/jit_cache, else ~/.cache/rbd_b200).  This is the analogue of the reference compiling
  * its generic functions for a concrete MechanismState{X,M,C} on first call (Julia's JIT).
@@ -150,6 +150,8 @@ int32_t rbd_get_launch_info(rbd_launch_info* info);
 #define RBD_SPEC_INVERSE_DYNAMICS 8  /* inverse_dynamics!                                */
 #define RBD_SPEC_DYNAMICS_BIAS 16    /* dynamics_bias!                                   */
 #define RBD_SPEC_DYNAMICS_GATHER 32  /* rbd_dynamics_gather (stores to peer GPUs)        */
+#define RBD_SPEC_MASS_MATRIX 64      /* mass_matrix! (both triangles)                    */
+#define RBD_SPEC_MASS_MATRIX_LOWER 128 /* mass_matrix! (lower triangle, RBD_UPLO_LOWER)  */
 int32_t rbd_model_precompile(rbd_model* model, int32_t dtype, int32_t what, int32_t load);
 
 /*

@@ -17,6 +17,7 @@ RBD_OK, RBD_EINVAL, RBD_EDIM, RBD_ELOOP, RBD_ESTALE, RBD_ECUDA, RBD_EUNSUPPORTED
 RBD_F32, RBD_F64, RBD_DUAL64X6 = 0, 1, 2
 RBD_SPEC_DYNAMICS, RBD_SPEC_DYNAMICS_QDOT, RBD_SPEC_DYNAMICS_NOTAU, RBD_SPEC_INVERSE_DYNAMICS, RBD_SPEC_DYNAMICS_BIAS = 1, 2, 4, 8, 16
 RBD_SPEC_DYNAMICS_GATHER = 32
+RBD_SPEC_MASS_MATRIX, RBD_SPEC_MASS_MATRIX_LOWER = 64, 128
 RBD_SPEC_ALL = 63
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -355,10 +355,12 @@ template <class T> struct CrbaArgs {
   T* M;
   int64_t ld, B;
   bool lower;
+  const int* gate;       // non-NULL: run only if *gate != 0 (fallback behind the model-specialised kernel, see AbaArgs)
 };
 
 template <class T, int NT, int KMAX>
 __global__ void __launch_bounds__(NT, sizeof(T) == 4 ? (KMAX == 1 ? 28 : 20) : 1) crba_kernel(const __grid_constant__ ModelDev<T> M, const CrbaArgs<T> a) {
+  if (a.gate && *a.gate == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   const Stash<T, NT> st{sh + threadIdx.x};
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(NT, sizeof(T) == 4 ? (KMAX == 1 ? 28 : 20) : 1
     io.q = {a.q + bl, a.ld};
     io.M = {a.M + bl, a.ld, active};
     io.lower = a.lower;
-    crba_sample<T, NT, KMAX>(M, io, st);
+    crba_sample<T, Stash<T, NT>, KMAX>(M, io, st);
   }
 }
 
@@ -689,10 +691,30 @@ template <class T>
 int mass_matrix_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, void* Mout, cudaStream_t stream, bool lower = false) {
   const HostModel& hm = model->hm;
   const ModelDev<T>& M = dev_model<T>(hm);
-  CrbaArgs<T> a{(const T*)q, (T*)Mout, ld, B, lower};
+  CrbaArgs<T> a{(const T*)q, (T*)Mout, ld, B, lower, nullptr};
   const int rows = std::max(1, crba_rows(hm));
   bool multi = false;
   for (int i = 0; i < hm.nb; ++i) multi |= kind_nv(M.body[i].kind) > 1;
+  {      // model-specialised kernel: the composite-rigid-body algorithm traced on this mechanism (rbd_codegen.cpp)
+    SpecKey key; key.algo = SPEC_CRBA; key.f64 = sizeof(T) == 8; key.has_in2 = false; key.lower = lower;
+    const SpecLaunchArgs sa{q, nullptr, nullptr, Mout, nullptr, ld, B};
+    bool used = false;
+    std::string err;
+    const int* gate = nullptr;
+    if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, &gate, err)) return fail(rc, err);
+    if (used) {
+      g_launch.specialised = 1;
+      if (!gate) return RBD_OK;
+      const rbd_launch_info keep = g_launch;      // gated generic fallback, see dynamics_t
+      a.gate = gate;
+      const int rc = multi ? launch<T>(crba_kernel<T, kNT, 6>, M, a, kNT, rows, 0, stream)
+                           : launch<T>(crba_kernel<T, kNT, 1>, M, a, kNT, rows, 0, stream);
+      const int n = g_launch.kernels_launched;
+      g_launch = keep;
+      g_launch.kernels_launched = n;
+      return rc;
+    }
+  }
   return multi ? launch<T>(crba_kernel<T, kNT, 6>, M, a, kNT, rows, 0, stream)
                : launch<T>(crba_kernel<T, kNT, 1>, M, a, kNT, rows, 0, stream);
 }
@@ -1369,6 +1391,15 @@ int32_t rbd_model_precompile(rbd_model* model, int32_t dtype, int32_t what, int3
   if (what & RBD_SPEC_DYNAMICS_NOTAU) { one(SPEC_ABA, false, false); one(SPEC_ABA, false, true); }
   if (what & RBD_SPEC_INVERSE_DYNAMICS) one(SPEC_RNEA, true, false);
   if (what & RBD_SPEC_DYNAMICS_BIAS) one(SPEC_RNEA, false, false);
+  if (what & (RBD_SPEC_MASS_MATRIX | RBD_SPEC_MASS_MATRIX_LOWER)) {
+    for (int lower = 0; lower < 2; ++lower) {
+      if (!(what & (lower ? RBD_SPEC_MASS_MATRIX_LOWER : RBD_SPEC_MASS_MATRIX))) continue;
+      SpecKey key; key.algo = SPEC_CRBA; key.f64 = dtype == RBD_F64; key.has_in2 = false; key.lower = lower != 0;
+      std::string e;
+      const int rc = spec_prepare(model, key, load != 0, e);
+      if (rc != RBD_OK) { rc_all = rc; err = e; }
+    }
+  }
   if (what & RBD_SPEC_DYNAMICS_GATHER) {
     SpecKey key; key.algo = SPEC_ABA; key.f64 = dtype == RBD_F64; key.has_in2 = true; key.peers = true;
     std::string e;

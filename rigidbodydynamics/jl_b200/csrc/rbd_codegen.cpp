@@ -14,7 +14,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 14;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 15;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -53,6 +53,15 @@ bool run_trace(const HostModel& hm, const SpecKey& key, SymTrace& tr, int& stash
     io.ext = {false};
     rnea_sample<Sym>(*M, io, st);
     stash_rows = rnea_rows(hm);
+    return true;
+  }
+  if (key.algo == SPEC_CRBA) {
+    CrbaIO<Sym> io;
+    io.q = {A_Q, true};
+    io.M = {A_OUT0, true};
+    io.lower = key.lower;
+    crba_sample<Sym, SymStash, 6>(*M, io, st);      // KMAX 6 covers every joint kind; unused columns are never touched
+    stash_rows = crba_rows(hm);
     return true;
   }
   err = "spec: algorithm not specialisable";
@@ -318,7 +327,9 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
   return true;
 }
 
-int spec_stash_rows(const HostModel& hm, const SpecKey& key) { return key.algo == SPEC_ABA ? hm.dev64.nrows : rnea_rows(hm); }
+int spec_stash_rows(const HostModel& hm, const SpecKey& key) {
+  return key.algo == SPEC_ABA ? hm.dev64.nrows : (key.algo == SPEC_RNEA ? rnea_rows(hm) : std::max(1, crba_rows(hm)));
+}
 
 int spec_uni_smem_warps(const HostModel& hm, const SpecKey& key) {
   const int per_warp = std::max(1, spec_stash_rows(hm, key)) * 32 * (key.f64 ? 8 : 4);
@@ -362,7 +373,7 @@ bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, std::string& out
            "#define RBD_SPEC_HAS_IN2 %d\n#define RBD_SPEC_HAS_OUT1 %d\n#define RBD_SPEC_OUT0_ROWS %d\n#define RBD_SPEC_OUT1_ROWS %d\n"
            "#define RBD_UNI_SW %d\n#include \"rbd_jit_prelude.cuh\"\n",
            st.nodes_live, st.n_add, st.n_mul, st.n_div, st.n_sincos, st.n_load, st.n_sld, st.n_sst,
-           key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, hm.nv, hm.nq,
+           key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, key.algo == SPEC_CRBA ? hm.nv * hm.nv : hm.nv, hm.nq,
            std::max(4, spec_uni_smem_warps(hm, key)));
   out += buf;
   out += "#define RBD_FLAVOR_SMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_smem;

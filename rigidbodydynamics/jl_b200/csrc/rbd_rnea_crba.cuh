@@ -371,8 +371,9 @@ template <class T> RBD_HD void rbi_mul(const Rbi<T>& I, const Mot<T>& v, T* n, T
   f[2] = I.m * v.l[2] - (h[0] * v.w[1] - h[1] * v.w[0]);
 }
 
-template <class T, int STRIDE, int KMAX>
-RBD_HD void crba_sample(const ModelDev<T>& M, const CrbaIO<T>& io, const Stash<T, STRIDE>& st) {
+// ST: Stash<T, STRIDE> on the device / host tier, SymStash when the algorithm is traced for a model-specialised kernel (rbd_sym.h)
+template <class T, class ST, int KMAX>
+RBD_HD void crba_sample(const ModelDev<T>& M, const CrbaIO<T>& io, const ST& st) {
   const int nb = M.nb, nv = M.nv;
   const int slot_base = nb * kCrbaRowsPerBody;
   // pass 0: sin / cos (or prismatic displacement) of every 1-DoF joint

@@ -93,7 +93,7 @@ void spec_release(rbd_model* m) {
 // are therefore always specialised, fp64 programs only below an estimated size.
 bool spec_worthwhile(const HostModel& hm, const SpecKey& key) {
   if (!key.f64) return true;
-  const int est = hm.nb * (key.algo == SPEC_ABA ? 410 : 190);
+  const int est = hm.nb * (key.algo == SPEC_ABA ? 410 : (key.algo == SPEC_RNEA ? 190 : 600));
   return est <= 6500;
 }
 

@@ -104,8 +104,8 @@ template <class T> void run_crba(const HostModel& hm, int64_t B, const T* q, T* 
     io.q = {q + b, B};
     io.M = {Mout + b, B, true};
     io.lower = false;
-    if (multi) crba_sample<T, 1, 6>(M, io, Stash<T, 1>{stash.data()});
-    else crba_sample<T, 1, 1>(M, io, Stash<T, 1>{stash.data()});
+    if (multi) crba_sample<T, Stash<T, 1>, 6>(M, io, Stash<T, 1>{stash.data()});
+    else crba_sample<T, Stash<T, 1>, 1>(M, io, Stash<T, 1>{stash.data()});
   }
 }
 // dv̇/dq, dv̇/dv (csrc/rbd_deriv.cuh): the five phases run one sample at a time with a scratch of one column
@@ -184,7 +184,8 @@ extern "C" {
 char* hostsim_spec_source(const rbd_model_desc* d, int algo, int dtype, int has_in2, int has_out1, int flavor, int* stats) {
   HostModel hm; std::string err;
   if (build_host_model(d, hm, err) != RBD_OK) return nullptr;
-  SpecKey key; key.algo = algo; key.f64 = dtype == 1; key.has_in2 = has_in2 != 0; key.has_out1 = has_out1 != 0;
+  SpecKey key; key.algo = algo; key.f64 = dtype == 1; key.has_in2 = (has_in2 & 1) != 0; key.has_out1 = has_out1 != 0;
+  key.lower = (has_in2 & 2) != 0;      // CRBA: bit 1 of has_in2 selects the lower triangle
   SpecStats st; std::string out;
   bool ok;
   if (flavor == 0) ok = spec_emit_cpu_tu(hm, key, "rbd_spec_cpu", out, &st, err);

@@ -34,6 +34,29 @@ def test_specialised_program_matches_oracle_cpu(built, name, floating, dtype, to
     assert rel_err(hostsim.SpecProgram(desc, "rnea", dtype, False).run(q, v), o.dynamics_bias(q, v)) < tol
 
 
+def _mm_err(got, ref, nv, lower):
+    G = np.asarray(got, float).reshape(nv, nv, -1); R = np.asarray(ref, float).reshape(nv, nv, -1)     # [column, row, sample]
+    if not lower:
+        return np.abs(G - R).max() / max(1.0, np.abs(R).max())
+    keep = np.tril(np.ones((nv, nv), bool)).T           # row >= column  <->  [c, r] with r >= c
+    assert np.isnan(G[~keep]).all()                     # the strict upper triangle is left untouched (NaN-filled by the caller)
+    return np.abs(G[keep] - R[keep]).max() / max(1.0, np.abs(R).max())
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)])
+def test_specialised_mass_matrix_program_cpu(built, dtype, tol):
+    """mass_matrix! traced on the mechanism (both triangles / lower only, mechanism_algorithms.jl:248-272): Atlas, the 7-DoF arm and
+    random trees with every joint type against the oracle's composite-rigid-body algorithm."""
+    for mech in (rbd.load_model("atlas", floating=True), rbd.load_model("iiwa14"), randmech(3, shuffle=True), axis_aligned_tree(1)):
+        desc = mech.flatten()
+        q = rand_inputs(mech, 5, 6)[0]
+        ref = Oracle(desc).mass_matrix(q)
+        for lower in (0, 1):
+            prog = hostsim.SpecProgram(desc, "crba", dtype, has_in2=2 * lower, has_out1=False)
+            got = prog.run(q, np.zeros((desc.nv, 5)), None, out0_rows=desc.nv * desc.nv)
+            assert _mm_err(got, ref, desc.nv, lower) < tol
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_specialised_program_all_joint_types_cpu(built, seed):
     """The tracer resolves every joint kind / flag at generation time: random trees with all eight joint types and the
@@ -120,6 +143,32 @@ def test_specialised_kernels_match_oracle_gpu(built, name, floating, B):
     assert rel_err(out[:, :512].double().cpu().numpy(), o.inverse_dynamics(q[:, :512], v[:, :512], vd[:, :512])) < FP32_TOL
     rbd.dynamics_bias_(out, st)
     assert rel_err(out[:, :512].double().cpu().numpy(), o.dynamics_bias(q[:, :512], v[:, :512])) < FP32_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,floating,B", [("atlas", True, 40001), ("iiwa14", False, 1 << 15)])
+def test_specialised_mass_matrix_gpu(built, name, floating, B):
+    """mass_matrix! on the model-specialised kernel (batch above the compile threshold), both triangles and lower only, fp32 and
+    fp64 (the fp64 Atlas program is above the size limit and runs the generic kernel: same check), plus an angle beyond the fast
+    sin / cos range, which must come out of the gated generic kernel."""
+    import torch
+    mech = rbd.load_model(name, floating=floating)
+    o = Oracle(mech.flatten())
+    q = rand_inputs(mech, B, 3)[0]
+    q[-1, 7] = 3.0e4                     # exactly representable in fp32
+    idx = np.array([0, 7, 31, 32, B // 2, B - 1])
+    ref = o.mass_matrix(q[:, idx])
+    nv = mech.num_velocities()
+    for dtype, tol in ((torch.float32, 2e-5), (torch.float64, 1e-11)):
+        st = rbd.MechanismState(mech, B, dtype)
+        st.q.copy_(torch.from_numpy(q).to(dtype))
+        for uplo in ("F", "L"):
+            M = torch.full((nv * nv, B), float("nan"), dtype=dtype, device="cuda")
+            rbd.mass_matrix_(M, st, uplo="L" if uplo == "L" else "full")
+            torch.cuda.synchronize()
+            if dtype == torch.float32:
+                assert rbd.launch_info().specialised == 1
+            assert _mm_err(M[:, idx].double().cpu().numpy(), ref, nv, uplo == "L") < tol, (name, dtype, uplo)
 
 
 @pytest.mark.gpu
