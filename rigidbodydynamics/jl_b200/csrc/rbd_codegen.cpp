@@ -14,7 +14,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 15;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 20;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -371,10 +371,10 @@ bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, std::string& out
            "%d global loads, %d stash loads, %d stash stores)\n"
            "#define RBD_SPEC_F64 %d\n#define RBD_SPEC_NQ %d\n#define RBD_SPEC_NV %d\n#define RBD_SPEC_ROWS %d\n"
            "#define RBD_SPEC_HAS_IN2 %d\n#define RBD_SPEC_HAS_OUT1 %d\n#define RBD_SPEC_OUT0_ROWS %d\n#define RBD_SPEC_OUT1_ROWS %d\n"
-           "#define RBD_UNI_SW %d\n#include \"rbd_jit_prelude.cuh\"\n",
+           "#define RBD_UNI_SW %d\n#define RBD_SPEC_ROW32 %d\n#include \"rbd_jit_prelude.cuh\"\n",
            st.nodes_live, st.n_add, st.n_mul, st.n_div, st.n_sincos, st.n_load, st.n_sld, st.n_sst,
            key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, key.algo == SPEC_CRBA ? hm.nv * hm.nv : hm.nv, hm.nq,
-           std::max(4, spec_uni_smem_warps(hm, key)));
+           std::max(4, spec_uni_smem_warps(hm, key)), key.algo == SPEC_CRBA ? 1 : 0);
   out += buf;
   out += "#define RBD_FLAVOR_SMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_smem;
   out += "#undef RBD_FLAVOR_SMEM\n#define RBD_FLAVOR_TMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_tmem;

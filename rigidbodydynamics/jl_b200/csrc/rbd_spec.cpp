@@ -143,6 +143,7 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
   if (gate) *gate = nullptr;
   const Env& ev = env();
   if (!ev.jit || !spec_worthwhile(m->hm, key)) return RBD_OK;
+  if (a.ld * (key.f64 ? 8 : 4) >= (1ll << 32)) return RBD_OK;   // the generated code forms row offsets as 32 x 32 -> 64-bit products of the byte stride
   const int rows = spec_stash_rows(m->hm, key);
   if (rows > 256) return RBD_OK;                     // one warp's share of Tensor Memory: 256 fp32 rows (128 x 2 columns in fp64)
   Props p;
