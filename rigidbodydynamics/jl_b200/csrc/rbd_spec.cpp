@@ -93,7 +93,8 @@ void spec_release(rbd_model* m) {
 // are therefore always specialised, fp64 programs only below an estimated size.
 bool spec_worthwhile(const HostModel& hm, const SpecKey& key) {
   if (!key.f64) return true;
-  const int est = hm.nb * (key.algo == SPEC_ABA ? 410 : (key.algo == SPEC_RNEA ? 190 : 600));
+  if (key.algo == SPEC_CRBA) return !getenv("RBD_JIT_NO_CRBA64");   // small stash (2 rows per body): fp64 keeps its resident warps
+  const int est = hm.nb * (key.algo == SPEC_ABA ? 410 : 190);
   return est <= 6500;
 }
 
