@@ -203,6 +203,32 @@ def other_configs(steps):
     rbd.rand_(st18, rng)
     ms = time_fn(lambda: rbd.mass_matrix_(Mfull, st18), steps)
     out["atlas_f32_mass_matrix_b262144"] = {"evals_per_s": (1 << 18) / (ms * 1e-3), "ms": ms, "algorithmic_GBps": (1 << 18) * (37 + 1296) * 4 / (ms * 1e-3) / 1e9}
+    ms = time_fn(lambda: rbd.mass_matrix_(Mfull, st18, uplo="L"), steps)          # the triangle the reference's mass_matrix! fills
+    out["atlas_f32_mass_matrix_lower_b262144"] = {"evals_per_s": (1 << 18) / (ms * 1e-3), "ms": ms, "algorithmic_GBps": (1 << 18) * (37 + 666) * 4 / (ms * 1e-3) / 1e9}
+    st17 = rbd.MechanismState(atlas, 1 << 17, torch.float64)
+    rbd.rand_(st17, rng)
+    M64 = torch.empty((36 * 36, 1 << 17), dtype=torch.float64, device="cuda")
+    ms = time_fn(lambda: rbd.mass_matrix_(M64, st17), steps)
+    out["atlas_f64_mass_matrix_b131072"] = {"evals_per_s": (1 << 17) / (ms * 1e-3), "ms": ms, "algorithmic_GBps": (1 << 17) * (37 + 1296) * 8 / (ms * 1e-3) / 1e9}
+    del M64, st17
+    # contact_dynamics! -- one contact point per foot corner against the ground half-space (8 points), fp32
+    catlas = rbd.load_model("atlas", floating=True)
+    cmodel = rbd.SoftContactModel(rbd.hunt_crossley_hertz(), rbd.ViscoelasticCoulombModel(0.8, 20e3, 100.0))
+    for foot in ("l_foot", "r_foot"):
+        for x in (-0.08, 0.17):
+            for y in (-0.06, 0.06):
+                rbd.add_contact_point(catlas.findbody(foot), rbd.ContactPoint([x, y, -0.08], cmodel))
+    rbd.add_environment_primitive(catlas, rbd.HalfSpace3D([0.0, 0.0, 0.0], [0.0, 0.0, 1.0]))
+    cst = rbd.MechanismState(catlas, B, torch.float32)
+    cst.q.copy_(st.q); cst.v.copy_(st.v)
+    cw = torch.empty((6 * 31, B), dtype=torch.float32, device="cuda")
+    ns = rbd.num_contact_states(catlas)
+    cs = torch.zeros((ns, B), dtype=torch.float32, device="cuda")
+    csd = torch.empty_like(cs)
+    ms = time_fn(lambda: rbd.contact_dynamics_(cst, cw, cs, csd), steps)
+    out["atlas_f32_contact_dynamics_8points_b1048576"] = {"evals_per_s": B / (ms * 1e-3), "ms": ms,
+                                                          "algorithmic_GBps": B * (37 + 36 + 2 * ns + 6 * 31) * 4 / (ms * 1e-3) / 1e9}
+    del cst, cw, cs, csd
     del res, wext, tau, vd, tout, st, A, small, Mfull, st18
     # config 4: dynamics! on ForwardDiff.Dual{Tag,Float64,6} (value + 6 partials per scalar), batch 8192
     Bd = 8192
