@@ -384,11 +384,13 @@ template <class T> struct KinArgs {
   T* tr; T* com; T* ke; T* pe; T* mom; T* mrb; T* A; T* J;
   T* scratch;
   int64_t ld, B;
+  const int* gate;       // non-NULL: run only if *gate != 0 (fallback behind the model-specialised kernel, see AbaArgs)
 };
 
 template <class T, int NT>
 __global__ void __launch_bounds__(NT, sizeof(T) == 4 ? 28 : 12) kin_kernel(const __grid_constant__ ModelDev<T> M, const KinArgs<T> a,
                                                   const __grid_constant__ KinDev<T> K) {
+  if (a.gate && *a.gate == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sh = reinterpret_cast<T*>(smem_raw);
   const Stash<T, NT> st{sh + threadIdx.x};
@@ -735,9 +737,28 @@ int kinematics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, c
   K.inv_mass = (T)(1.0 / hm.total_mass);
   KinArgs<T> a{(const T*)q, (const T*)v, (T*)o.transforms_to_root, (T*)o.center_of_mass, (T*)o.kinetic_energy,
                (T*)o.gravitational_potential_energy, (T*)o.momentum, (T*)o.momentum_rate_bias, (T*)o.momentum_matrix,
-               (T*)o.geometric_jacobian, nullptr, ld, B};
+               (T*)o.geometric_jacobian, nullptr, ld, B, nullptr};
   DeviceProps p;
   if (int rc = get_props(p)) return rc;
+  if (!o.momentum_matrix) {      // model-specialised kernel for this output subset (and this jacobian path); the momentum matrix
+    SpecKey key;                 // needs the per-thread pose scratch and stays on the generic kernel
+    key.algo = SPEC_KIN; key.f64 = sizeof(T) == 8; key.has_in2 = v != nullptr;
+    void* const outs[8] = {o.transforms_to_root, o.center_of_mass, o.kinetic_energy, o.gravitational_potential_energy, o.momentum,
+                           o.momentum_rate_bias, o.momentum_matrix, o.geometric_jacobian};
+    SpecLaunchArgs sa{q, v, nullptr, nullptr, nullptr, ld, B};
+    for (int k = 0; k < 8; ++k) { if (outs[k]) key.kin_mask |= 1 << k; sa.ko[k] = outs[k]; }
+    for (int i = 0; i < hm.nb; ++i) key.kin_sign[i] = K.sign[i];
+    bool used = false;
+    std::string err;
+    const int* gate = nullptr;
+    if (key.kin_mask)
+      if (int rc = spec_try_launch(const_cast<rbd_model*>(model), key, sa, stream, used, g_launch, &gate, err)) return fail(rc, err);
+    if (used) {
+      g_launch.specialised = 1;
+      if (!gate) return RBD_OK;
+      a.gate = gate;               // gated generic fallback (angles beyond the fast sin / cos range), see dynamics_t
+    }
+  }
   auto kernel = kin_kernel<T, kNT>;
   const size_t smem = (size_t)std::max(1, kin_rows(hm)) * kNT * sizeof(T);
   int bps = 0;

@@ -10,11 +10,12 @@
 
 #include "rbd_rnea_crba.cuh"
 #include "rbd_sym.h"
+#include "rbd_kin.cuh"
 
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 20;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 21;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -62,6 +63,23 @@ bool run_trace(const HostModel& hm, const SpecKey& key, SymTrace& tr, int& stash
     io.lower = key.lower;
     crba_sample<Sym, SymStash, 6>(*M, io, st);      // KMAX 6 covers every joint kind; unused columns are never touched
     stash_rows = crba_rows(hm);
+    return true;
+  }
+  if (key.algo == SPEC_KIN) {
+    std::unique_ptr<KinDev<Sym>> K(new KinDev<Sym>());
+    for (int p = 0; p < hm.nb; ++p) {
+      for (int k = 0; k < 9; ++k) K->At[p][k] = Sym(hm.alignT[9 * p + k]);
+      K->sign[p] = key.kin_sign[p];
+    }
+    K->inv_mass = Sym(1.0 / hm.total_mass);
+    KinIO<Sym> io;
+    io.q = {A_Q, true}; io.v = {A_V, key.has_in2};
+    auto out = [&](int k) { return ColOut<Sym>{A_K0 + k, (key.kin_mask >> k & 1) != 0}; };
+    io.tr = out(0); io.com = out(1); io.ke = out(2); io.pe = out(3); io.mom = out(4); io.mrb = out(5); io.A = out(6); io.J = out(7);
+    io.poses = {false};
+    if (io.A.valid()) { err = "spec: the momentum matrix is not specialised"; return false; }
+    kin_sample<Sym, SymStash>(*M, *K, io, st);
+    stash_rows = std::max(1, kin_rows(hm));
     return true;
   }
   err = "spec: algorithm not specialisable";
@@ -143,6 +161,8 @@ struct Emitter {
       case A_WEXT: return "wext";
       case A_OUT0: return "o0";
       case A_OUT1: return "o1";
+      case A_K0: return "ko0"; case A_K1: return "ko1"; case A_K2: return "ko2"; case A_K3: return "ko3";
+      case A_K4: return "ko4"; case A_K5: return "ko5"; case A_K6: return "ko6"; case A_K7: return "ko7";
     }
     return "?";
   }
@@ -313,7 +333,7 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
   std::string sig;
   if (flavor == FLAVOR_CPU) {
     sig = std::string("extern \"C\" void ") + name + "(const " + F + "* q, const " + F + "* v, const " + F + "* in2, " + F + "* o0, " +
-          F + "* o1, long long ld, " + F + "* sh)";
+          F + "* o1, long long ld, " + F + "* sh" + (key.algo == SPEC_KIN ? std::string(", ") + F + "* const* ko)" : std::string(")"));
   } else {
     sig = std::string("__device__ __forceinline__ void ") + name + "(const rbd_f* __restrict__ q, const rbd_f* __restrict__ v, "
           "const rbd_f* __restrict__ in2, rbd_f* __restrict__ o0, rbd_f* __restrict__ o1, const long long ld, const bool active, "
@@ -321,6 +341,7 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
   }
   out += sig + " {\n";
   if (flavor != FLAVOR_CPU) out += "RBD_FN_BEGIN\n";
+  if (key.algo == SPEC_KIN) out += flavor == FLAVOR_CPU ? "RBD_KIN_BEGIN_CPU\n" : "RBD_KIN_BEGIN\n";
   out += em.out;
   if (flavor != FLAVOR_CPU) out += "RBD_FN_END\n";
   out += "}\n";
@@ -328,6 +349,7 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
 }
 
 int spec_stash_rows(const HostModel& hm, const SpecKey& key) {
+  if (key.algo == SPEC_KIN) return std::max(1, kin_rows(hm));
   return key.algo == SPEC_ABA ? hm.dev64.nrows : (key.algo == SPEC_RNEA ? rnea_rows(hm) : std::max(1, crba_rows(hm)));
 }
 
@@ -346,6 +368,7 @@ uint64_t spec_hash(const HostModel& hm, const SpecKey& key) {
   };
   const int hdr[9] = {kGeneratorVersion, key.algo, key.f64, key.has_in2, key.has_out1, key.lower, hm.nb, hm.general, key.peers};
   mix(hdr, sizeof hdr);
+  if (key.algo == SPEC_KIN) { mix(&key.kin_mask, sizeof key.kin_mask); mix(key.kin_sign, sizeof key.kin_sign); }
   if (key.f64) {
     const ModelDev<double>& M = hm.dev64;
     mix(&M, offsetof(ModelDev<double>, body) + sizeof(BodyDev<double>) * (size_t)M.nb);
@@ -371,10 +394,10 @@ bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, std::string& out
            "%d global loads, %d stash loads, %d stash stores)\n"
            "#define RBD_SPEC_F64 %d\n#define RBD_SPEC_NQ %d\n#define RBD_SPEC_NV %d\n#define RBD_SPEC_ROWS %d\n"
            "#define RBD_SPEC_HAS_IN2 %d\n#define RBD_SPEC_HAS_OUT1 %d\n#define RBD_SPEC_OUT0_ROWS %d\n#define RBD_SPEC_OUT1_ROWS %d\n"
-           "#define RBD_UNI_SW %d\n#define RBD_SPEC_ROW32 %d\n#include \"rbd_jit_prelude.cuh\"\n",
+           "#define RBD_UNI_SW %d\n#define RBD_SPEC_ROW32 %d\n#define RBD_SPEC_KIN %d\n#include \"rbd_jit_prelude.cuh\"\n",
            st.nodes_live, st.n_add, st.n_mul, st.n_div, st.n_sincos, st.n_load, st.n_sld, st.n_sst,
            key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, key.algo == SPEC_CRBA ? hm.nv * hm.nv : hm.nv, hm.nq,
-           std::max(4, spec_uni_smem_warps(hm, key)), key.algo == SPEC_CRBA ? 1 : 0);
+           std::max(4, spec_uni_smem_warps(hm, key)), key.algo == SPEC_CRBA ? 1 : 0, key.algo == SPEC_KIN ? 1 : 0);
   out += buf;
   out += "#define RBD_FLAVOR_SMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_smem;
   out += "#undef RBD_FLAVOR_SMEM\n#define RBD_FLAVOR_TMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_tmem;
@@ -391,6 +414,7 @@ bool spec_emit_cpu_tu(const HostModel& hm, const SpecKey& key, const std::string
          "#define RBD_SLD(r) sh[r]\n#define RBD_SST(r, x) sh[r] = (x)\n#define RBD_SFENCE()\n"
          "#define RBD_RCP(x) (1 / (x))\n#define RBD_DIV(a, b) ((a) / (b))\n#define RBD_SINCOS(x, s, c) rbd::sincos_t(x, s, c)\n"
          "#define RBD_K(x) (x)\n#define RBD_ADD(a, b) ((a) + (b))\n#define RBD_SUB(a, b) ((a) - (b))\n#define RBD_MUL(a, b) ((a) * (b))\n"
+         "#define RBD_KIN_BEGIN_CPU rbd_v *ko0 = ko[0], *ko1 = ko[1], *ko2 = ko[2], *ko3 = ko[3], *ko4 = ko[4], *ko5 = ko[5], *ko6 = ko[6], *ko7 = ko[7]; (void)ko0; (void)ko1; (void)ko2; (void)ko3; (void)ko4; (void)ko5; (void)ko6; (void)ko7;\n"
          "#define RBD_NEG(a) (-(a))\n#define RBD_FMA(a, b, c) std::fma(a, b, c)\n#define RBD_FMS(a, b, c) std::fma(a, b, -(c))\n"
          "#define RBD_FNMA(a, b, c) std::fma(-(a), b, c)\n";
   out += std::string("typedef ") + (key.f64 ? "double" : "float") + " rbd_v;\n";

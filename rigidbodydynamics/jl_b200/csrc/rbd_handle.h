@@ -24,6 +24,8 @@ struct SpecEntry {
   int rows = 0;
   bool from_cache = false;
   std::string why;               // reason for state -1
+  int8_t kin_sign[kMaxBodies] = {0};   // SPEC_KIN: the path this entry was generated for
+  bool kin_set = false;
 };
 
 constexpr int kCounterRing = 256;   // work-queue counters, one per call in flight
@@ -48,7 +50,7 @@ struct rbd_model {
   unsigned next_call = 0;
   // model-specialised kernels, keyed by SpecKey bits
   std::mutex spec_mu;
-  std::map<uint32_t, rbd::SpecEntry> spec;
+  std::map<uint64_t, rbd::SpecEntry> spec;
 };
 
 namespace rbd {
@@ -63,8 +65,14 @@ struct PairCtx {
 // Returns a cudaError_t (cudaSuccess = 0).
 cudaError_t pair_begin(rbd_model* m, cudaStream_t stream, PairCtx& ctx);
 
-inline uint32_t spec_key_bits(const SpecKey& k) {
-  return (uint32_t)k.algo | (k.f64 ? 8u : 0u) | (k.has_in2 ? 16u : 0u) | (k.has_out1 ? 32u : 0u) | (k.lower ? 64u : 0u) | (k.peers ? 128u : 0u);
+inline uint64_t spec_key_bits(const SpecKey& k) {
+  uint64_t b = (uint64_t)k.algo | (k.f64 ? 8u : 0u) | (k.has_in2 ? 16u : 0u) | (k.has_out1 ? 32u : 0u) | (k.lower ? 64u : 0u) | (k.peers ? 128u : 0u);
+  if (k.algo == SPEC_KIN) {      // output subset and jacobian path: 8 mask bits + a 40-bit hash of the path signs (the entry keeps the
+    uint64_t h = 1469598103934665603ull;   // signs themselves and is only used when they match, see spec_try_launch)
+    for (int i = 0; i < kMaxBodies; ++i) { h ^= (uint8_t)k.kin_sign[i]; h *= 1099511628211ull; }
+    b |= ((uint64_t)(k.kin_mask & 0xff) << 8) | ((h >> 24) << 24);
+  }
+  return b;
 }
 
 struct SpecLaunchArgs {
@@ -76,6 +84,7 @@ struct SpecLaunchArgs {
   void* mc = nullptr;            // NVLS multicast mapping of the peers' arrays, or NULL
   int npeers = 0;
   int64_t peer_ld = 0, peer_col0 = 0;
+  void* ko[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SPEC_KIN: the rbd_kinematics_out pointers
 };
 // Tries the model-specialised kernels for (model, key).  `used` = false (and RBD_OK) when they are unavailable, not yet
 // compiled and the batch is below the compile threshold, or the batch is too small: the caller then runs the generic kernels.

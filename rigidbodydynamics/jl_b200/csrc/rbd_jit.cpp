@@ -59,7 +59,7 @@ bool dir_writable(const std::string& d) {
 
 std::string key_name(const HostModel& hm, const SpecKey& k) {
   char buf[96];
-  const char* algo = k.algo == SPEC_ABA ? "aba" : (k.algo == SPEC_RNEA ? "rnea" : "crba");
+  const char* algo = k.algo == SPEC_ABA ? "aba" : (k.algo == SPEC_RNEA ? "rnea" : (k.algo == SPEC_CRBA ? "crba" : "kin"));
   snprintf(buf, sizeof buf, "%016llx_%s_%s_%d%d%d%s", (unsigned long long)spec_hash(hm, k), algo, k.f64 ? "f64" : "f32",
            (int)k.has_in2, (int)k.has_out1, (int)k.lower, k.peers ? "p" : "");
   return buf;

@@ -94,6 +94,7 @@ void spec_release(rbd_model* m) {
 bool spec_worthwhile(const HostModel& hm, const SpecKey& key) {
   if (!key.f64) return true;
   if (key.algo == SPEC_CRBA) return !getenv("RBD_JIT_NO_CRBA64");   // small stash (2 rows per body): fp64 keeps its resident warps
+  if (key.algo == SPEC_KIN) return true;                             // stash = the pending branch nodes only
   const int est = hm.nb * (key.algo == SPEC_ABA ? 410 : 190);
   return est <= 6500;
 }
@@ -157,6 +158,11 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
     std::lock_guard<std::mutex> lk(m->spec_mu);
     se = &m->spec[spec_key_bits(key)];
   }
+  if (key.algo == SPEC_KIN) {        // the 64-bit map key carries only a hash of the jacobian path: use the entry only for ITS path
+    std::lock_guard<std::mutex> lk(m->spec_mu);
+    if (!se->kin_set) { std::memcpy(se->kin_sign, key.kin_sign, sizeof se->kin_sign); se->kin_set = true; }
+    else if (std::memcmp(se->kin_sign, key.kin_sign, sizeof se->kin_sign) != 0) return RBD_OK;
+  }
   if (se->state == -1) return RBD_OK;
   if (se->state == 0) {
     if (a.B < ev.min_batch) {          // small call and nothing loaded yet: use a cached cubin if there is one, never compile
@@ -192,6 +198,7 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
   struct KArgs {
     const void* q; const void* v; const void* in2; void* o0; void* o1; long long ld, B; unsigned long long* counter; int* flag;
     void* peers[8]; long long peer_ld, peer_col0; void* mc; int npeers;
+    void* ko[8];
   };
   int launched = 0;
   int* last_flag = nullptr;
@@ -202,6 +209,7 @@ int spec_try_launch(rbd_model* m, const SpecKey& key, const SpecLaunchArgs& a, c
     KArgs ka = {a.q, a.v, a.in2, a.o0, a.o1, (long long)a.ld, (long long)a.B, ctx.counter, ctx.flag, {}, (long long)a.peer_ld,
                 (long long)a.peer_col0, a.mc, a.npeers};
     for (int i = 0; i < a.npeers && i < 8; ++i) ka.peers[i] = a.peers[i];
+    for (int i = 0; i < 8; ++i) ka.ko[i] = a.ko[i];
     void* params[] = {&ka};
     if (variant == 2) {
       e = cudaLaunchKernel((const void*)se->k_uni, dim3(p.sms), dim3(32 * uni_warps), params, smem * se->uni_sw, stream);

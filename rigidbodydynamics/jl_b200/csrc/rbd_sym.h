@@ -36,7 +36,9 @@ enum SymOp : int32_t {
 };
 
 // arrays a traced algorithm may touch (the code generator maps them to kernel arguments)
-enum SymArr : int32_t { A_Q = 0, A_V, A_TAU, A_VD_IN, A_WEXT, A_OUT0, A_OUT1, A_COUNT };
+enum SymArr : int32_t { A_Q = 0, A_V, A_TAU, A_VD_IN, A_WEXT, A_OUT0, A_OUT1,
+                        A_K0, A_K1, A_K2, A_K3, A_K4, A_K5, A_K6, A_K7,      // the eight outputs of rbd_kinematics, in rbd_kinematics_out order
+                        A_COUNT };
 
 struct SymNode {
   int32_t op;

@@ -172,13 +172,21 @@ def spec_source(desc, algo="aba", dtype=np.float64, has_in2=True, has_out1=False
     fn.restype = ctypes.c_void_p
     fn.argtypes = [ctypes.POINTER(RbdModelDesc)] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
     stats = (ctypes.c_int * 12)()
-    p = fn(ctypes.byref(d), {"aba": 0, "rnea": 1, "crba": 2}[algo], 0 if np.dtype(dtype) == np.float32 else 1, int(has_in2),
+    p = fn(ctypes.byref(d), {"aba": 0, "rnea": 1, "crba": 2, "kin": 3}[algo], 0 if np.dtype(dtype) == np.float32 else 1, int(has_in2),
            int(has_out1), flavor, stats)
     assert p, "specialisation failed"
     src = ctypes.string_at(p).decode()
     lib().hostsim_free.argtypes = [ctypes.c_void_p]
     lib().hostsim_free(p)
     return src, dict(zip(SPEC_STATS, stats))
+
+
+def spec_kin(mask, sign=None, nb=0):
+    """Select the rbd_kinematics variant the next spec_source / SpecProgram(algo="kin") call generates: bit k of ``mask`` = output k of
+    KIN_ROWS, ``sign`` = the geometric jacobian's path signs in reference joint order."""
+    sg = None if sign is None else np.ascontiguousarray(sign, np.int8)
+    lib().hostsim_spec_kin.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib().hostsim_spec_kin(int(mask), _p(sg), int(nb))
 
 
 class SpecProgram:
@@ -200,8 +208,21 @@ class SpecProgram:
                                    "-I", _CSRC, "-o", so + ".tmp", cpp])
             os.replace(so + ".tmp", so)
         self.fn = ctypes.CDLL(so).rbd_spec_cpu
-        self.fn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_longlong, ctypes.c_void_p]
+        self.fn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_longlong, ctypes.c_void_p] + ([ctypes.c_void_p] if algo == "kin" else [])
         self.has_in2, self.has_out1 = has_in2, has_out1
+
+    def run_kin(self, q, v, rows):
+        """rbd_kinematics variant: ``rows`` = list of 8 row counts (0 = output not requested); returns the list of outputs."""
+        dt = self.dtype
+        q = np.ascontiguousarray(q, dt); v = None if v is None else np.ascontiguousarray(v, dt)
+        B = q.shape[1]
+        outs = [np.full((r, B), np.nan, dt) if r else None for r in rows]
+        sh = np.zeros(self.stats["stash_rows"] + 8, dt)
+        es = dt.itemsize
+        for b in range(B):
+            ko = (ctypes.c_void_p * 8)(*[None if o is None else o.ctypes.data + b * es for o in outs])
+            self.fn(q.ctypes.data + b * es, None if v is None else v.ctypes.data + b * es, None, None, None, B, sh.ctypes.data, ko)
+        return outs
 
     def run(self, q, v, in2=None, out0_rows=None, out1_rows=None):
         dt = self.dtype

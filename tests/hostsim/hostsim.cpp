@@ -181,11 +181,22 @@ extern "C" {
 // Model-specialised program (csrc/rbd_codegen.cpp) for the mechanism: flavor 0 = self-contained C++ (one sample per call),
 // 1 / 2 = the per-sample CUDA function bodies, 3 = the whole NVRTC translation unit.  Returns a malloc'ed string (free with
 // hostsim_free) or NULL; stats = {nodes_traced, nodes_live, add, mul, div, neg, sincos, load, store, sld, sst, stash_rows}.
+// kin_mask / kin_sign (reference joint order, may be NULL): the rbd_kinematics variant (algo 3)
+static int g_kin_mask = 0;
+static int8_t g_kin_sign[rbd::kMaxBodies] = {0};
+void hostsim_spec_kin(int mask, const int8_t* sign, int nb) {
+  g_kin_mask = mask;
+  for (int i = 0; i < rbd::kMaxBodies; ++i) g_kin_sign[i] = (sign && i < nb) ? sign[i] : 0;
+}
 char* hostsim_spec_source(const rbd_model_desc* d, int algo, int dtype, int has_in2, int has_out1, int flavor, int* stats) {
   HostModel hm; std::string err;
   if (build_host_model(d, hm, err) != RBD_OK) return nullptr;
   SpecKey key; key.algo = algo; key.f64 = dtype == 1; key.has_in2 = (has_in2 & 1) != 0; key.has_out1 = has_out1 != 0;
   key.lower = (has_in2 & 2) != 0;      // CRBA: bit 1 of has_in2 selects the lower triangle
+  if (algo == SPEC_KIN) {
+    key.kin_mask = g_kin_mask;
+    for (int p = 0; p < hm.nb; ++p) key.kin_sign[p] = g_kin_sign[hm.order[p]];
+  }
   SpecStats st; std::string out;
   bool ok;
   if (flavor == 0) ok = spec_emit_cpu_tu(hm, key, "rbd_spec_cpu", out, &st, err);

@@ -57,6 +57,28 @@ def test_specialised_mass_matrix_program_cpu(built, dtype, tol):
             assert _mm_err(got, ref, desc.nv, lower) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 3e-5)])
+def test_specialised_kinematics_programs_cpu(built, dtype, tol):
+    """rbd_kinematics traced per mechanism, output subset and jacobian path (everything but the momentum matrix): all outputs at
+    once, and the two subsets bench.py times, against the oracle."""
+    KR = hostsim.KIN_ROWS
+    for mech in (rbd.load_model("atlas", floating=True), randmech(2, shuffle=True), axis_aligned_tree(4)):
+        desc = mech.flatten()
+        o = Oracle(desc)
+        q, v, _, _, _ = rand_inputs(mech, 4, 9)
+        sign = np.random.default_rng(1).integers(-1, 2, desc.nb).astype(np.int8)
+        ref = o.kinematics(q, v, sign)
+        full = {"transforms": 12 * desc.nb, "com": 3, "ke": 1, "pe": 1, "momentum": 6, "mrb": 6, "A": 0, "J": 6 * desc.nv}
+        for sub, with_v in ((tuple(k for k in KR if full[k]), True), (("J",), False), (("com", "ke", "pe", "momentum", "mrb"), True),
+                            (("transforms", "com", "pe"), False)):
+            rows = [full[k] if k in sub else 0 for k in KR]
+            hostsim.spec_kin(sum(1 << k for k, r in enumerate(rows) if r), sign, desc.nb)
+            outs = hostsim.SpecProgram(desc, "kin", dtype, has_in2=1 if with_v else 0, has_out1=False).run_kin(q, v if with_v else None, rows)
+            for k, name in enumerate(KR):
+                if rows[k]:
+                    assert rel_err(outs[k], ref[name]) < tol, (name, sub)
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_specialised_program_all_joint_types_cpu(built, seed):
     """The tracer resolves every joint kind / flag at generation time: random trees with all eight joint types and the
@@ -169,6 +191,41 @@ def test_specialised_mass_matrix_gpu(built, name, floating, B):
             if dtype == torch.float32:
                 assert rbd.launch_info().specialised == 1
             assert _mm_err(M[:, idx].double().cpu().numpy(), ref, nv, uplo == "L") < tol, (name, dtype, uplo)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [40001])
+def test_specialised_kinematics_gpu(built, B):
+    """rbd_kinematics on the model-specialised kernels (batch above the compile threshold): output subsets with and without a
+    jacobian path, two different paths through the same handle, fp32 and fp64, one angle beyond the fast sin / cos range; the
+    momentum matrix keeps the generic kernel."""
+    import torch
+    mech = rbd.load_model("atlas", floating=True)
+    o = Oracle(mech.flatten())
+    q, v, _, _, _ = rand_inputs(mech, B, 6)
+    q[-1, 11] = 2.0e4
+    idx = np.array([0, 11, 31, 32, B // 3, B - 1])
+    p1 = rbd.path(mech, mech.findbody("r_foot"), mech.findbody("l_hand"))
+    p2 = rbd.path(mech, mech.findbody("l_foot"), mech.findbody("head"))
+    nb, nv = len(mech.joints), mech.num_velocities()
+    for dtype, tol in ((torch.float32, 3e-5), (torch.float64, 1e-9)):
+        st = rbd.MechanismState(mech, B, dtype)
+        st.q.copy_(torch.from_numpy(q).to(dtype)); st.v.copy_(torch.from_numpy(v).to(dtype))
+        for pth, names in ((p1, ("geometric_jacobian",)), (p2, ("geometric_jacobian", "center_of_mass")),
+                           (None, ("center_of_mass", "kinetic_energy", "gravitational_potential_energy", "momentum", "momentum_rate_bias")),
+                           (p1, ("transforms_to_root", "geometric_jacobian", "momentum")), (None, ("momentum_matrix", "center_of_mass"))):
+            rows = {"transforms_to_root": 12 * nb, "center_of_mass": 3, "kinetic_energy": 1, "gravitational_potential_energy": 1,
+                    "momentum": 6, "momentum_rate_bias": 6, "momentum_matrix": 6 * nv, "geometric_jacobian": 6 * nv}
+            outs = {k: torch.full((rows[k], B), float("nan"), dtype=dtype, device="cuda") for k in names}
+            rbd.kinematics_(st, pth, **outs)
+            torch.cuda.synchronize()
+            assert rbd.launch_info().specialised == (0 if "momentum_matrix" in names else 1), names
+            sign = None if pth is None else pth.sign
+            ref = o.kinematics(q[:, idx], v[:, idx], sign)
+            short = {"transforms_to_root": "transforms", "center_of_mass": "com", "kinetic_energy": "ke", "gravitational_potential_energy": "pe",
+                     "momentum": "momentum", "momentum_rate_bias": "mrb", "momentum_matrix": "A", "geometric_jacobian": "J"}
+            for k in names:
+                assert rel_err(outs[k][:, idx].double().cpu().numpy(), ref[short[k]]) < tol, (dtype, k, names)
 
 
 @pytest.mark.gpu
