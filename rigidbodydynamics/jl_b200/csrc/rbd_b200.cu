@@ -740,8 +740,8 @@ int kinematics_t(const rbd_model* model, int64_t B, int64_t ld, const void* q, c
                (T*)o.geometric_jacobian, nullptr, ld, B, nullptr};
   DeviceProps p;
   if (int rc = get_props(p)) return rc;
-  if (!o.momentum_matrix) {      // model-specialised kernel for this output subset (and this jacobian path); the momentum matrix
-    SpecKey key;                 // needs the per-thread pose scratch and stays on the generic kernel
+  {                              // model-specialised kernel for this output subset (and this jacobian path)
+    SpecKey key;
     key.algo = SPEC_KIN; key.f64 = sizeof(T) == 8; key.has_in2 = v != nullptr;
     void* const outs[8] = {o.transforms_to_root, o.center_of_mass, o.kinetic_energy, o.gravitational_potential_energy, o.momentum,
                            o.momentum_rate_bias, o.momentum_matrix, o.geometric_jacobian};

@@ -15,7 +15,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 21;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 22;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -76,8 +76,8 @@ bool run_trace(const HostModel& hm, const SpecKey& key, SymTrace& tr, int& stash
     io.q = {A_Q, true}; io.v = {A_V, key.has_in2};
     auto out = [&](int k) { return ColOut<Sym>{A_K0 + k, (key.kin_mask >> k & 1) != 0}; };
     io.tr = out(0); io.com = out(1); io.ke = out(2); io.pe = out(3); io.mom = out(4); io.mrb = out(5); io.A = out(6); io.J = out(7);
-    io.poses = {false};
-    if (io.A.valid()) { err = "spec: the momentum matrix is not specialised"; return false; }
+    std::vector<int32_t> poses;            // the momentum matrix' return sweep re-uses the traced poses themselves (Scr<Sym>::fwd)
+    io.poses = {io.A.valid(), &poses};
     kin_sample<Sym, SymStash>(*M, *K, io, st);
     stash_rows = std::max(1, kin_rows(hm));
     return true;

@@ -16,8 +16,7 @@ struct SpecKey {
   bool has_out1 = false; // ABA: q̇ output requested
   bool lower = false;    // CRBA: lower triangle only
   bool peers = false;    // ABA: v̇ is stored into every peer GPU's gathered array (rbd_dynamics_gather) instead of o0
-  // KIN (rbd_kinematics): bit k of kin_mask = output k of rbd_kinematics_out requested (the momentum matrix, bit 6, is not
-  // specialised: it needs a per-thread scratch); has_in2 = v given; kin_sign = the geometric jacobian's path, PREORDER positions
+  // KIN (rbd_kinematics): bit k of kin_mask = output k of rbd_kinematics_out requested; has_in2 = v given; kin_sign = the geometric jacobian's path, PREORDER positions
   int kin_mask = 0;
   int8_t kin_sign[kMaxBodies] = {0};
 };

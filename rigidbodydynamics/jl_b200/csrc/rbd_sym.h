@@ -197,10 +197,17 @@ template <> struct ColOut<Sym> {
   void st(int row, const Sym& v) const { if (present) sym_trace()->store(arr, row, v.id); }
   bool valid() const { return present; }
 };
+// Per-thread scratch.  With `fwd` the rows are not memory at all: a value written in one sweep is simply the SAME traced value when
+// it is read back in the next (the compiler keeps it in a register or spills it to local memory, which is per-thread and
+// coalesced like the generic kernels' scratch column).
 template <> struct Scr<Sym> {
   bool present;
-  Sym get(int row) const { return mk(sym_trace()->xld(row)); }
-  void st(int row, const Sym& v) const { sym_trace()->xst(row, v.id); }
+  std::vector<int32_t>* fwd = nullptr;
+  Sym get(int row) const { return fwd ? mk((*fwd)[row]) : mk(sym_trace()->xld(row)); }
+  void st(int row, const Sym& v) const {
+    if (fwd) { if ((int)fwd->size() <= row) fwd->resize(row + 1, -1); (*fwd)[row] = v.id; }
+    else sym_trace()->xst(row, v.id);
+  }
   bool valid() const { return present; }
 };
 struct SymStash {

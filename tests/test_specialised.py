@@ -59,8 +59,8 @@ def test_specialised_mass_matrix_program_cpu(built, dtype, tol):
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 3e-5)])
 def test_specialised_kinematics_programs_cpu(built, dtype, tol):
-    """rbd_kinematics traced per mechanism, output subset and jacobian path (everything but the momentum matrix): all outputs at
-    once, and the two subsets bench.py times, against the oracle."""
+    """rbd_kinematics traced per mechanism, output subset and jacobian path: all outputs at once, and the subsets bench.py times,
+    against the oracle."""
     KR = hostsim.KIN_ROWS
     for mech in (rbd.load_model("atlas", floating=True), randmech(2, shuffle=True), axis_aligned_tree(4)):
         desc = mech.flatten()
@@ -68,9 +68,9 @@ def test_specialised_kinematics_programs_cpu(built, dtype, tol):
         q, v, _, _, _ = rand_inputs(mech, 4, 9)
         sign = np.random.default_rng(1).integers(-1, 2, desc.nb).astype(np.int8)
         ref = o.kinematics(q, v, sign)
-        full = {"transforms": 12 * desc.nb, "com": 3, "ke": 1, "pe": 1, "momentum": 6, "mrb": 6, "A": 0, "J": 6 * desc.nv}
-        for sub, with_v in ((tuple(k for k in KR if full[k]), True), (("J",), False), (("com", "ke", "pe", "momentum", "mrb"), True),
-                            (("transforms", "com", "pe"), False)):
+        full = {"transforms": 12 * desc.nb, "com": 3, "ke": 1, "pe": 1, "momentum": 6, "mrb": 6, "A": 6 * desc.nv, "J": 6 * desc.nv}
+        for sub, with_v in ((tuple(KR), True), (("J",), False), (("com", "ke", "pe", "momentum", "mrb"), True),
+                            (("transforms", "com", "pe"), False), (("A",), False)):
             rows = [full[k] if k in sub else 0 for k in KR]
             hostsim.spec_kin(sum(1 << k for k, r in enumerate(rows) if r), sign, desc.nb)
             outs = hostsim.SpecProgram(desc, "kin", dtype, has_in2=1 if with_v else 0, has_out1=False).run_kin(q, v if with_v else None, rows)
@@ -197,8 +197,7 @@ def test_specialised_mass_matrix_gpu(built, name, floating, B):
 @pytest.mark.parametrize("B", [40001])
 def test_specialised_kinematics_gpu(built, B):
     """rbd_kinematics on the model-specialised kernels (batch above the compile threshold): output subsets with and without a
-    jacobian path, two different paths through the same handle, fp32 and fp64, one angle beyond the fast sin / cos range; the
-    momentum matrix keeps the generic kernel."""
+    jacobian path, two different paths through the same handle, fp32 and fp64, one angle beyond the fast sin / cos range."""
     import torch
     mech = rbd.load_model("atlas", floating=True)
     o = Oracle(mech.flatten())
@@ -219,7 +218,7 @@ def test_specialised_kinematics_gpu(built, B):
             outs = {k: torch.full((rows[k], B), float("nan"), dtype=dtype, device="cuda") for k in names}
             rbd.kinematics_(st, pth, **outs)
             torch.cuda.synchronize()
-            assert rbd.launch_info().specialised == (0 if "momentum_matrix" in names else 1), names
+            assert rbd.launch_info().specialised == 1, names
             sign = None if pth is None else pth.sign
             ref = o.kinematics(q[:, idx], v[:, idx], sign)
             short = {"transforms_to_root": "transforms", "center_of_mass": "com", "kinetic_energy": "ke", "gravitational_potential_energy": "pe",
