@@ -249,8 +249,12 @@ function inverse_dynamics_bodies!(jointwrenchesout, accelerations, state::Batche
     nothing
 end
 
-"Generate + NVRTC-compile the model-specialised kernels ahead of the first large call (`rbd_model_precompile`; `what` = RBD_SPEC_* bits)."
-precompile_kernels(model::Model, ::Type{T} = Float32; what::Integer = 31, load::Bool = true) where {T} =
+"""
+Generate + NVRTC-compile the model-specialised kernels ahead of the first large call (`rbd_model_precompile`).  `what` = OR of the
+RBD_SPEC_* bits of include/rbd_b200.h: 1 dynamics!, 2 ... with q̇, 4 zero-torque variants, 8 inverse_dynamics!, 16 dynamics_bias!,
+32 multi-GPU gather, 64 mass_matrix! (both triangles), 128 mass_matrix! (lower triangle).
+"""
+precompile_kernels(model::Model, ::Type{T} = Float32; what::Integer = 31 | 64 | 128, load::Bool = true) where {T} =
     check(ccall((:rbd_model_precompile, librbd), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), model.handle, dtype_code(T), Int32(what), Int32(load)))
 
 
