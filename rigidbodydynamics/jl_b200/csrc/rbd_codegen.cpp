@@ -15,7 +15,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 22;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 23;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -76,6 +76,12 @@ bool run_trace(const HostModel& hm, const SpecKey& key, SymTrace& tr, int& stash
     io.q = {A_Q, true}; io.v = {A_V, key.has_in2};
     auto out = [&](int k) { return ColOut<Sym>{A_K0 + k, (key.kin_mask >> k & 1) != 0}; };
     io.tr = out(0); io.com = out(1); io.ke = out(2); io.pe = out(3); io.mom = out(4); io.mrb = out(5); io.A = out(6); io.J = out(7);
+    if (key.kin_mask == (1 << 6) && 6 * hm.nv + kSlotRowsMomMat * hm.nslots <= 256) {
+      // the momentum matrix on its own: the two body-frame sweeps (nothing but the result columns crosses them)
+      momentum_matrix_sample<Sym, SymStash>(*M, io.q, io.A, st);
+      stash_rows = spec_stash_rows(hm, key);
+      return true;
+    }
     std::vector<int32_t> poses;            // the momentum matrix' return sweep re-uses the traced poses themselves (Scr<Sym>::fwd)
     io.poses = {io.A.valid(), &poses};
     kin_sample<Sym, SymStash>(*M, *K, io, st);
@@ -349,7 +355,10 @@ bool spec_emit_function(const HostModel& hm, const SpecKey& key, int flavor, con
 }
 
 int spec_stash_rows(const HostModel& hm, const SpecKey& key) {
-  if (key.algo == SPEC_KIN) return std::max(1, kin_rows(hm));
+  if (key.algo == SPEC_KIN) {
+    const int two_sweep = 6 * hm.nv + kSlotRowsMomMat * hm.nslots;
+    return (key.kin_mask == (1 << 6) && two_sweep <= 256) ? two_sweep : std::max(1, kin_rows(hm));
+  }
   return key.algo == SPEC_ABA ? hm.dev64.nrows : (key.algo == SPEC_RNEA ? rnea_rows(hm) : std::max(1, crba_rows(hm)));
 }
 

@@ -295,6 +295,130 @@ RBD_HD void kin_sample(const ModelDev<T>& M, const KinDev<T>& K, const KinIO<T>&
 }
 
 // ==================================================================================================================
+// momentum_matrix! alone, in two BODY-FRAME sweeps (mechanism_algorithms.jl:313-327: A[:, k] = Ic_{body(k)} S_k).  kin_sample
+// keeps every body's root-frame pose from its outward sweep for the return sweep (12 nb scalars per sample: a global scratch
+// column in the generic kernel, spills in the traced one).  Here nothing but the result columns crosses the sweeps:
+//   inward   composite inertias in body frames exactly like mass_matrix! (carry in registers, pending slots for branch nodes),
+//            F_k = Ic e_k (one-hot subspaces) parked in the stash, 6 rows per velocity coordinate;
+//   outward  root-frame pose carried in registers (pending slots for branch nodes), each parked column transformed to the root
+//            frame (f = R f_b, n = R n_b + p x f) and written.
+// Stash: 6 nv rows + 12 per pending slot.  Used by the model-specialised kernels when that fits one warp's stash.
+// ==================================================================================================================
+constexpr int kSlotRowsMomMat = 12;
+template <class T, class ST>
+RBD_HD void momentum_matrix_sample(const ModelDev<T>& M, const Col<T>& q, const ColOut<T>& A, const ST& st) {
+  const int nb = M.nb;
+  const int slot_base = 6 * M.nv;
+  Rbi<T> carry;
+  carry.m = T(0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) carry.h[k] = T(0);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) carry.J[k] = T(0);
+  for (int i = nb - 1; i >= 0; --i) {
+    const BodyDev<T>& bd = M.body[i];
+    Rbi<T> ic;
+    body_rbi(bd, ic);
+    if (!(bd.flags & F_LEAF)) {
+      ic.m += carry.m;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ic.h[k] += carry.h[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ic.J[k] += carry.J[k];
+    }
+    if (bd.flags & F_HAS_PENDING) {
+      const int row = slot_base + bd.oslot * kSlotRowsMomMat;
+      st.fence_st();
+      ic.m += st.ld(row);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ic.h[k] += st.ld(row + 1 + k);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ic.J[k] += st.ld(row + 4 + k);
+    }
+    const int nvj = kind_nv_dev(bd.kind);
+    for (int k = 0; k < nvj; ++k) {
+      const int c = sub_comp(bd.kind, k);
+      Mot<T> e;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { e.w[d] = (c == d) ? T(1) : T(0); e.l[d] = (c == 3 + d) ? T(1) : T(0); }
+      T n[3], f[3];
+      rbi_mul(ic, e, n, f);
+      const int row = 6 * (bd.vrow + k);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { st.st(row + d, n[d]); st.st(row + 3 + d, f[d]); }
+    }
+    if (bd.flags & F_ROOT_CHILD) continue;
+    T R[9], r[3];
+    frame_any(bd, q, R, r);
+    Rbi<T> up;
+    rbi_to_parent(R, r, ic, up);
+    if (bd.flags & F_FIRST_CHILD) carry = up;
+    else {
+      const int row = slot_base + bd.pslot * kSlotRowsMomMat;
+      if (bd.flags & F_SLOT_INIT) {
+        st.st(row, up.m);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st.st(row + 1 + k, up.h[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st.st(row + 4 + k, up.J[k]);
+      } else {
+        st.add(row, up.m);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st.add(row + 1 + k, up.h[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st.add(row + 4 + k, up.J[k]);
+      }
+    }
+  }
+  st.fence_st();
+  Pose<T> cur;
+  pose_identity(cur);
+  for (int i = 0; i < nb; ++i) {
+    const BodyDev<T>& bd = M.body[i];
+    Pose<T> pp;
+    if (bd.flags & F_ROOT_CHILD) pose_identity(pp);
+    else if (bd.flags & F_FIRST_CHILD) pp = cur;
+    else {
+      const int row = slot_base + bd.pslot * kSlotRowsMomMat;
+      T t[12];
+      st.fence_st();
+      st.template ldv<12>(row, t);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) pp.R[k] = t[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pp.p[k] = t[9 + k];
+    }
+    T R[9], r[3], t3[3];
+    frame_any(bd, q, R, r);
+    Pose<T> w;
+    mat_mul3(pp.R, R, w.R);
+    mat_vec(pp.R, r, t3);
+    w.p[0] = pp.p[0] + t3[0]; w.p[1] = pp.p[1] + t3[1]; w.p[2] = pp.p[2] + t3[2];
+    const int nvj = kind_nv_dev(bd.kind);
+    for (int k = 0; k < nvj; ++k) {
+      const int row = 6 * (bd.vrow + k);
+      T c6[6], n[3], f[3], nw[3], fw[3], x[3];
+      st.template ldv<6>(row, c6);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { n[d] = c6[d]; f[d] = c6[3 + d]; }
+      mat_vec(w.R, f, fw);
+      mat_vec(w.R, n, nw);
+      cross3(w.p, fw, x);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { A.st(row + d, nw[d] + x[d]); A.st(row + 3 + d, fw[d]); }
+    }
+    if (bd.flags & F_HAS_PENDING) {
+      const int row = slot_base + bd.oslot * kSlotRowsMomMat;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) st.st(row + k, w.R[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) st.st(row + 9 + k, w.p[k]);
+    }
+    cur = w;
+  }
+}
+
+// ==================================================================================================================
 // Per-body outputs of inverse_dynamics!: the `accelerations` and `jointwrenchesout` arguments of
 //   inverse_dynamics!(torquesout, jointwrenchesout, accelerations, state, v̇, externalwrenches)   mechanism_algorithms.jl:542-553
 // in the reference's own terms -- ROOT-frame quantities per body:

@@ -212,7 +212,8 @@ def test_specialised_kinematics_gpu(built, B):
         st.q.copy_(torch.from_numpy(q).to(dtype)); st.v.copy_(torch.from_numpy(v).to(dtype))
         for pth, names in ((p1, ("geometric_jacobian",)), (p2, ("geometric_jacobian", "center_of_mass")),
                            (None, ("center_of_mass", "kinetic_energy", "gravitational_potential_energy", "momentum", "momentum_rate_bias")),
-                           (p1, ("transforms_to_root", "geometric_jacobian", "momentum")), (None, ("momentum_matrix", "center_of_mass"))):
+                           (p1, ("transforms_to_root", "geometric_jacobian", "momentum")), (None, ("momentum_matrix", "center_of_mass")),
+                           (None, ("momentum_matrix",))):      # alone: the two-sweep body-frame program
             rows = {"transforms_to_root": 12 * nb, "center_of_mass": 3, "kinetic_energy": 1, "gravitational_potential_energy": 1,
                     "momentum": 6, "momentum_rate_bias": 6, "momentum_matrix": 6 * nv, "geometric_jacobian": 6 * nv}
             outs = {k: torch.full((rows[k], B), float("nan"), dtype=dtype, device="cuda") for k in names}
