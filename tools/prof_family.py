@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Runs ONE entry point twice (first call warms up / loads the module, the second is the one ncu captures with `-s 1 -c 1` on the
 kernel-name regex).  usage: prof_family.py <what> [log2 batch]
-  what: aba_f32 | aba_f64 | id_f32 | bias_f32 | crba_f32 | crba_lower_f32 | kin_A | kin_small | dual | rk4 | bodies | aba_ext | iiwa_id | iiwa_crba"""
+  what: aba_f32 | aba_f64 | id_f32 | bias_f32 | crba_f32 | crba_lower_f32 | kin_A | kin_J | kin_small | dual | rk4 | bodies | aba_ext | iiwa_id | iiwa_crba"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -36,6 +36,8 @@ def call():
         rbd.mass_matrix_(call.M, st, uplo="L")
     elif what == "kin_A":
         rbd.momentum_matrix_(call.A, st)
+    elif what == "kin_J":
+        rbd.geometric_jacobian_(call.A, st, call.pth)
     elif what == "kin_small":
         rbd.kinematics_(st, None, **call.small)
     elif what == "dual":
@@ -50,8 +52,9 @@ def call():
 
 if what.startswith("crba") or what == "iiwa_crba":
     call.M = torch.empty((nv * nv, B), dtype=dt, device="cuda")
-if what == "kin_A":
+if what in ("kin_A", "kin_J"):
     call.A = torch.empty((6 * nv, B), dtype=dt, device="cuda")
+    call.pth = rbd.path(mech, mech.findbody("r_foot"), mech.findbody("l_hand"))
 if what == "kin_small":
     call.small = {k: torch.empty((r, B), dtype=dt, device="cuda") for k, r in
                   (("center_of_mass", 3), ("kinetic_energy", 1), ("gravitational_potential_energy", 1), ("momentum", 6), ("momentum_rate_bias", 6))}
