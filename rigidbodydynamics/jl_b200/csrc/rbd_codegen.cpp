@@ -15,7 +15,7 @@
 namespace rbd {
 namespace {
 
-constexpr int kGeneratorVersion = 23;   // bump when the emitted code changes (part of the cubin cache key)
+constexpr int kGeneratorVersion = 24;   // bump when the emitted code changes (part of the cubin cache key)
 
 template <class F> const ModelDev<F>& devm(const HostModel& m);
 template <> const ModelDev<float>& devm<float>(const HostModel& m) { return m.dev32; }
@@ -223,6 +223,7 @@ struct Emitter {
         case S_COS: break;
         case S_LOAD:
           ++stats.n_load;
+          if (n.arr == A_V) ++stats.n_load_v;
           snprintf(line, sizeof line, "const rbd_v t%zu = RBD_LDG(%s, %d);\n", i, arr_name(n.arr), n.row);
           out += line;
           break;
@@ -403,10 +404,10 @@ bool spec_emit_cuda_tu(const HostModel& hm, const SpecKey& key, std::string& out
            "%d global loads, %d stash loads, %d stash stores)\n"
            "#define RBD_SPEC_F64 %d\n#define RBD_SPEC_NQ %d\n#define RBD_SPEC_NV %d\n#define RBD_SPEC_ROWS %d\n"
            "#define RBD_SPEC_HAS_IN2 %d\n#define RBD_SPEC_HAS_OUT1 %d\n#define RBD_SPEC_OUT0_ROWS %d\n#define RBD_SPEC_OUT1_ROWS %d\n"
-           "#define RBD_UNI_SW %d\n#define RBD_SPEC_ROW32 %d\n#define RBD_SPEC_KIN %d\n#include \"rbd_jit_prelude.cuh\"\n",
+           "#define RBD_UNI_SW %d\n#define RBD_SPEC_ROW32 %d\n#define RBD_SPEC_KIN %d\n#define RBD_SPEC_USES_V %d\n#include \"rbd_jit_prelude.cuh\"\n",
            st.nodes_live, st.n_add, st.n_mul, st.n_div, st.n_sincos, st.n_load, st.n_sld, st.n_sst,
            key.f64 ? 1 : 0, hm.nq, hm.nv, rows, key.has_in2 ? 1 : 0, key.has_out1 ? 1 : 0, key.algo == SPEC_CRBA ? hm.nv * hm.nv : hm.nv, hm.nq,
-           std::max(4, spec_uni_smem_warps(hm, key)), key.algo == SPEC_CRBA ? 1 : 0, key.algo == SPEC_KIN ? 1 : 0);
+           std::max(4, spec_uni_smem_warps(hm, key)), key.algo == SPEC_CRBA ? 1 : 0, key.algo == SPEC_KIN ? 1 : 0, st.n_load_v > 0 ? 1 : 0);
   out += buf;
   out += "#define RBD_FLAVOR_SMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_smem;
   out += "#undef RBD_FLAVOR_SMEM\n#define RBD_FLAVOR_TMEM 1\n#include \"rbd_jit_flavor.cuh\"\n" + fn_tmem;

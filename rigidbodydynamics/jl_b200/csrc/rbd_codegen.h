@@ -25,6 +25,7 @@ struct SpecStats {
   int nodes_traced = 0, nodes_live = 0;
   int n_add = 0, n_mul = 0, n_div = 0, n_neg = 0, n_sincos = 0, n_load = 0, n_store = 0, n_sld = 0, n_sst = 0;
   int stash_rows = 0;
+  int n_load_v = 0;      // global loads of the v array (0: the kernel shell does not prefetch it)
 };
 
 enum SpecFlavor : int { FLAVOR_CPU = 0, FLAVOR_SMEM = 1, FLAVOR_TMEM = 2, FLAVOR_UNI = 3 };   // UNI emits like TMEM (batched loads)

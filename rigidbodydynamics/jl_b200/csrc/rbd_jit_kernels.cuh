@@ -18,7 +18,7 @@
     if (gn < ngroups) {                                                                             \
       const long long bn = gn * 32;                                                                 \
       rbd_prefetch_rows(a.q, RBD_SPEC_NQ, a.ld, bn);                                                \
-      rbd_prefetch_rows(a.v, RBD_SPEC_NV, a.ld, bn);                                                \
+      if (RBD_SPEC_USES_V) rbd_prefetch_rows(a.v, RBD_SPEC_NV, a.ld, bn);   /* not when the program never reads v */ \
       if (RBD_SPEC_HAS_IN2) rbd_prefetch_rows(a.in2, RBD_SPEC_NV, a.ld, bn);                        \
     }                                                                                               \
     const long long b = g * 32 + lane;                                                              \
