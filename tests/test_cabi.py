@@ -95,3 +95,28 @@ def test_kinematics_and_integrate_argument_checks(built):
     assert b"path_sign" in lib.rbd_last_error()
     assert lib.rbd_integrate(None, 0, 1, 1, dummy, dummy, None, 1e-3, 1, None) == _cabi.RBD_EINVAL
     assert lib.rbd_integrate(h.ptr, 0, 4, 2, dummy, dummy, None, 1e-3, 1, None) == _cabi.RBD_EDIM
+
+
+def test_derivative_and_precompile_entry_points_without_a_gpu(built):
+    """Host-side behaviour of the round-2 entry points that needs no device: argument checks of rbd_dynamics_derivatives (empty batch,
+    NULL pointers, Dual dtype, size mismatch) and ahead-of-time compilation of the model-specialised kernels for the derivative solve
+    and for mass_matrix! (NVRTC runs without a GPU; skipped when NVRTC is not installed)."""
+    lib = rbd.load_library()
+    h = _cabi.ModelHandle(rbd.load_model("iiwa14").flatten())
+    fake = ctypes.c_void_p(64)
+    args = lambda dtype, B, ld, q: (h.ptr, dtype, B, ld, q, fake, None, fake, fake, fake, None)     # noqa: E731
+    assert lib.rbd_dynamics_derivatives(*args(_cabi.RBD_F64, 0, 0, None)) == _cabi.RBD_OK          # empty batch: nothing touched
+    assert lib.rbd_dynamics_derivatives(*args(_cabi.RBD_F64, 4, 4, None)) == _cabi.RBD_EINVAL      # q NULL
+    assert lib.rbd_dynamics_derivatives(*args(_cabi.RBD_DUAL64X6, 4, 4, fake)) == _cabi.RBD_EUNSUPPORTED
+    assert lib.rbd_dynamics_derivatives(*args(_cabi.RBD_F32, 8, 4, fake)) == _cabi.RBD_EDIM        # ld < B
+    assert lib.rbd_dynamics_derivatives(None, _cabi.RBD_F32, 4, 4, fake, fake, None, fake, fake, fake, None) == _cabi.RBD_EINVAL
+    assert lib.rbd_model_precompile_derivatives(None, _cabi.RBD_F64) == _cabi.RBD_EINVAL
+    assert lib.rbd_model_precompile_derivatives(h.ptr, _cabi.RBD_DUAL64X6) == _cabi.RBD_EINVAL
+    rc = lib.rbd_model_precompile_derivatives(h.ptr, _cabi.RBD_F64)
+    if rc == _cabi.RBD_EUNSUPPORTED and b"NVRTC" in lib.rbd_last_error():
+        pytest.skip("NVRTC not available")
+    assert rc == _cabi.RBD_OK, lib.rbd_last_error()
+    assert lib.rbd_model_precompile_derivatives(h.ptr, _cabi.RBD_F32) == _cabi.RBD_OK
+    h.precompile(_cabi.RBD_F32, _cabi.RBD_SPEC_MASS_MATRIX | _cabi.RBD_SPEC_MASS_MATRIX_LOWER, load=False)
+    h.precompile(_cabi.RBD_F64, _cabi.RBD_SPEC_MASS_MATRIX, load=False)
+    h.close()
