@@ -253,6 +253,7 @@ int derivatives_t(const rbd_model* model, int32_t dtype, int64_t B, int64_t ld, 
   DerivAnc A;
   if (!build_deriv_dev(M, D, A))
     return api_fail(RBD_EUNSUPPORTED, "rbd_dynamics_derivatives: more than 128 velocity coordinates or 4096 mass-matrix entries");
+  if (D.nv == 0) return RBD_OK;        // nothing to differentiate (only fixed joints): no outputs have any rows
   Props p;
   if (int rc = get_props(p)) return rc;
   // chunk size from the scratch budget

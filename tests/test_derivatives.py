@@ -70,6 +70,34 @@ def test_derivatives_hostsim_fp32():
     assert rel_err(gq, rq) < TOL32 and rel_err(gv, rv) < TOL32, (rel_err(gq, rq), rel_err(gv, rv))
 
 
+def test_specialised_solve_kernel_compiles_without_a_gpu(tmp_path, monkeypatch):
+    """The generator of the model-specialised solve kernel (csrc/rbd_deriv_jit.cpp) on mechanisms of different shapes -- 51
+    coordinates with every joint type (one fp64 column per thread), Valkyrie, a serial chain -- through NVRTC (no GPU needed); the
+    cubins land in the cache directory."""
+    from rigidbodydynamics.jl_b200 import _cabi
+    monkeypatch.setenv("RBD_JIT_CACHE", str(tmp_path))
+    rng = np.random.default_rng(0)
+    for mech in (randmech(6, shuffle=True), rbd.load_model("valkyrie", floating=True), rbd.rand_chain_mechanism(rng, [rbd.Revolute] * 30)):
+        h = _cabi.ModelHandle(mech.flatten())
+        for code in (_cabi.RBD_F64, _cabi.RBD_F32):
+            try:
+                h.precompile_derivatives(code)
+            except _cabi.RbdError as e:
+                if "NVRTC" in str(e):
+                    pytest.skip("NVRTC not available")
+                raise
+        h.close()
+    assert len([f for f in os.listdir(tmp_path) if "deriv" in f]) == 6
+    # a 40-joint serial chain has 820 stored mass-matrix entries: in fp64 that does not fit into shared memory next to nothing
+    # else -> RBD_EUNSUPPORTED, and rbd_dynamics_derivatives serves the model with the table-driven kernels
+    h = _cabi.ModelHandle(rbd.rand_chain_mechanism(rng, [rbd.Revolute] * 40).flatten())
+    with pytest.raises(_cabi.RbdError) as e:
+        h.precompile_derivatives(_cabi.RBD_F64)
+    assert e.value.status == _cabi.RBD_EUNSUPPORTED
+    h.precompile_derivatives(_cabi.RBD_F32)
+    h.close()
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def built():
