@@ -629,6 +629,20 @@ def main():
                                  "HBM: the model-specialised program is ~12.4 k warp-instructions per 32 samples (generic: 27.5 k) but "
                                  "streams from L2 at ~1.4 instr/clk/SM (ncu: no_instruction stalls dominate, profiles/r2_jit_aba_*)"},
         }
+        # The roofline that actually bounds this kernel: warp-instruction ISSUE (4 schedulers x 1 instruction/clk per SM).  The executed
+        # instruction count per 32 samples is ncu's smsp__inst_executed of the specialised program (profiles/r2_jit_aba_*: 12.4 k; the
+        # generic kernel pair: 27.5 k, profiles/r1_aba_f32_fast_smem_kernel_2p20_summary.txt) -- a constant of the program, not measured
+        # in this run; the clock is the one sampled under load above.
+        try:
+            if args.dtype == "f32" and clocks and clocks.get("sm_mhz"):
+                wi = 12.4e3 if linfo.specialised else 27.5e3
+                ipc_peak = 148 * 4 * float(clocks["sm_mhz"]) * 1e6
+                issued = value / world / 32.0 * wi
+                out["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": issued / 1e9, "peak": ipc_peak / 1e9,
+                                         "unit": "G warp-instr/s", "frac": issued / ipc_peak, "warp_instr_per_32_samples": wi,
+                                         "evals_per_s_at_peak_issue": ipc_peak / wi * 32.0}
+        except Exception:      # a descriptor, never a reason to lose the bench line
+            pass
         if config5:
             out["with_nccl_gather"] = config5["with_nccl_gather"]
             out["strong_scaling"] = config5["strong_scaling"]
